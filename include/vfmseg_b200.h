@@ -1,0 +1,195 @@
+/*
+ * vfmseg_b200 — C ABI of the B200-native (sm_100a) slide-inference hot path.
+ *
+ * The reference (tpy001/VFMSeg) is pure Python and has no FFI of its own; what a maintainer binds
+ * instead are the torch module calls on its hot path. Every entry point below names the
+ * reference call it replaces (paths relative to the reference repo). See INTEGRATION.md for the
+ * ctypes stub a `rein` maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the parameter says "host"; the caller owns every
+ *     buffer; nothing here allocates device memory or synchronises the stream;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - activations are token-major: row = (crop, token), channels contiguous;
+ *   - bf16 buffers are `void*`, 16-byte aligned, leading dimensions multiples of 8 elements;
+ *   - return value: 0 = ok, < 0 = error (message in vfm_last_error(), thread-local).
+ */
+#ifndef VFMSEG_B200_H_
+#define VFMSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFM_ABI_VERSION 1
+
+enum {
+  VFM_OK = 0,
+  VFM_ERR_INVALID = -1,   /* bad shape / alignment / null pointer */
+  VFM_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed  */
+  VFM_ERR_WORKSPACE = -3, /* workspace too small                  */
+  VFM_ERR_DEVICE = -4     /* current device is not sm_100         */
+};
+
+const char* vfm_last_error(void);
+int vfm_abi_version(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+long long vfm_launch_count(void);
+/* 0 when the current CUDA device can run this library (compute capability 10.x). */
+int vfm_device_check(void);
+
+/* ---------------------------------------------------------------- dense operators (tcgen05)
+ * All GEMMs compute acc[M,N] = A[M,K] * W[N,K]^T with bf16 operands and fp32 accumulation in
+ * TMEM; W is exactly the nn.Linear / 1x1-conv weight layout. They differ in the fused epilogue. */
+
+/* out = bf16(acc + bias).  bias may be NULL.
+ * Replaces nn.Linear qkv (+ merged peft LoRA) rein/models/backbones/dino_layers/attention.py:51,58
+ * and the bias-free 1x1 fusion conv rein/models/heads/linear_head.py:36-40. */
+int vfm_gemm_bias_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out,
+                       int ldo, int M, int N, int K, void* stream);
+
+/* out = bf16(gelu_erf(acc + bias)).  Replaces Mlp.fc1 + nn.GELU, dino_layers/mlp.py:35-36. */
+int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, const float* bias,
+                            void* out, int ldo, int M, int N, int K, void* stream);
+
+/* x[M,N] (fp32, in place) += gamma * (acc + bias); when tap != NULL also stores bf16(x) into
+ * tap[(row - crop - 1), tap_col0 + col] for every non-cls row (crop = row / tokens_per_crop).
+ * Replaces attn.proj / mlp.fc2 + LayerScale + residual add, dino_layers/block.py:112-113,
+ * layer_scale.py:27, and the feature tap dino_v2.py:261-267. */
+int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, const float* bias,
+                              const float* gamma, float* x, int ldx, void* tap, int tap_ld,
+                              int tap_col0, int tokens_per_crop, int M, int N, int K, void* stream);
+
+/* x[crop*(patches+1) + 1 + p, :] = acc + bias + pos[1 + p, :] for GEMM row = crop*patches + p.
+ * Replaces PatchEmbed.proj (conv k=s=16) + pos-embed add, patch_embed.py:75-77, dino_v2.py:219-226. */
+int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias,
+                         const float* pos, float* x, int patches, int M, int N, int K, void* stream);
+
+/* ConvTranspose2d(k=2,s=2) (+ folded eval BatchNorm) + GELU as GEMM + pixel shuffle.
+ * W is [4*c_out, K] with row (dy*2+dx)*c_out + co; in rows = crop*h*w + y*w + x; out is
+ * token-major [n*4hw, c_out]. Replaces linear_head.py:42-48. */
+int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const float* bias,
+                           void* out, int c_out, int h, int w, int M, int K, void* stream);
+
+/* conv_seg: out[crop, cls, pix] (fp32 NCHW) = acc + bias[cls]; W is [32, K] zero-padded past
+ * num_classes (<= 32). Replaces mmseg BaseDecodeHead.cls_seg as used at linear_head.py:68. */
+int vfm_gemm_cls_nchw(const void* A, int lda, const void* W, int ldw, const float* bias, float* out,
+                      int num_classes, int pix_per_crop, int M, int K, void* stream);
+
+/* out(fp32) = acc (+ bias): plain GEMM used by the parity tests. */
+int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out,
+                 int ldo, int M, int N, int K, void* stream);
+
+/* softmax(Q K^T) V per (sequence, head), head_dim 64, scale already folded into Q.
+ * qkv: [n_seq*seq_len, 3*heads*64] bf16 as emitted by the qkv GEMM; out: [n_seq*seq_len, heads*64].
+ * Replaces dino_layers/attention.py:58-66 (and the xformers branch :79-84). */
+int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream);
+
+/* ---------------------------------------------------------------- memory-bound operators */
+
+typedef struct {
+  float mean[3];    /* per OUTPUT channel (RGB after the flip), in 0..255 units */
+  float inv_std[3];
+  int flip;         /* 1: stored channel order is BGR (mmseg bgr_to_rgb=True)   */
+} VfmPixelNorm;
+
+/* Gathers 16x16 patches of every crop window into the patch-embed GEMM operand
+ * out[(crop*gh*gw + gy*gw + gx), c*256 + py*16 + px] (bf16). crops: device int[4*n_crops] =
+ * {image, y1, x1, 0}. img is fp32 normalised NCHW (is_u8 = 0) or uint8 NCHW (is_u8 = 1, then
+ * nrm applies mmseg SegDataPreProcessor: lora_dinov2_linear.py:13-21).
+ * Replaces the crop slicing of slide_inference (Ms_VFM_encoder_decoder.py:433-442) and the
+ * unfold implicit in patch_embed.py:75. */
+int vfm_patch_gather(const void* img, int is_u8, const VfmPixelNorm* nrm /*host*/, int img_h,
+                     int img_w, const int* crops, int n_crops, int gh, int gw, void* out,
+                     void* stream);
+
+/* x[crop*tokens, :] = cls_token + pos[0, :].  dino_v2.py:225-226. */
+int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops, int tokens, int C,
+                 void* stream);
+
+/* LayerNorm rows of fp32 x[M,C] -> bf16 out.  C in {128..1024, multiple of 128}. block.py:63,75. */
+int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int C,
+                  float eps, void* stream);
+
+/* GroupNorm(groups, C) (+ReLU) over bf16 token-major [n_crops*P, C]. linear_head.py:36-40. */
+int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const float* beta,
+                       int n_crops, int P, int C, int groups, float eps, int relu, void* stream);
+
+/* Bilinear-resize every crop's low-res logits to the crop size, accumulate overlapping windows
+ * in row-major crop order, divide by the cover count, argmax.  lowres: fp32
+ * [n_img*n_crops, nc, lh, lw]; boxes: device int[2*n_crops] = {y1, x1}; labels: uint8 [n_img,H,W];
+ * logits_out: optional fp32 [n_img, nc, H, W].
+ * Replaces mmseg predict_by_feat resize + slide_inference pad/add/count/divide
+ * (Ms_VFM_encoder_decoder.py:453-461) + postprocess_result argmax. */
+int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h,
+                           int crop_w, int lh, int lw, int H, int W, int n_img, uint8_t* labels,
+                           float* logits_out, void* stream);
+
+/* cm[(min(label, nc)) * nc + pred] += 1 over pixels with label != ignore_index; cm is int64
+ * [(nc+1) * nc], accumulated (not zeroed). area_intersect = diag, area_pred = column sums over all
+ * nc+1 rows, area_label = row sums of the first nc rows.
+ * Replaces mmseg IoUMetric.intersect_and_union as called at rein/dg_metrics.py:50-52. */
+int vfm_confusion_matrix(const uint8_t* pred, const uint8_t* label, long long n, int nc,
+                         int ignore_index, long long* cm, void* stream);
+
+/* ---------------------------------------------------------------- fused drivers */
+
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;   /* LoRA merged, q rows pre-scaled by head_dim^-0.5 */
+  const void* proj_w; const float* proj_b;
+  const float* ls1;                          /* LayerScale gamma (ones when absent) */
+  const float* ln2_w; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;
+  const void* fc2_w;  const float* fc2_b;
+  const float* ls2;
+} VfmBlockParams;
+
+typedef struct {
+  int embed_dim, depth, heads, mlp_hidden, n_taps;
+  int tap_blocks[8];            /* out_indices, ascending */
+  float ln_eps;
+  const void* patch_w;          /* [embed_dim, 768] bf16 */
+  const float* patch_b;
+  const float* cls_token;       /* [embed_dim] */
+  const float* pos_embed;       /* [1 + gh*gw, embed_dim] for the grid of this call */
+  const VfmBlockParams* blocks; /* host array [depth] */
+} VfmVitParams;
+
+size_t vfm_vit_workspace_bytes(const VfmVitParams* p /*host*/, int n_crops, int gh, int gw);
+
+/* DinoVisionTransformer.forward_features over a batch of crop windows
+ * (rein/models/backbones/dino_v2.py:252-268) with peft LoRA merged. Writes the four feature
+ * taps token-major, cls dropped: taps[(crop*gh*gw + p), t*embed_dim + c] (bf16). */
+int vfm_vit_forward(const VfmVitParams* p /*host*/, const void* img, int is_u8,
+                    const VfmPixelNorm* nrm /*host*/, int img_h, int img_w, const int* crops,
+                    int n_crops, int gh, int gw, void* taps, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+typedef struct {
+  int in_channels;   /* n_taps * embed_dim */
+  int mid_channels;  /* embed_dim */
+  int groups, num_classes;
+  float gn_eps;
+  const void* fusion_w;                 /* [mid, in] bf16, no bias */
+  const float* gn_w; const float* gn_b;
+  const void* up1_w; const float* up1_b; /* [4*mid/2, mid], eval BatchNorm folded in */
+  const void* up2_w; const float* up2_b; /* [4*mid/4, mid/2] */
+  const void* cls_w; const float* cls_b; /* [32, mid/4] zero padded; [num_classes] */
+} VfmLinearHeadParams;
+
+size_t vfm_linear_head_workspace_bytes(const VfmLinearHeadParams* p /*host*/, int n_crops, int gh, int gw);
+
+/* LinearHead.forward (rein/models/heads/linear_head.py:50-70) on token-major taps;
+ * lowres: fp32 [n_crops, num_classes, 4*gh, 4*gw]. */
+int vfm_linear_head_forward(const VfmLinearHeadParams* p /*host*/, const void* taps, int n_crops,
+                            int gh, int gw, float* lowres, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFMSEG_B200_H_ */

@@ -1,0 +1,228 @@
+"""Per-operator parity of the CUDA kernels (through the C ABI) against plain torch fp32.
+
+Tolerances: operands are bf16-rounded before both paths, accumulation is fp32 on both sides, so
+GEMM-only outputs agree to ~1e-3 relative; bf16 outputs add one rounding (2^-9 relative).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vfmseg_b200 import _C, ops
+    _C.check(_C.load().vfm_device_check())
+    return ops
+
+
+def _rand(*shape, scale=1.0, seed=0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _close(a, b, rtol, atol, what):
+    a = a.float()
+    b = b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} out of tolerance, max abs err {err.max().item():.4g}, ref max {b.abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1025, 1024, 1024), (18450, 3072, 1024),
+                                   (300, 384, 128), (2050, 1024, 4096), (77, 96, 72)])
+def test_gemm_f32(ops, M, N, K):
+    a = _rand(M, K, seed=1, dtype=torch.bfloat16)
+    w = _rand(N, K, scale=K ** -0.5, seed=2, dtype=torch.bfloat16)
+    b = _rand(N, seed=3)
+    out = ops.gemm_f32(a, w, b)
+    ref = a.float() @ w.float().t() + b
+    _close(out, ref, 2e-3, 2e-3, f"gemm_f32 {M}x{N}x{K}")
+
+
+def test_gemm_bias_bf16_and_gelu(ops):
+    M, N, K = 2050, 4096, 1024
+    a = _rand(M, K, seed=4, dtype=torch.bfloat16)
+    w = _rand(N, K, scale=K ** -0.5, seed=5, dtype=torch.bfloat16)
+    b = _rand(N, seed=6)
+    ref = a.float() @ w.float().t() + b
+    _close(ops.gemm_bias_bf16(a, w, b), ref, 1e-2, 1e-2, "gemm_bias_bf16")
+    _close(ops.gemm_bias_bf16(a, w, None), ref - b, 1e-2, 1e-2, "gemm_bias_bf16(no bias)")
+    _close(ops.gemm_bias_gelu_bf16(a, w, b), F.gelu(ref), 1e-2, 1e-2, "gemm_bias_gelu_bf16")
+
+
+def test_gemm_residual_with_tap(ops):
+    n_crops, T, C, K = 3, 65, 256, 512
+    M = n_crops * T
+    a = _rand(M, K, seed=7, dtype=torch.bfloat16)
+    w = _rand(C, K, scale=K ** -0.5, seed=8, dtype=torch.bfloat16)
+    b = _rand(C, seed=9)
+    g = _rand(C, seed=10)
+    x0 = _rand(M, C, seed=11)
+    ref = x0 + g * (a.float() @ w.float().t() + b)
+    x = x0.clone()
+    tap = torch.zeros(n_crops * (T - 1), 2 * C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_bias_ls_residual_(x, a, w, b, g, tap=tap, tap_col0=C, tokens_per_crop=T)
+    _close(x, ref, 2e-3, 2e-3, "residual")
+    ref_tap = ref.view(n_crops, T, C)[:, 1:].reshape(-1, C)
+    _close(tap[:, C:], ref_tap, 1e-2, 1e-2, "tap")
+    assert tap[:, :C].abs().max().item() == 0
+    x2 = x0.clone()
+    ops.gemm_bias_ls_residual_(x2, a, w, b, g)
+    assert torch.equal(x, x2)
+
+
+def test_patch_gather_and_embed(ops):
+    B, H, W, C = 2, 96, 128, 256
+    img = _rand(B, 3, H, W, seed=12)
+    crops = torch.tensor([[0, 0, 0, 0], [0, 32, 61, 0], [1, 13, 64, 0]], dtype=torch.int32).cuda()
+    gh = gw = 4
+    a = ops.patch_gather(img, crops, gh, gw)
+    ref_rows = []
+    for (b_, y1, x1, _) in crops.tolist():
+        crop = img[b_, :, y1:y1 + 64, x1:x1 + 64]
+        ref_rows.append(F.unfold(crop[None], kernel_size=16, stride=16)[0].t())  # [P, 3*256] (c, py, px)
+    ref_a = torch.cat(ref_rows).to(torch.bfloat16)
+    assert torch.equal(a, ref_a), "patch_gather fp32"
+    # uint8 BGR + normalisation
+    g = torch.Generator().manual_seed(13)
+    img8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda()
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    a8 = ops.patch_gather(img8, crops, gh, gw, ops.pixel_norm(mean, std, True))
+    imgf = (img8[:, [2, 1, 0]].float() - torch.tensor(mean).view(1, 3, 1, 1).cuda()) / torch.tensor(std).view(1, 3, 1, 1).cuda()
+    ref8 = torch.cat([F.unfold(imgf[b_, :, y1:y1 + 64, x1:x1 + 64][None], 16, stride=16)[0].t() for (b_, y1, x1, _) in crops.tolist()])
+    _close(a8, ref8, 1e-2, 1e-2, "patch_gather uint8")
+    # embed GEMM + pos + cls
+    w = _rand(C, 768, scale=768 ** -0.5, seed=14, dtype=torch.bfloat16)
+    bias = _rand(C, seed=15)
+    pos = _rand(gh * gw + 1, C, seed=16)
+    cls = _rand(C, seed=17)
+    x = ops.gemm_patch_embed(a, w, bias, pos, crops.shape[0], gh * gw)
+    ops.cls_rows_(x, cls, pos, crops.shape[0], gh * gw + 1)
+    tok = (ref_a.float() @ w.float().t() + bias).view(3, gh * gw, C)
+    ref_x = torch.cat([cls.expand(3, 1, C), tok], 1) + pos
+    _close(x, ref_x.reshape(-1, C), 2e-3, 2e-3, "patch_embed")
+
+
+@pytest.mark.parametrize("M,C", [(1025, 1024), (37, 128), (18450, 1024), (100, 384)])
+def test_layernorm(ops, M, C):
+    x = _rand(M, C, seed=18) * 3 + 0.5
+    g = _rand(C, seed=19)
+    b = _rand(C, seed=20)
+    out = ops.layernorm(x, g, b, 1e-6)
+    _close(out, F.layer_norm(x, (C,), g, b, 1e-6), 1e-2, 1e-2, "layernorm")
+
+
+@pytest.mark.parametrize("n_seq,S,heads", [(1, 128, 1), (2, 256, 2), (1, 1025, 16), (3, 1025, 4), (2, 197, 2), (1, 2049, 2)])
+def test_attention(ops, n_seq, S, heads):
+    C = heads * 64
+    qkv = _rand(n_seq * S, 3 * C, seed=21, dtype=torch.bfloat16)
+    out = ops.attention_fwd(qkv, n_seq, S, heads)
+    q, k, v = qkv.float().view(n_seq, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
+    _close(out, ref, 2e-2, 2e-2, f"attention S={S} heads={heads}")
+
+
+def test_attention_peaked(ops):
+    # large-magnitude scores: exercises the online-softmax rescaling
+    n_seq, S, heads = 1, 1025, 2
+    C = heads * 64
+    qkv = _rand(n_seq * S, 3 * C, seed=22, dtype=torch.bfloat16)
+    qkv[:, :C] *= 4
+    out = ops.attention_fwd(qkv, n_seq, S, heads)
+    q, k, v = qkv.float().view(n_seq, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
+    _close(out, ref, 3e-2, 3e-2, "attention peaked")
+
+
+def test_groupnorm_relu(ops):
+    n_crops, P, C, G = 3, 64, 256, 32
+    x = (_rand(n_crops * P, C, seed=23) * 2 + 0.3).to(torch.bfloat16)
+    g = _rand(C, seed=24)
+    b = _rand(C, seed=25)
+    out = ops.groupnorm_relu(x, g, b, n_crops, G, 1e-5)
+    xr = x.float().view(n_crops, P, C).permute(0, 2, 1)  # [n, C, P]
+    ref = F.relu(F.group_norm(xr, G, g, b, 1e-5)).permute(0, 2, 1).reshape(-1, C)
+    _close(out, ref, 1e-2, 1e-2, "groupnorm_relu")
+
+
+def test_convt_and_cls(ops):
+    n, h, w, Cin, Cout = 2, 8, 8, 256, 128
+    x = _rand(n * h * w, Cin, seed=26, dtype=torch.bfloat16)
+    wt = _rand(Cin, Cout, 2, 2, scale=Cin ** -0.5, seed=27)  # ConvTranspose2d weight [Cin, Cout, 2, 2]
+    bias = _rand(Cout, seed=28)
+    wg = wt.permute(2, 3, 1, 0).reshape(4 * Cout, Cin).to(torch.bfloat16).contiguous()  # row (dy*2+dx)*Cout + co
+    out = ops.gemm_convt2x2_gelu(x, wg, bias.repeat(4).contiguous(), Cout, h, w)
+    xin = x.float().view(n, h, w, Cin).permute(0, 3, 1, 2)
+    ref = F.gelu(F.conv_transpose2d(xin, wt.to(torch.bfloat16).float(), bias, stride=2))  # [n, Cout, 2h, 2w]
+    ref_tok = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    _close(out, ref_tok, 1e-2, 1e-2, "convt2x2_gelu")
+    nc = 19
+    wc = _rand(nc, Cout, scale=Cout ** -0.5, seed=29)
+    bc = _rand(nc, seed=30)
+    w32 = torch.zeros(32, Cout, device="cuda", dtype=torch.bfloat16)
+    w32[:nc] = wc.to(torch.bfloat16)
+    logits = ops.gemm_cls_nchw(out, w32, bc, nc, 4 * h * w)
+    ref_l = (out.float() @ w32[:nc].float().t() + bc).view(n, 4 * h * w, nc).permute(0, 2, 1)
+    _close(logits, ref_l, 2e-3, 2e-3, "cls_nchw")
+
+
+def _slide_boxes(H, W, ch, cw, sh, sw):
+    hg = max(H - ch + sh - 1, 0) // sh + 1
+    wg = max(W - cw + sw - 1, 0) // sw + 1
+    boxes = []
+    for hi in range(hg):
+        for wi in range(wg):
+            y2 = min(hi * sh + ch, H); x2 = min(wi * sw + cw, W)
+            boxes.append((max(y2 - ch, 0), max(x2 - cw, 0)))
+    return boxes
+
+
+@pytest.mark.parametrize("H,W,crop,stride,n_img", [(1024, 2048, 512, 341, 1), (160, 224, 64, 43, 2), (64, 64, 64, 43, 1)])
+def test_slide_merge_argmax(ops, H, W, crop, stride, n_img):
+    nc = 19
+    boxes = _slide_boxes(H, W, crop, crop, stride, stride)
+    lh = crop // 4
+    low = _rand(n_img * len(boxes), nc, lh, lh, seed=31)
+    labels, logits = ops.slide_merge_argmax(low, torch.tensor(boxes, dtype=torch.int32).cuda(), n_img, (crop, crop), (H, W), want_logits=True)
+    preds = torch.zeros(n_img, nc, H, W, device="cuda")
+    count = torch.zeros(n_img, 1, H, W, device="cuda")
+    lv = low.view(n_img, len(boxes), nc, lh, lh)
+    for k, (y1, x1) in enumerate(boxes):
+        up = F.interpolate(lv[:, k], size=(crop, crop), mode="bilinear", align_corners=False)
+        preds += F.pad(up, (x1, W - x1 - crop, y1, H - y1 - crop))
+        count[:, :, y1:y1 + crop, x1:x1 + crop] += 1
+    assert (count == 0).sum() == 0
+    ref = preds / count
+    _close(logits, ref, 1e-5, 1e-5, "merged logits")
+    ref_lab = ref.argmax(1)
+    agree = (labels.long() == ref_lab).float().mean().item()
+    assert agree >= 0.9999, f"label agreement {agree}"
+    # labels must be the argmax of the kernel's own logits (first max wins), exactly
+    assert torch.equal(labels.long(), logits.argmax(1))
+    labels2, none = ops.slide_merge_argmax(low, torch.tensor(boxes, dtype=torch.int32).cuda(), n_img, (crop, crop), (H, W))
+    assert none is None and torch.equal(labels, labels2)
+
+
+@pytest.mark.parametrize("n", [1024 * 2048, 16 * 1000 + 7, 5, 0])
+def test_confusion_matrix(ops, n):
+    nc = 19
+    g = torch.Generator().manual_seed(32)
+    pred = torch.randint(0, nc, (n,), generator=g, dtype=torch.uint8)
+    label = torch.randint(0, nc + 3, (n,), generator=g, dtype=torch.uint8)
+    label[label == nc + 2] = 255
+    # piecewise-constant stretch to exercise the run-length path
+    if n > 4096:
+        pred[:2048] = 3; label[:2048] = 3; label[2048:4096] = 255
+    cm = torch.zeros(nc + 1, nc, dtype=torch.int64, device="cuda")
+    ops.confusion_matrix_(cm, pred.cuda(), label.cuda(), nc, 255)
+    ops.confusion_matrix_(cm, pred.cuda(), label.cuda(), nc, 255)  # accumulates
+    keep = label != 255
+    p, l = pred[keep].long(), label[keep].long().clamp(max=nc)
+    ref = torch.zeros(nc + 1, nc, dtype=torch.int64)
+    ref.view(-1).index_add_(0, l * nc + p, torch.ones_like(p))
+    assert torch.equal(cm.cpu(), 2 * ref)

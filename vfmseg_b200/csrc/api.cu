@@ -1,0 +1,395 @@
+// C ABI of libvfmseg_b200.so (see include/vfmseg_b200.h). Host-side only: argument checks,
+// TMA tensor-map encoding, kernel launches and the two fused drivers (ViT backbone, LinearHead).
+#include "../../include/vfmseg_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "attention_sm100.cuh"
+#include "elementwise.cuh"
+#include "gemm_sm100.cuh"
+#include "slide_tail.cuh"
+
+using namespace vfm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define VFM_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(VFM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define VFM_LAUNCH_CHECK(name)                                                                  \
+  do {                                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                        \
+    if (e_ != cudaSuccess) return fail(VFM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}; 128-B swizzle.
+int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) != 0)
+    return fail(VFM_ERR_INVALID, "TMA operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%llu)", ptr,
+                static_cast<unsigned long long>(ld));
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return VFM_OK;
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+  }();
+  return n;
+}
+
+template <int BLOCK_N, class Epi>
+int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi, cudaStream_t st,
+                const char* name) {
+  if (!A || !W) return fail(VFM_ERR_INVALID, "%s: null operand", name);
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0)
+    return fail(VFM_ERR_INVALID, "%s: need M,N,K > 0, N %% 32 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", name, M, N, K);
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, GEMM_BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tb, W, N, K, ldw, BLOCK_N);
+  if (rc) return rc;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, Epi>;
+  static bool attr_done = false;  // per template instantiation
+  if (!attr_done) {
+    VFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int tiles = m_tiles * n_tiles;
+  int sms = sm_count();
+  if (sms <= 0) return fail(VFM_ERR_CUDA, "%s: no CUDA device", name);
+  const int grid = tiles < sms ? tiles : sms;
+  // K tail (K % 64 != 0) is covered by TMA zero fill of both operands.
+  const int K_pad = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K * GEMM_BLOCK_K;
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K_pad, epi);
+  VFM_LAUNCH_CHECK(name);
+  return VFM_OK;
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline __nv_bfloat16* BF(void* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+inline const __nv_bfloat16* BF(const void* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+const char* vfm_last_error(void) { return g_err; }
+int vfm_abi_version(void) { return VFM_ABI_VERSION; }
+long long vfm_launch_count(void) { return g_launches.load(); }
+
+int vfm_device_check(void) {
+  int dev = 0, major = 0;
+  VFM_CUDA(cudaGetDevice(&dev));
+  VFM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(VFM_ERR_DEVICE, "device compute capability %d.x, need 10.x (sm_100a)", major);
+  return VFM_OK;
+}
+
+int vfm_gemm_bias_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                       int N, int K, void* stream) {
+  if (!out || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_bf16: bad out/ldo");
+  EpiBiasBf16 e{BF(out), ldo, bias, N};
+  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16");
+}
+
+int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
+                            int M, int N, int K, void* stream) {
+  if (!out || !bias || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_gelu_bf16: bad out/bias/ldo");
+  EpiBiasGeluBf16 e{BF(out), ldo, bias};
+  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_gelu_bf16");
+}
+
+int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                              float* x, int ldx, void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int M,
+                              int N, int K, void* stream) {
+  if (!x || !bias || !gamma || (ldx % 4)) return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual: bad x/bias/gamma/ldx");
+  if (tap && ((tap_ld % 8) || (tap_col0 % 8) || tokens_per_crop <= 0))
+    return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual: bad tap layout");
+  EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, tokens_per_crop > 0 ? tokens_per_crop : 1};
+  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual");
+}
+
+int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
+                         int patches, int M, int N, int K, void* stream) {
+  if (!x || !bias || !pos || patches <= 0 || (M % patches)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
+  EpiPatchEmbed e{x, N, bias, pos, patches};
+  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
+}
+
+int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int c_out,
+                           int h, int w, int M, int K, void* stream) {
+  if (!out || !bias || c_out <= 0 || (c_out % 32) || h <= 0 || w <= 0 || (M % (h * w)))
+    return fail(VFM_ERR_INVALID, "gemm_convt2x2_gelu: bad args (c_out %% 32 == 0, M %% (h*w) == 0)");
+  EpiConvT2x2Gelu e{BF(out), bias, c_out, h, w};
+  return launch_gemm<256>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu");
+}
+
+int vfm_gemm_cls_nchw(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int num_classes,
+                      int pix_per_crop, int M, int K, void* stream) {
+  if (!out || !bias || num_classes <= 0 || num_classes > 32 || pix_per_crop <= 0 || (M % pix_per_crop))
+    return fail(VFM_ERR_INVALID, "gemm_cls_nchw: bad args (num_classes <= 32, M %% pix_per_crop == 0)");
+  EpiClsNCHW e{out, bias, num_classes, pix_per_crop};
+  return launch_gemm<32>(A, lda, W, ldw, M, 32, K, e, S(stream), "gemm_cls_nchw");
+}
+
+int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, int M, int N,
+                 int K, void* stream) {
+  if (!out || (ldo % 4)) return fail(VFM_ERR_INVALID, "gemm_f32: bad out/ldo");
+  EpiF32 e{out, ldo, bias};
+  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_f32");
+}
+
+int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream) {
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_fwd: bad args");
+  const int C = heads * ATT_D;
+  CUtensorMap tq;
+  int rc = make_tmap(&tq, qkv, static_cast<uint64_t>(n_seq) * seq_len, 3 * C, 3 * C, ATT_BLOCK_KV);
+  if (rc) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VFM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int q_tiles = (seq_len + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
+  const long long grid = static_cast<long long>(n_seq) * heads * q_tiles;
+  if (grid > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention_fwd: grid too large");
+  attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, S(stream)>>>(tq, BF(out), seq_len,
+                                                                                              heads, q_tiles);
+  VFM_LAUNCH_CHECK("attention_fwd");
+  return VFM_OK;
+}
+
+int vfm_patch_gather(const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w, const int* crops,
+                     int n_crops, int gh, int gw, void* out, void* stream) {
+  if (!img || !crops || !out || n_crops <= 0 || gh <= 0 || gw <= 0) return fail(VFM_ERR_INVALID, "patch_gather: bad args");
+  if (is_u8 && !nrm) return fail(VFM_ERR_INVALID, "patch_gather: uint8 input needs a VfmPixelNorm");
+  PixelNorm pn{};
+  if (nrm) {
+    for (int i = 0; i < 3; ++i) { pn.mean[i] = nrm->mean[i]; pn.inv_std[i] = nrm->inv_std[i]; }
+    pn.flip = nrm->flip;
+  }
+  const long long total = static_cast<long long>(n_crops) * gh * gw * 96;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (is_u8)
+    patch_gather_kernel<uint8_t><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
+        reinterpret_cast<const uint8_t*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
+  else
+    patch_gather_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
+        reinterpret_cast<const float*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
+  VFM_LAUNCH_CHECK("patch_gather");
+  return VFM_OK;
+}
+
+int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops, int tokens, int C, void* stream) {
+  if (!x || !cls_token || !pos) return fail(VFM_ERR_INVALID, "cls_rows: null");
+  const int n = n_crops * C;
+  cls_rows_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(x, cls_token, pos, n_crops, tokens, C);
+  VFM_LAUNCH_CHECK("cls_rows");
+  return VFM_OK;
+}
+
+int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                  void* stream) {
+  if (!x || !gamma || !beta || !out || M <= 0) return fail(VFM_ERR_INVALID, "layernorm: bad args");
+  if (C % 128 || C < 128 || C > 1024) return fail(VFM_ERR_INVALID, "layernorm: C must be a multiple of 128 in [128,1024] (C=%d)", C);
+  const int grid = (M + 7) / 8;
+  cudaStream_t st = S(stream);
+  switch (C / 128) {
+#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps); break;
+    VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
+#undef VFM_LN_CASE
+  }
+  VFM_LAUNCH_CHECK("layernorm");
+  return VFM_OK;
+}
+
+int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const float* beta, int n_crops, int P, int C,
+                       int groups, float eps, int relu, void* stream) {
+  if (!in || !out || !gamma || !beta || n_crops <= 0 || P <= 0 || groups <= 0 || C % groups || (C / groups) % 8)
+    return fail(VFM_ERR_INVALID, "groupnorm_relu: bad args (C/groups must be a multiple of 8)");
+  groupnorm_relu_kernel<<<n_crops * groups, 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, P, C, groups, eps, relu);
+  VFM_LAUNCH_CHECK("groupnorm_relu");
+  return VFM_OK;
+}
+
+int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh,
+                           int lw, int H, int W, int n_img, uint8_t* labels, float* logits_out, void* stream) {
+  if (!lowres || !boxes || !labels || n_crops <= 0 || nc <= 0 || nc > 32 || n_img <= 0)
+    return fail(VFM_ERR_INVALID, "slide_merge_argmax: bad args (num_classes <= 32)");
+  const long long total = static_cast<long long>(n_img) * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = sizeof(int2) * n_crops;
+  if (nc <= 19)
+    slide_merge_argmax_kernel<19><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
+        lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
+  else
+    slide_merge_argmax_kernel<32><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
+        lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
+  VFM_LAUNCH_CHECK("slide_merge_argmax");
+  return VFM_OK;
+}
+
+int vfm_confusion_matrix(const uint8_t* pred, const uint8_t* label, long long n, int nc, int ignore_index,
+                         long long* cm, void* stream) {
+  if (n == 0) return VFM_OK;
+  if (!pred || !label || !cm || n < 0 || nc <= 0 || nc > 64) return fail(VFM_ERR_INVALID, "confusion_matrix: bad args");
+  if ((reinterpret_cast<uintptr_t>(pred) & 15) || (reinterpret_cast<uintptr_t>(label) & 15))
+    return fail(VFM_ERR_INVALID, "confusion_matrix: pred/label must be 16-byte aligned");
+  long long blocks = ((n >> 4) + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  confusion_matrix_kernel<<<static_cast<unsigned>(blocks), 256, sizeof(int) * (nc + 1) * nc, S(stream)>>>(
+      pred, label, n, nc, ignore_index, reinterpret_cast<unsigned long long*>(cm));
+  VFM_LAUNCH_CHECK("confusion_matrix");
+  return VFM_OK;
+}
+
+// ------------------------------------------------------------------------------ fused drivers
+// ViT workspace layout (all 256-byte aligned):
+//   x     fp32 [M, C]        residual stream          M = n_crops * (gh*gw + 1)
+//   xn    bf16 [M, C]        LayerNorm output / attention output (disjoint lifetimes -> two buffers)
+//   att   bf16 [M, C]
+//   qkv   bf16 [M, 3C]
+//   hid   bf16 [M, hidden]   (the patch operand [n_crops*gh*gw, 768] aliases this buffer)
+size_t vfm_vit_workspace_bytes(const VfmVitParams* p, int n_crops, int gh, int gw) {
+  if (!p) return 0;
+  const size_t M = static_cast<size_t>(n_crops) * (static_cast<size_t>(gh) * gw + 1);
+  const size_t C = p->embed_dim;
+  size_t hid = M * p->mlp_hidden * 2;
+  const size_t patches = static_cast<size_t>(n_crops) * gh * gw * 768 * 2;
+  if (patches > hid) hid = patches;
+  return align_up(M * C * 4, 256) + 2 * align_up(M * C * 2, 256) + align_up(M * 3 * C * 2, 256) + align_up(hid, 256);
+}
+
+int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w,
+                    const int* crops, int n_crops, int gh, int gw, void* taps, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  if (!p || !p->blocks || !img || !crops || !taps || !workspace) return fail(VFM_ERR_INVALID, "vit_forward: null argument");
+  const int C = p->embed_dim, Hd = p->mlp_hidden;
+  if (C != p->heads * 64) return fail(VFM_ERR_INVALID, "vit_forward: head_dim must be 64 (embed_dim=%d heads=%d)", C, p->heads);
+  if (p->n_taps <= 0 || p->n_taps > 8) return fail(VFM_ERR_INVALID, "vit_forward: n_taps out of range");
+  const size_t need = vfm_vit_workspace_bytes(p, n_crops, gh, gw);
+  if (workspace_bytes < need) return fail(VFM_ERR_WORKSPACE, "vit_forward: workspace %zu < %zu", workspace_bytes, need);
+  const int P = gh * gw, T = P + 1;
+  const int M = n_crops * T;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws);            ws += align_up(static_cast<size_t>(M) * C * 4, 256);
+  void* xn = ws;                                      ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* att = ws;                                     ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* qkv = ws;                                     ws += align_up(static_cast<size_t>(M) * 3 * C * 2, 256);
+  void* hid = ws;
+  int rc;
+  // tokens: patch gather -> patch-embed GEMM (+bias +pos) ; cls rows
+  if ((rc = vfm_patch_gather(img, is_u8, nrm, img_h, img_w, crops, n_crops, gh, gw, hid, stream))) return rc;
+  if ((rc = vfm_gemm_patch_embed(hid, 768, p->patch_w, 768, p->patch_b, p->pos_embed, x, P, n_crops * P, C, 768, stream))) return rc;
+  if ((rc = vfm_cls_rows(x, p->cls_token, p->pos_embed, n_crops, T, C, stream))) return rc;
+  int next_tap = 0;
+  for (int l = 0; l < p->depth; ++l) {
+    const VfmBlockParams& b = p->blocks[l];
+    if ((rc = vfm_layernorm(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, stream))) return rc;
+    if ((rc = vfm_gemm_bias_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, 3 * C, M, 3 * C, C, stream))) return rc;
+    if ((rc = vfm_attention_fwd(qkv, att, n_crops, T, p->heads, stream))) return rc;
+    if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, b.ls1, x, C, nullptr, 0, 0, T, M, C, C, stream))) return rc;
+    if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
+    if ((rc = vfm_gemm_bias_gelu_bf16(xn, C, b.fc1_w, C, b.fc1_b, hid, Hd, M, Hd, C, stream))) return rc;
+    void* tap = nullptr;
+    int tap_col0 = 0;
+    if (next_tap < p->n_taps && p->tap_blocks[next_tap] == l) {
+      tap = taps;
+      tap_col0 = next_tap * C;
+      ++next_tap;
+    }
+    if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, tap, p->n_taps * C, tap_col0, T, M, C, Hd, stream))) return rc;
+  }
+  if (next_tap != p->n_taps) return fail(VFM_ERR_INVALID, "vit_forward: tap_blocks must be ascending and < depth");
+  return VFM_OK;
+}
+
+// LinearHead workspace: f0 bf16 [R, mid] (fusion out), f1 bf16 [R, mid] (GN+ReLU), u1 bf16 [4R, mid/2],
+// u2 bf16 [16R, mid/4]; R = n_crops * gh * gw.
+size_t vfm_linear_head_workspace_bytes(const VfmLinearHeadParams* p, int n_crops, int gh, int gw) {
+  if (!p) return 0;
+  const size_t R = static_cast<size_t>(n_crops) * gh * gw, mid = p->mid_channels;
+  return 2 * align_up(R * mid * 2, 256) + align_up(4 * R * (mid / 2) * 2, 256) + align_up(16 * R * (mid / 4) * 2, 256);
+}
+
+int vfm_linear_head_forward(const VfmLinearHeadParams* p, const void* taps, int n_crops, int gh, int gw, float* lowres,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !taps || !lowres || !workspace) return fail(VFM_ERR_INVALID, "linear_head_forward: null argument");
+  const int mid = p->mid_channels;
+  if (mid % 128) return fail(VFM_ERR_INVALID, "linear_head_forward: mid_channels must be a multiple of 128");
+  const size_t need = vfm_linear_head_workspace_bytes(p, n_crops, gh, gw);
+  if (workspace_bytes < need) return fail(VFM_ERR_WORKSPACE, "linear_head_forward: workspace %zu < %zu", workspace_bytes, need);
+  const int P = gh * gw;
+  const int R = n_crops * P;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  void* f0 = ws; ws += align_up(static_cast<size_t>(R) * mid * 2, 256);
+  void* f1 = ws; ws += align_up(static_cast<size_t>(R) * mid * 2, 256);
+  void* u1 = ws; ws += align_up(static_cast<size_t>(4) * R * (mid / 2) * 2, 256);
+  void* u2 = ws;
+  int rc;
+  if ((rc = vfm_gemm_bias_bf16(taps, p->in_channels, p->fusion_w, p->in_channels, nullptr, f0, mid, R, mid, p->in_channels, stream))) return rc;
+  if ((rc = vfm_groupnorm_relu(f0, f1, p->gn_w, p->gn_b, n_crops, P, mid, p->groups, p->gn_eps, 1, stream))) return rc;
+  if ((rc = vfm_gemm_convt2x2_gelu(f1, mid, p->up1_w, mid, p->up1_b, u1, mid / 2, gh, gw, R, mid, stream))) return rc;
+  if ((rc = vfm_gemm_convt2x2_gelu(u1, mid / 2, p->up2_w, mid / 2, p->up2_b, u2, mid / 4, 2 * gh, 2 * gw, 4 * R, mid / 2, stream))) return rc;
+  if ((rc = vfm_gemm_cls_nchw(u2, mid / 4, p->cls_w, mid / 4, p->cls_b, lowres, p->num_classes, 16 * P, 16 * R, mid / 4, stream))) return rc;
+  return VFM_OK;
+}
+
+}  // extern "C"

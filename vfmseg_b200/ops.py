@@ -1,0 +1,166 @@
+"""Tensor-level wrappers over the C ABI: each takes torch CUDA tensors (device memory + the current
+stream are all torch contributes) and calls one entry point of libvfmseg_b200.so.
+
+These are the per-operator building blocks the parity tests exercise; the product path uses the
+fused drivers in `engine.py`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _C
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "vfmseg_b200 ops need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _bf16(t):
+    assert t.dtype == torch.bfloat16
+    return _ptr(t)
+
+
+def _f32(t):
+    if t is None:
+        return None
+    assert t.dtype == torch.float32
+    return _ptr(t)
+
+
+def gemm_f32(a, w, bias=None):
+    """fp32 out = a @ w.T (+ bias); a [M,K] bf16, w [N,K] bf16."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _C.call("vfm_gemm_f32", _bf16(a), K, _bf16(w), K, _f32(bias), _f32(out), N, M, N, K, _stream())
+    return out
+
+
+def gemm_bias_bf16(a, w, bias=None, out=None):
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_bias_bf16", _bf16(a), a.stride(0), _bf16(w), K, _f32(bias), _bf16(out), out.stride(0),
+            M, N, K, _stream())
+    return out
+
+
+def gemm_bias_gelu_bf16(a, w, bias):
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_bias_gelu_bf16", _bf16(a), K, _bf16(w), K, _f32(bias), _bf16(out), N, M, N, K, _stream())
+    return out
+
+
+def gemm_bias_ls_residual_(x, a, w, bias, gamma, tap=None, tap_col0=0, tokens_per_crop=1):
+    """x (fp32 [M,N]) += gamma * (a @ w.T + bias) in place; optional bf16 tap snapshot."""
+    M, K = a.shape
+    N = w.shape[0]
+    _C.call("vfm_gemm_bias_ls_residual", _bf16(a), K, _bf16(w), K, _f32(bias), _f32(gamma), _f32(x), N,
+            _bf16(tap) if tap is not None else None, tap.shape[1] if tap is not None else 0, tap_col0,
+            tokens_per_crop, M, N, K, _stream())
+    return x
+
+
+def gemm_patch_embed(a, w, bias, pos, n_crops, patches):
+    M, K = a.shape
+    N = w.shape[0]
+    x = torch.empty(n_crops * (patches + 1), N, device=a.device, dtype=torch.float32)
+    _C.call("vfm_gemm_patch_embed", _bf16(a), K, _bf16(w), K, _f32(bias), _f32(pos), _f32(x), patches, M, N, K,
+            _stream())
+    return x
+
+
+def gemm_convt2x2_gelu(a, w, bias, c_out, h, w_):
+    M, K = a.shape
+    out = torch.empty(4 * M, c_out, device=a.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_convt2x2_gelu", _bf16(a), K, _bf16(w), K, _f32(bias), _bf16(out), c_out, h, w_, M, K, _stream())
+    return out
+
+
+def gemm_cls_nchw(a, w32, bias, num_classes, pix_per_crop):
+    M, K = a.shape
+    assert w32.shape[0] == 32
+    out = torch.empty(M // pix_per_crop, num_classes, pix_per_crop, device=a.device, dtype=torch.float32)
+    _C.call("vfm_gemm_cls_nchw", _bf16(a), K, _bf16(w32), K, _f32(bias), _f32(out), num_classes, pix_per_crop, M, K,
+            _stream())
+    return out
+
+
+def attention_fwd(qkv, n_seq, seq_len, heads):
+    out = torch.empty(n_seq * seq_len, heads * 64, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_fwd", _bf16(qkv), _bf16(out), n_seq, seq_len, heads, _stream())
+    return out
+
+
+def pixel_norm(mean, std, flip) -> _C.VfmPixelNorm:
+    n = _C.VfmPixelNorm()
+    for i in range(3):
+        n.mean[i] = float(mean[i])
+        n.inv_std[i] = 1.0 / float(std[i])
+    n.flip = int(bool(flip))
+    return n
+
+
+def patch_gather(img, crops, gh, gw, norm: _C.VfmPixelNorm | None = None):
+    """img: [B,3,H,W] fp32 (normalised) or uint8; crops: int32 [n,4] = (image, y1, x1, 0)."""
+    is_u8 = img.dtype == torch.uint8
+    assert is_u8 or img.dtype == torch.float32
+    assert crops.dtype == torch.int32 and crops.shape[1] == 4
+    n = crops.shape[0]
+    out = torch.empty(n * gh * gw, 768, device=img.device, dtype=torch.bfloat16)
+    _C.call("vfm_patch_gather", _ptr(img), int(is_u8), C.byref(norm) if norm is not None else None,
+            img.shape[2], img.shape[3], _ptr(crops), n, gh, gw, _bf16(out), _stream())
+    return out
+
+
+def cls_rows_(x, cls_token, pos, n_crops, tokens):
+    _C.call("vfm_cls_rows", _f32(x), _f32(cls_token), _f32(pos), n_crops, tokens, x.shape[1], _stream())
+    return x
+
+
+def layernorm(x, gamma, beta, eps):
+    M, Cc = x.shape
+    out = torch.empty(M, Cc, device=x.device, dtype=torch.bfloat16)
+    _C.call("vfm_layernorm", _f32(x), _f32(gamma), _f32(beta), _bf16(out), M, Cc, float(eps), _stream())
+    return out
+
+
+def groupnorm_relu(x, gamma, beta, n_crops, groups, eps, relu=True):
+    R, Cc = x.shape
+    out = torch.empty_like(x)
+    _C.call("vfm_groupnorm_relu", _bf16(x), _bf16(out), _f32(gamma), _f32(beta), n_crops, R // n_crops, Cc, groups,
+            float(eps), int(relu), _stream())
+    return out
+
+
+def slide_merge_argmax(lowres, boxes, n_img, crop_hw, out_hw, want_logits=False):
+    """lowres: fp32 [n_img*n_crops, nc, lh, lw]; boxes: int32 [n_crops, 2] = (y1, x1)."""
+    n_crops = boxes.shape[0]
+    _, nc, lh, lw = lowres.shape
+    H, W = out_hw
+    labels = torch.empty(n_img, H, W, device=lowres.device, dtype=torch.uint8)
+    logits = torch.empty(n_img, nc, H, W, device=lowres.device, dtype=torch.float32) if want_logits else None
+    _C.call("vfm_slide_merge_argmax", _f32(lowres), _ptr(boxes), n_crops, nc, crop_hw[0], crop_hw[1], lh, lw, H, W,
+            n_img, _ptr(labels), _f32(logits), _stream())
+    return labels, logits
+
+
+def confusion_matrix_(cm, pred, label, num_classes, ignore_index=255):
+    """cm: int64 [(nc+1), nc], accumulated in place."""
+    assert cm.dtype == torch.int64 and cm.numel() == (num_classes + 1) * num_classes
+    assert pred.dtype == torch.uint8 and label.dtype == torch.uint8 and pred.numel() == label.numel()
+    _C.call("vfm_confusion_matrix", _ptr(pred), _ptr(label), pred.numel(), num_classes, ignore_index, _ptr(cm),
+            _stream())
+    return cm
