@@ -1,0 +1,267 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Never imported by the product path (vfmseg_b200/).
+
+Plain-PyTorch fp32 CPU restatement of the reference's slide-inference hot path, written as free
+functions over a state dict that uses the reference's own key names. Each function cites the
+reference lines it follows (paths relative to /root/reference). Third-party semantics that are
+not vendored in the reference (mmseg 1.2.2, mmcv 2.1.0, peft 0.10.0) are restated from their
+published behaviour and marked [3P]; where the reference holds a verbatim in-repo copy, that copy
+is cited instead.
+
+Pinning: this restatement is validated against the reference's OWN modules (imported unmodified
+through oracle/ref_shim.py) by oracle/make_golden.py and tests/test_oracle_vs_reference.py; the
+reference ships no tests or golden vectors of its own, and the [3P] pieces cannot
+be run here (packages absent), so parity is pinned for the in-repo code and "unpinned" at the
+third-party boundary.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------- slide grid
+def slide_boxes(H: int, W: int, crop: Sequence[int], stride: Sequence[int]) -> List[Tuple[int, int, int, int]]:
+    """(y1, y2, x1, x2) per window, row-major. rein/models/segmentors/Ms_VFM_encoder_decoder.py:424-441
+    (verbatim in-repo copy of mmseg EncoderDecoder.slide_inference [3P])."""
+    h_crop, w_crop = crop
+    h_stride, w_stride = stride
+    h_grids = max(H - h_crop + h_stride - 1, 0) // h_stride + 1
+    w_grids = max(W - w_crop + w_stride - 1, 0) // w_stride + 1
+    boxes = []
+    for h_idx in range(h_grids):
+        for w_idx in range(w_grids):
+            y1 = h_idx * h_stride
+            x1 = w_idx * w_stride
+            y2 = min(y1 + h_crop, H)
+            x2 = min(x1 + w_crop, W)
+            y1 = max(y2 - h_crop, 0)
+            x1 = max(x2 - w_crop, 0)
+            boxes.append((y1, y2, x1, x2))
+    return boxes
+
+
+# --------------------------------------------------------------------------- preprocessing
+def preprocess(img_u8_bgr: Tensor, mean, std, bgr_to_rgb=True) -> Tensor:
+    """mmseg SegDataPreProcessor.forward [3P], configured at configs/_base_/models/lora_dinov2_linear.py:13-21:
+    channel flip, .float(), (x - mean) / std. img: uint8 [B,3,H,W]."""
+    x = img_u8_bgr
+    if bgr_to_rgb:
+        x = x[:, [2, 1, 0]]
+    x = x.float()
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return (x - m) / s
+
+
+# --------------------------------------------------------------------------- backbone
+def interpolate_pos_encoding(pos_embed: Tensor, npatch: int, w: int, h: int, patch: int) -> Tensor:
+    """rein/models/backbones/dino_v2.py:184-215. NB the caller unpacks `B, nc, w, h = x.shape`
+    (:218), so `w` is the image HEIGHT and `h` the WIDTH; kept as in the reference."""
+    N = pos_embed.shape[1] - 1
+    if npatch == N and w == h:
+        return pos_embed
+    pos_embed = pos_embed.float()
+    class_pos = pos_embed[:, 0]
+    patch_pos = pos_embed[:, 1:]
+    dim = pos_embed.shape[-1]
+    w0 = w // patch
+    h0 = h // patch
+    w0, h0 = w0 + 0.1, h0 + 0.1
+    s = int(math.sqrt(N))
+    patch_pos = F.interpolate(patch_pos.reshape(1, s, s, dim).permute(0, 3, 1, 2),
+                              scale_factor=(w0 / math.sqrt(N), h0 / math.sqrt(N)), mode="bicubic")
+    assert int(w0) == patch_pos.shape[-2] and int(h0) == patch_pos.shape[-1]
+    patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, -1, dim)
+    return torch.cat((class_pos.unsqueeze(0), patch_pos), dim=1)
+
+
+def _linear(x, sd, name):
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def _qkv(x, sd, pre, lora_scale):
+    """nn.Linear qkv, optionally peft-wrapped: base(x) + lora_B(lora_A(x)) * (alpha / r)
+    (peft 0.10.0 lora.Linear.forward [3P]; dropout is identity in eval)."""
+    if pre + ".base_layer.weight" in sd:
+        y = F.linear(x, sd[pre + ".base_layer.weight"], sd.get(pre + ".base_layer.bias"))
+        a = sd[pre + ".lora_A.default.weight"]
+        b = sd[pre + ".lora_B.default.weight"]
+        return y + F.linear(F.linear(x, a), b) * lora_scale
+    return _linear(x, sd, pre)
+
+
+def attention(x: Tensor, sd, pre: str, num_heads: int, lora_scale: float) -> Tensor:
+    """rein/models/backbones/dino_layers/attention.py:56-69 (the branch MemEffAttention.forward takes
+    when xformers is absent, :73-77)."""
+    B, N, C = x.shape
+    qkv = _qkv(x, sd, pre + ".qkv", lora_scale).reshape(B, N, 3, num_heads, C // num_heads).permute(2, 0, 3, 1, 4)
+    scale = (C // num_heads) ** -0.5
+    q, k, v = qkv[0] * scale, qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)).softmax(dim=-1)
+    x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    return _linear(x, sd, pre + ".proj")
+
+
+def block(x: Tensor, sd, pre: str, num_heads: int, lora_scale: float, eps: float = 1e-6) -> Tensor:
+    """rein/models/backbones/dino_layers/block.py:89-114, eval branch (:111-113); LayerScale
+    layer_scale.py:27; Mlp mlp.py:34-40 (exact-erf GELU); LayerNorm eps 1e-6 dino_v2.py:104."""
+    C = x.shape[-1]
+    h = F.layer_norm(x, (C,), sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"], eps)
+    h = attention(h, sd, pre + ".attn", num_heads, lora_scale)
+    if pre + ".ls1.gamma" in sd:
+        h = h * sd[pre + ".ls1.gamma"]
+    x = x + h
+    h = F.layer_norm(x, (C,), sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"], eps)
+    h = _linear(F.gelu(_linear(h, sd, pre + ".mlp.fc1")), sd, pre + ".mlp.fc2")
+    if pre + ".ls2.gamma" in sd:
+        h = h * sd[pre + ".ls2.gamma"]
+    return x + h
+
+
+def dino_forward(x: Tensor, sd: Dict[str, Tensor], *, depth: int, num_heads: int, patch: int = 16,
+                 out_indices=(7, 11, 15, 23), lora_scale: float = 1.0, return_tokens: bool = False):
+    """DinoVisionTransformer.forward_features, rein/models/backbones/dino_v2.py:252-268, with
+    prepare_tokens_with_masks :217-228 and PatchEmbed.forward patch_embed.py:68-81.
+    `sd` holds un-prefixed backbone keys (cls_token, pos_embed, patch_embed.proj.*, blocks.N.*)."""
+    B, _, h, w = x.shape
+    t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch)
+    t = t.flatten(2).transpose(1, 2)
+    t = torch.cat((sd["cls_token"].expand(B, -1, -1), t), dim=1)
+    # dino_v2.py:218 names the spatial dims (w, h) = (H, W)
+    t = t + interpolate_pos_encoding(sd["pos_embed"], t.shape[1] - 1, h, w, patch)
+    outs, toks = [], []
+    for i in range(depth):
+        t = block(t, sd, f"blocks.{i}", num_heads, lora_scale)
+        if i in out_indices:
+            toks.append(t)
+            outs.append(t[:, 1:, :].permute(0, 2, 1).reshape(B, -1, h // patch, w // patch).contiguous())
+    return (outs, toks) if return_tokens else outs
+
+
+# --------------------------------------------------------------------------- LinearHead
+def linear_head_forward(feats: Sequence[Tensor], sd: Dict[str, Tensor], *, groups: int = 32) -> Tensor:
+    """LinearHead.forward, rein/models/heads/linear_head.py:50-70: cat -> fusion_conv (mmcv ConvModule
+    [3P]: 1x1 conv without bias -> GroupNorm(eps 1e-5) -> ReLU, :36-40) -> ConvT(k2,s2) ->
+    SyncBatchNorm (eval: running stats) -> GELU -> ConvT(k2,s2) -> GELU (:42-48) -> cls_seg =
+    conv_seg(dropout(x)) (mmseg BaseDecodeHead [3P]; Dropout2d is identity in eval).
+    `sd` holds un-prefixed decode_head keys."""
+    x = torch.cat(list(feats), dim=1)
+    x = F.conv2d(x, sd["fusion_conv.conv.weight"])
+    x = F.relu(F.group_norm(x, groups, sd["fusion_conv.gn.weight"], sd["fusion_conv.gn.bias"], 1e-5))
+    x = F.conv_transpose2d(x, sd["output_upscaling.0.weight"], sd["output_upscaling.0.bias"], stride=2)
+    x = F.batch_norm(x, sd["output_upscaling.1.running_mean"], sd["output_upscaling.1.running_var"],
+                     sd["output_upscaling.1.weight"], sd["output_upscaling.1.bias"], False, 0.0, 1e-5)
+    x = F.gelu(x)
+    x = F.conv_transpose2d(x, sd["output_upscaling.3.weight"], sd["output_upscaling.3.bias"], stride=2)
+    x = F.gelu(x)
+    return F.conv2d(x, sd["conv_seg.weight"], sd["conv_seg.bias"])
+
+
+# --------------------------------------------------------------------------- segmentor
+def split_state_dict(sd: Dict[str, Tensor]):
+    """Full LoraBackboneEncoderDecoder state dict -> (backbone, head) dicts with the prefixes
+    'backbone.base_model.model.' (peft naming [3P], Lora_encoder_decoder.py:24,36) / 'decode_head.' removed."""
+    bb, hd = {}, {}
+    for k, v in sd.items():
+        if k.startswith("backbone.base_model.model."):
+            bb[k[len("backbone.base_model.model."):]] = v
+        elif k.startswith("backbone."):
+            bb[k[len("backbone."):]] = v
+        elif k.startswith("decode_head."):
+            hd[k[len("decode_head."):]] = v
+    return bb, hd
+
+
+def encode_decode(x: Tensor, sd, cfg) -> Tensor:
+    """mmseg EncoderDecoder.encode_decode [3P] = decode_head.predict(extract_feat(x)): head forward then
+    predict_by_feat's bilinear resize (align_corners=False) to the input size."""
+    bb, hd = sd
+    feats = dino_forward(x, bb, depth=cfg["depth"], num_heads=cfg["num_heads"], patch=cfg.get("patch", 16),
+                         out_indices=cfg["out_indices"], lora_scale=cfg.get("lora_scale", 1.0))
+    low = linear_head_forward(feats, hd, groups=cfg.get("groups", 32))
+    return F.interpolate(low, size=x.shape[2:], mode="bilinear", align_corners=False), low
+
+
+def slide_inference(inputs: Tensor, sd, cfg, *, crop, stride, return_lowres: bool = False):
+    """mmseg EncoderDecoder.slide_inference [3P]; in-repo verbatim copy
+    rein/models/segmentors/Ms_VFM_encoder_decoder.py:424-461 (grid, F.pad add, count_mat, divide)."""
+    B, _, H, W = inputs.shape
+    preds = None
+    count = inputs.new_zeros((B, 1, H, W))
+    lows = []
+    for (y1, y2, x1, x2) in slide_boxes(H, W, crop, stride):
+        logit, low = encode_decode(inputs[:, :, y1:y2, x1:x2], sd, cfg)
+        lows.append(low)
+        if preds is None:
+            preds = inputs.new_zeros((B, logit.shape[1], H, W))
+        preds += F.pad(logit, (int(x1), int(W - x2), int(y1), int(H - y2)))
+        count[:, :, y1:y2, x1:x2] += 1
+    assert (count == 0).sum() == 0
+    out = preds / count
+    return (out, lows) if return_lowres else out
+
+
+def whole_inference(inputs: Tensor, sd, cfg) -> Tensor:
+    """mmseg EncoderDecoder.whole_inference [3P] = encode_decode on the full image."""
+    return encode_decode(inputs, sd, cfg)[0]
+
+
+def postprocess(seg_logits: Tensor) -> Tensor:
+    """mmseg BaseSegmentor.postprocess_result [3P] with ori_shape == img_shape and no padding:
+    argmax over classes (first maximum wins), int64 [B,1,H,W]."""
+    return seg_logits.argmax(dim=1, keepdim=True)
+
+
+# --------------------------------------------------------------------------- metric (integer/np)
+def intersect_and_union(pred: Tensor, label: Tensor, num_classes: int, ignore_index: int):
+    """mmseg IoUMetric.intersect_and_union [3P] as called from rein/dg_metrics.py:50-52:
+    three float32 histc over the non-ignored pixels."""
+    mask = label != ignore_index
+    pred = pred[mask]
+    label = label[mask]
+    inter = pred[pred == label]
+    area_i = torch.histc(inter.float(), bins=num_classes, min=0, max=num_classes - 1).cpu()
+    area_p = torch.histc(pred.float(), bins=num_classes, min=0, max=num_classes - 1).cpu()
+    area_l = torch.histc(label.float(), bins=num_classes, min=0, max=num_classes - 1).cpu()
+    return area_i, area_p + area_l - area_i, area_p, area_l
+
+
+def confusion_matrix_np(pred: np.ndarray, label: np.ndarray, num_classes: int, ignore_index: int) -> np.ndarray:
+    """Integer restatement: cm[(min(label, nc)), pred] over label != ignore. diag / column sums /
+    row sums reproduce intersect_and_union exactly (int64 instead of float32 counts)."""
+    pred = pred.reshape(-1).astype(np.int64)
+    label = label.reshape(-1).astype(np.int64)
+    keep = label != ignore_index
+    p, l = pred[keep], np.minimum(label[keep], num_classes)
+    ok = p < num_classes
+    cm = np.bincount(l[ok] * num_classes + p[ok], minlength=(num_classes + 1) * num_classes)
+    return cm.reshape(num_classes + 1, num_classes)
+
+
+def areas_from_confusion(cm: np.ndarray, num_classes: int):
+    inter = np.diag(cm[:num_classes]).astype(np.int64)
+    pred = cm.sum(0).astype(np.int64)
+    label = cm[:num_classes].sum(1).astype(np.int64)
+    return inter, pred + label - inter, pred, label
+
+
+def total_area_to_metrics(inter, union, pred, label) -> Dict[str, float]:
+    """mmseg IoUMetric.compute_metrics / total_area_to_metrics [3P] for metrics=['mIoU'], in the
+    reference's float32 tensor arithmetic: aAcc = sum(I)/sum(L); IoU = I/U; Acc = I/L;
+    np.round(np.nanmean(v) * 100, 2)."""
+    f = lambda a: torch.as_tensor(np.asarray(a)).to(torch.float32)
+    inter, union, label = f(inter), f(union), f(label)
+    aacc = (inter.sum() / label.sum()).numpy()
+    iou = (inter / union).numpy()
+    acc = (inter / label).numpy()
+    return {"aAcc": float(np.round(np.nanmean(aacc) * 100, 2)), "mIoU": float(np.round(np.nanmean(iou) * 100, 2)),
+            "mAcc": float(np.round(np.nanmean(acc) * 100, 2))}
