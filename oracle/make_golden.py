@@ -1,0 +1,102 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Generates tests/golden/*.npz by running the REFERENCE's own
+modules (imported unmodified from /root/reference through oracle/ref_shim.py) on the deterministic
+synthetic weights/images of vfmseg_b200.synthetic. Run here (the reference tree does not exist on the
+GPU box):   python -m oracle.make_golden
+
+Files
+  tiny_slide.npz : tiny model (dim 256, depth 4), 1 image 80x112, crop 64 / stride 43 (2x3 windows):
+                   reference slide_inference logits, argmax labels, IoUMetric areas, mIoU summary.
+  tiny_whole.npz : same model, whole_inference on a non-square 64x96 input (bicubic pos-embed path).
+  vitl_crop.npz  : config 1 — DINOv2 ViT-L/16 + LoRA + LinearHead, one 512x512 crop, fp32 CPU:
+                   low-res logits subsampled [:, ::2, ::2] and per-tap statistics.
+Inputs and weights are NOT stored: they are regenerated from seeds (torch CPU generators).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_shim, torch_ref  # noqa: E402
+from vfmseg_b200 import synthetic  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def build_reference(cfg, sd):
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not [m for m in missing if "num_batches_tracked" not in m], missing
+    return model.eval()
+
+
+def tiny_slide():
+    cfg = synthetic.tiny_config()
+    sd = synthetic.synthetic_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd)
+    img = synthetic.synthetic_images(1, 80, 112, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    with torch.no_grad():
+        logits = model.inference(x, [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)])
+        samples = model.postprocess_result(logits.clone())
+    pred = samples[0].pred_sem_seg.data  # int64 [1,H,W]
+    gt = synthetic.synthetic_labels(1, 80, 112, 19, seed=4321)
+    metric_mod = ref_shim.load("dg_metrics")
+    m = metric_mod.DGIoUMetric(dataset_keys=["citys"], ignore_index=255, iou_metrics=["mIoU"])
+    m.dataset_meta = dict(classes=list(range(19)))
+    m.process({}, [dict(pred_sem_seg=dict(data=pred), gt_sem_seg=dict(data=gt[0:1].long()), seg_map_path="x/citys/y.png", img_path="a.png")])
+    key, ai, au, ap, al = m.results[0]
+    summary = m.compute_metrics(m.results)
+    np.savez_compressed(GOLDEN / "tiny_slide.npz", logits=logits.numpy(), labels=pred.numpy().astype(np.uint8),
+                        area_intersect=ai.numpy(), area_union=au.numpy(), area_pred=ap.numpy(), area_label=al.numpy(),
+                        mIoU=np.float64(summary["citys_mIoU"]), mAcc=np.float64(summary["citys_mAcc"]), aAcc=np.float64(summary["citys_aAcc"]))
+    print("tiny_slide", logits.shape, summary)
+
+
+def tiny_whole():
+    cfg = synthetic.tiny_config(mode="whole")
+    sd = synthetic.synthetic_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd)
+    img = synthetic.synthetic_images(1, 64, 96, seed=77)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    with torch.no_grad():
+        logits = model.inference(x, [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)])
+    np.savez_compressed(GOLDEN / "tiny_whole.npz", logits=logits.numpy())
+    print("tiny_whole", logits.shape)
+
+
+def vitl_crop():
+    cfg = synthetic.model_config()
+    sd = synthetic.synthetic_state_dict(cfg, seed=0)
+    model = build_reference(cfg, sd)
+    img = synthetic.synthetic_images(1, 512, 512, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    t0 = time.time()
+    with torch.no_grad():
+        feats = model.extract_feat(x)
+        low = model.decode_head(feats)
+    print(f"vitl_crop reference forward {time.time() - t0:.1f}s", low.shape)
+    stats = np.array([[f.mean().item(), f.std().item(), f.abs().max().item()] for f in feats], dtype=np.float64)
+    np.savez_compressed(GOLDEN / "vitl_crop.npz", lowres_sub=low[0, :, ::2, ::2].numpy(), tap_stats=stats,
+                        lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8))
+
+
+if __name__ == "__main__":
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop"]
+    for w in which:
+        globals()[w]()

@@ -1,0 +1,106 @@
+"""CPU: the oracle restatement (oracle/torch_ref.py) against the golden vectors produced by the
+reference's OWN modules (oracle/make_golden.py), and against the live reference when the tree exists."""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, torch_ref
+from vfmseg_b200 import synthetic
+
+GOLDEN = Path(__file__).parent / "golden"
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def _cfg_of(cfg):
+    bb, lc = cfg["backbone"], cfg["Lora_config"]
+    return dict(depth=bb["depth"], num_heads=bb["num_heads"], patch=bb["patch_size"], out_indices=tuple(bb["out_indices"]),
+                lora_scale=lc["lora_alpha"] / lc["r"], groups=cfg["decode_head"]["norm_cfg"]["num_groups"])
+
+
+def _oracle_model(cfg, seed=0):
+    sd = synthetic.synthetic_state_dict(cfg, seed=seed)
+    return torch_ref.split_state_dict(sd), _cfg_of(cfg)
+
+
+def test_slide_boxes_match_survey():
+    boxes = torch_ref.slide_boxes(1024, 2048, (512, 512), (341, 341))
+    assert len(boxes) == 18
+    assert sorted({b[0] for b in boxes}) == [0, 341, 512]
+    assert sorted({b[2] for b in boxes}) == [0, 341, 682, 1023, 1364, 1536]
+    assert len(torch_ref.slide_boxes(1024, 2048, (512, 512), (320, 320))) == 18
+    assert torch_ref.slide_boxes(64, 64, (64, 64), (43, 43)) == [(0, 64, 0, 64)]
+
+
+def test_tiny_slide_against_reference_golden():
+    g = np.load(GOLDEN / "tiny_slide.npz")
+    cfg = synthetic.tiny_config()
+    sd, oc = _oracle_model(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 80, 112, seed=1234), MEAN, STD, True)
+    with torch.no_grad():
+        logits = torch_ref.slide_inference(x, sd, oc, crop=(64, 64), stride=(43, 43))
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=1e-4)
+    labels = torch_ref.postprocess(logits)[0].numpy().astype(np.uint8)
+    assert (labels == g["labels"]).mean() >= 0.9995
+    # metric: identical prediction map -> bit-exact areas and summary
+    gt = synthetic.synthetic_labels(1, 80, 112, 19, seed=4321)
+    pred = torch.from_numpy(g["labels"].astype(np.int64))
+    ai, au, ap, al = torch_ref.intersect_and_union(pred, gt.long(), 19, 255)
+    for a, k in ((ai, "area_intersect"), (au, "area_union"), (ap, "area_pred"), (al, "area_label")):
+        assert np.array_equal(a.numpy(), g[k]), k
+    cm = torch_ref.confusion_matrix_np(g["labels"], gt.numpy(), 19, 255)
+    ci, cu, cp, cl = torch_ref.areas_from_confusion(cm, 19)
+    assert np.array_equal(ci, g["area_intersect"].astype(np.int64)) and np.array_equal(cu, g["area_union"].astype(np.int64))
+    assert np.array_equal(cp, g["area_pred"].astype(np.int64)) and np.array_equal(cl, g["area_label"].astype(np.int64))
+    s = torch_ref.total_area_to_metrics(ci, cu, cp, cl)
+    assert s["mIoU"] == pytest.approx(float(g["mIoU"]), abs=1e-6)
+    assert s["mAcc"] == pytest.approx(float(g["mAcc"]), abs=1e-6)
+    assert s["aAcc"] == pytest.approx(float(g["aAcc"]), abs=1e-6)
+
+
+def test_tiny_whole_nonsquare_against_reference_golden():
+    g = np.load(GOLDEN / "tiny_whole.npz")
+    cfg = synthetic.tiny_config(mode="whole")
+    sd, oc = _oracle_model(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 64, 96, seed=77), MEAN, STD, True)
+    with torch.no_grad():
+        logits = torch_ref.whole_inference(x, sd, oc)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=1e-4)
+
+
+def test_vitl_crop_against_reference_golden():
+    """Config 1: DINOv2 ViT-L/16 + LoRA + LinearHead, one 512x512 crop, fp32 on CPU."""
+    g = np.load(GOLDEN / "vitl_crop.npz")
+    cfg = synthetic.model_config()
+    (bb, hd), oc = _oracle_model(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 512, 512, seed=1234), MEAN, STD, True)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        feats = torch_ref.dino_forward(x, bb, depth=oc["depth"], num_heads=oc["num_heads"], out_indices=oc["out_indices"],
+                                       lora_scale=oc["lora_scale"])
+        low = torch_ref.linear_head_forward(feats, hd)
+    stats = np.array([[f.mean().item(), f.std().item(), f.abs().max().item()] for f in feats])
+    np.testing.assert_allclose(stats, g["tap_stats"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(low[0, :, ::2, ::2].numpy(), g["lowres_sub"], rtol=2e-3, atol=2e-3)
+    assert (low[0].argmax(0).numpy() == g["lowres_argmax"]).mean() >= 0.999
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_against_live_reference_modules():
+    """Different seed / shapes than the goldens, straight against the reference's classes."""
+    import tempfile
+    cfg = synthetic.tiny_config(stride=(32, 32))
+    sd = synthetic.synthetic_state_dict(cfg, seed=5)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "bb.pth")
+        torch.save(synthetic.backbone_checkpoint_from(sd), ck)
+        ref = ref_shim.build_reference_segmentor(cfg, ck)
+    ref.load_state_dict(sd, strict=False)
+    x = torch_ref.preprocess(synthetic.synthetic_images(2, 96, 96, seed=9), MEAN, STD, True)
+    meta = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)] * 2
+    with torch.no_grad():
+        want = ref.inference(x, meta)
+        got = torch_ref.slide_inference(x, torch_ref.split_state_dict(sd), _cfg_of(cfg), crop=(64, 64), stride=(32, 32))
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)

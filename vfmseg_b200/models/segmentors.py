@@ -1,0 +1,173 @@
+"""`LoraBackboneEncoderDecoder` — registered segmentor mirroring
+rein/models/segmentors/Lora_encoder_decoder.py:12-36 on top of mmseg's EncoderDecoder contract
+(predict / inference / slide_inference / whole_inference / encode_decode / extract_feat;
+SURVEY.md Appendix A1-A3), with the whole slide loop executed by the sm_100a engine:
+
+  reference, per image : 18 x (crop slice -> backbone -> head -> resize -> F.pad add) -> divide -> argmax
+  here                 : one gather of all windows -> batched backbone/head -> one merge+argmax kernel
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from ..engine import PackedLinearHead, PackedVit, SlideEngine
+from ..registry import MODELS, ConfigDict
+from ..structures import PixelData, SegDataSample
+from .lora import LoraConfig, get_peft_model
+
+
+@MODELS.register_module()
+class SegDataPreProcessor(nn.Module):
+    """mmseg SegDataPreProcessor (test mode) as configured at configs/_base_/models/lora_dinov2_linear.py:13-21.
+    Stacks the uint8 images and moves them to the device; the channel flip and (x-mean)/std are applied
+    inside the patch-gather kernel, so no normalised fp32 image is ever materialised."""
+
+    def __init__(self, mean=None, std=None, size=None, size_divisor=None, pad_val=0, seg_pad_val=255, bgr_to_rgb=False,
+                 rgb_to_bgr=False, batch_augments=None, test_cfg=None, **unused):
+        super().__init__()
+        assert not (bgr_to_rgb and rgb_to_bgr)
+        self.mean = list(mean) if mean is not None else [0.0, 0.0, 0.0]
+        self.std = list(std) if std is not None else [1.0, 1.0, 1.0]
+        self.channel_conversion = bool(bgr_to_rgb or rgb_to_bgr)
+        self.register_buffer("_dummy", torch.zeros(0), persistent=False)  # tracks the module's device
+
+    def forward(self, data: dict, training: bool = False) -> dict:
+        assert not training, "vfmseg_b200 covers the inference path only"
+        inputs = data["inputs"]
+        if isinstance(inputs, (list, tuple)):
+            inputs = torch.stack(list(inputs), dim=0)
+        return dict(inputs=inputs.to(self._dummy.device, non_blocking=True).contiguous(), data_samples=data.get("data_samples"))
+
+
+@MODELS.register_module()
+class LoraBackboneEncoderDecoder(nn.Module):
+    def __init__(self, checkpoint=None, Lora_config=None, *, backbone, decode_head, neck=None, auxiliary_head=None,
+                 train_cfg=None, test_cfg=None, data_preprocessor=None, pretrained=None, init_cfg=None,
+                 max_crops_per_pass: int = 36):
+        super().__init__()
+        if neck is not None or auxiliary_head is not None:
+            raise NotImplementedError("neck / auxiliary_head are not part of the LoRA slide-inference configs")
+        self.backbone = MODELS.build(backbone)
+        self.decode_head = MODELS.build(decode_head)
+        self.align_corners = self.decode_head.align_corners
+        self.num_classes = self.decode_head.num_classes
+        self.out_channels = self.decode_head.out_channels
+        self.train_cfg = ConfigDict(train_cfg or {})
+        self.test_cfg = ConfigDict(test_cfg or {})
+        self.data_preprocessor = MODELS.build(data_preprocessor) if isinstance(data_preprocessor, dict) else data_preprocessor
+        self.max_crops_per_pass = max_crops_per_pass
+        if Lora_config is not None:
+            self.Lora_config = LoraConfig(r=Lora_config["r"], lora_alpha=Lora_config["lora_alpha"],
+                                          target_modules=Lora_config["target_modules"],
+                                          lora_dropout=Lora_config.get("lora_dropout", 0.0), bias="none")
+            self.backbone = get_peft_model(self.backbone, self.Lora_config)   # Lora_encoder_decoder.py:24
+            if checkpoint is not None:
+                self.load_pretrained_backbone(checkpoint, Lora_config["target_modules"])
+        self._engine: Optional[SlideEngine] = None
+        self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
+
+    # ------------------------------------------------------------------ weights
+    def load_pretrained_backbone(self, checkpoint, target_modules):
+        """Lora_encoder_decoder.py:28-36: plain backbone checkpoint, target modules renamed to '<t>.base_layer'."""
+        original = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, str) else checkpoint
+        new = {}
+        for name, weight in original.items():
+            for t in target_modules:
+                if t in name:
+                    name = name.replace(t, t + ".base_layer")
+                new[name] = weight
+        self.inner_backbone.load_state_dict(new, strict=False)
+        self.invalidate()
+
+    @property
+    def inner_backbone(self):
+        b = self.backbone
+        return b.base_model.model if hasattr(b, "base_model") else b
+
+    def invalidate(self):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self) -> SlideEngine:
+        if self._engine is None:
+            bb = self.inner_backbone
+            dev = bb.cls_token.device
+            if dev.type != "cuda":
+                raise RuntimeError("vfmseg_b200 runs on CUDA (sm_100a) only: call .cuda(); there is no CPU path")
+            eng = SlideEngine(bb.packed(dev), self.decode_head.packed(), self.max_crops_per_pass)
+            if self.data_preprocessor is not None:
+                eng.set_pixel_norm(self.data_preprocessor.mean, self.data_preprocessor.std, self.data_preprocessor.channel_conversion)
+            self._engine = eng
+        return self._engine
+
+    # ------------------------------------------------------------------ mmseg EncoderDecoder contract
+    def extract_feat(self, inputs: torch.Tensor) -> List[torch.Tensor]:
+        return self.backbone(inputs)
+
+    def encode_decode(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        """Whole-window forward: logits resized to the input size."""
+        _, logits, _ = self.engine().whole(self._as_input(inputs), want_logits=True)
+        return logits
+
+    def slide_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        _, logits, _ = self.engine().slide(self._as_input(inputs), self.test_cfg.crop_size, self.test_cfg.stride, want_logits=True)
+        return logits
+
+    def whole_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        return self.encode_decode(inputs, batch_img_metas)
+
+    def inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        mode = self.test_cfg.get("mode", "whole")
+        assert mode in ("slide", "whole"), f'Only "slide" or "whole" test mode are supported, but got {mode}.'
+        return self.slide_inference(inputs, batch_img_metas) if mode == "slide" else self.whole_inference(inputs, batch_img_metas)
+
+    @staticmethod
+    def _as_input(inputs: torch.Tensor) -> torch.Tensor:
+        if inputs.dtype not in (torch.uint8, torch.float32):
+            inputs = inputs.float()
+        return inputs.contiguous()
+
+    def predict_labels(self, inputs: torch.Tensor, want_logits: bool = False):
+        """Throughput path: uint8 label maps [B,H,W] (argmax fused into the merge kernel); the 159 MB/image
+        fp32 logits are only produced when asked for."""
+        mode = self.test_cfg.get("mode", "whole")
+        eng = self.engine()
+        x = self._as_input(inputs)
+        if mode == "slide":
+            labels, logits, _ = eng.slide(x, self.test_cfg.crop_size, self.test_cfg.stride, want_logits=want_logits)
+        else:
+            labels, logits, _ = eng.whole(x, want_logits=want_logits)
+        return labels, logits
+
+    def predict(self, inputs: torch.Tensor, data_samples: Optional[Sequence[SegDataSample]] = None) -> List[SegDataSample]:
+        """mmseg BaseSegmentor.predict + postprocess_result for un-padded, un-resized inputs
+        (ori_shape == img_shape, which is what the reference's Cityscapes test pipeline produces)."""
+        labels, logits = self.predict_labels(inputs, want_logits=True)
+        B, H, W = labels.shape
+        if data_samples is None:
+            data_samples = [SegDataSample(metainfo=dict(ori_shape=(H, W), img_shape=(H, W))) for _ in range(B)]
+        for i, s in enumerate(data_samples):
+            meta = getattr(s, "metainfo", {})
+            ori = tuple(meta.get("ori_shape", (H, W)))[:2]
+            pad = meta.get("padding_size", [0, 0, 0, 0])
+            if ori != (H, W) or any(pad):
+                raise NotImplementedError("predict(): padded / resized test inputs are outside the slide-inference path")
+            s.set_data({"seg_logits": PixelData(data=logits[i]), "pred_sem_seg": PixelData(data=labels[i:i + 1].long())})
+        return list(data_samples)
+
+    def forward(self, inputs, data_samples=None, mode="predict"):
+        if mode == "predict":
+            return self.predict(inputs, data_samples)
+        if mode == "tensor":
+            return self.inference(inputs, None)
+        raise NotImplementedError("mode='loss' (training) is out of scope for vfmseg_b200")
+
+    def test_step(self, data: dict):
+        data = self.data_preprocessor(data, False) if self.data_preprocessor is not None else data
+        return self.predict(data["inputs"], data.get("data_samples"))

@@ -164,3 +164,12 @@ def confusion_matrix_(cm, pred, label, num_classes, ignore_index=255):
     _C.call("vfm_confusion_matrix", _ptr(pred), _ptr(label), pred.numel(), num_classes, ignore_index, _ptr(cm),
             _stream())
     return cm
+
+
+def resize_bilinear(low, size):
+    """Bilinear (align_corners=False) resize of fp32 [B,nc,h,w] logits to `size`, through the merge
+    kernel with one window covering the whole output (mmseg predict_by_feat / resize)."""
+    B = low.shape[0]
+    boxes = torch.zeros(1, 2, dtype=torch.int32, device=low.device)
+    _, logits = slide_merge_argmax(low.contiguous(), boxes, B, tuple(size), tuple(size), want_logits=True)
+    return logits

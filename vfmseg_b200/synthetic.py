@@ -1,0 +1,147 @@
+"""Deterministic synthetic weights, images and labels (there are no checkpoints or datasets here).
+
+The reference's default initialisation would make parity vacuous — cls_token / pos_embed are zeros
+(rein/models/backbones/dino_v2.py:123-126), LayerScale gamma is 1e-5
+(configs/_base_/models/lora_dinov2_linear.py:31) and peft's LoRA B is zeros — so every tensor is
+drawn from a distribution that actually exercises the kernels. The state dict uses
+the reference's key names, so the same dict loads into the reference modules (oracle) and into
+vfmseg_b200's registered classes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+
+def model_config(embed_dim=1024, depth=24, num_heads=16, img_size=512, out_indices=(7, 11, 15, 23), num_classes=19,
+                 crop_size=(512, 512), stride=(341, 341), lora_r=32, lora_alpha=32, mode="slide", gn_groups=32) -> dict:
+    """A config dict shaped like configs/_base_/models/lora_dinov2_linear.py:4-55 (same `type=` names)."""
+    return dict(
+        type="LoraBackboneEncoderDecoder",
+        checkpoint=None,
+        Lora_config=dict(r=lora_r, lora_alpha=lora_alpha, target_modules=["qkv"], lora_dropout=0.1),
+        data_preprocessor=dict(type="SegDataPreProcessor", mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375],
+                               size=tuple(crop_size), bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
+        backbone=dict(type="DinoVisionTransformer", patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads,
+                      mlp_ratio=4, img_size=img_size, ffn_layer="mlp", init_values=1e-05, block_chunks=0, qkv_bias=True,
+                      proj_bias=True, ffn_bias=True, out_indices=list(out_indices)),
+        decode_head=dict(type="LinearHead", in_channels=[embed_dim] * len(out_indices), in_index=list(range(len(out_indices))),
+                         channels=embed_dim // 4, dropout_ratio=0.1, num_classes=num_classes,
+                         norm_cfg=dict(type="GN", num_groups=gn_groups), align_corners=False,
+                         loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0)),
+        train_cfg=dict(),
+        test_cfg=dict(mode=mode, stride=list(stride), crop_size=list(crop_size)),
+    )
+
+
+def tiny_config(**kw) -> dict:
+    """Small model for fast CPU oracle runs: dim 256 (4 heads), depth 4, 64x64 crops."""
+    d = dict(embed_dim=256, depth=4, num_heads=4, img_size=64, out_indices=(0, 1, 2, 3), crop_size=(64, 64),
+             stride=(43, 43), lora_r=8, lora_alpha=16, gn_groups=32)
+    d.update(kw)
+    return model_config(**d)
+
+
+def synthetic_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Full segmentor state dict (keys as in the reference: 'backbone.base_model.model.*' because the
+    backbone is peft-wrapped inside the segmentor, Lora_encoder_decoder.py:24; 'decode_head.*')."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    bb, hd, lc = cfg["backbone"], cfg["decode_head"], cfg["Lora_config"]
+    C, depth, P = bb["embed_dim"], bb["depth"], bb["patch_size"]
+    hidden = int(C * bb["mlp_ratio"])
+    n_pos = (bb["img_size"] // P) ** 2
+    r = lc["r"]
+
+    def normal(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    def uniform(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+    sd: Dict[str, torch.Tensor] = {}
+    p = "backbone.base_model.model."
+    sd[p + "cls_token"] = normal(1, 1, C, std=0.1)
+    sd[p + "pos_embed"] = normal(1, 1 + n_pos, C, std=0.1)
+    sd[p + "mask_token"] = torch.zeros(1, C)
+    sd[p + "patch_embed.proj.weight"] = normal(C, 3, P, P)
+    sd[p + "patch_embed.proj.bias"] = normal(C)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        sd[b + "norm1.weight"] = uniform(C, lo=0.5, hi=1.5)
+        sd[b + "norm1.bias"] = normal(C, std=0.1)
+        sd[b + "attn.qkv.base_layer.weight"] = normal(3 * C, C)
+        # queries/keys a little hotter than 0.02 so the softmax is not uniform
+        sd[b + "attn.qkv.base_layer.weight"][: 2 * C] *= 2.0
+        sd[b + "attn.qkv.base_layer.bias"] = normal(3 * C)
+        bound = 1.0 / math.sqrt(C)  # kaiming_uniform(a=sqrt(5)) bound, as peft initialises lora_A
+        sd[b + "attn.qkv.lora_A.default.weight"] = uniform(r, C, lo=-bound, hi=bound)
+        sd[b + "attn.qkv.lora_B.default.weight"] = normal(3 * C, r)
+        sd[b + "attn.proj.weight"] = normal(C, C)
+        sd[b + "attn.proj.bias"] = normal(C)
+        sd[b + "ls1.gamma"] = uniform(C, lo=0.05, hi=0.5)
+        sd[b + "norm2.weight"] = uniform(C, lo=0.5, hi=1.5)
+        sd[b + "norm2.bias"] = normal(C, std=0.1)
+        sd[b + "mlp.fc1.weight"] = normal(hidden, C)
+        sd[b + "mlp.fc1.bias"] = normal(hidden)
+        sd[b + "mlp.fc2.weight"] = normal(C, hidden)
+        sd[b + "mlp.fc2.bias"] = normal(C)
+        sd[b + "ls2.gamma"] = uniform(C, lo=0.05, hi=0.5)
+    sd[p + "norm.weight"] = torch.ones(C)
+    sd[p + "norm.bias"] = torch.zeros(C)
+
+    h = "decode_head."
+    n_in = sum(hd["in_channels"])
+    mid = hd["in_channels"][0]
+    ch = hd["channels"]
+    nc = hd["num_classes"]
+    assert ch == mid // 4, "LinearHead: conv_seg input channels (channels) must equal in_channels[0] // 4"
+    sd[h + "fusion_conv.conv.weight"] = normal(mid, n_in, 1, 1, std=n_in ** -0.5)
+    sd[h + "fusion_conv.gn.weight"] = uniform(mid, lo=0.5, hi=1.5)
+    sd[h + "fusion_conv.gn.bias"] = normal(mid, std=0.1)
+    sd[h + "output_upscaling.0.weight"] = normal(mid, mid // 2, 2, 2, std=mid ** -0.5)
+    sd[h + "output_upscaling.0.bias"] = normal(mid // 2)
+    sd[h + "output_upscaling.1.weight"] = uniform(mid // 2, lo=0.5, hi=1.5)
+    sd[h + "output_upscaling.1.bias"] = normal(mid // 2, std=0.1)
+    sd[h + "output_upscaling.1.running_mean"] = normal(mid // 2, std=0.1)
+    sd[h + "output_upscaling.1.running_var"] = uniform(mid // 2, lo=0.5, hi=2.0)
+    sd[h + "output_upscaling.1.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    sd[h + "output_upscaling.3.weight"] = normal(mid // 2, mid // 4, 2, 2, std=(mid // 2) ** -0.5)
+    sd[h + "output_upscaling.3.bias"] = normal(mid // 4)
+    sd[h + "conv_seg.weight"] = normal(nc, ch, 1, 1, std=2.0 * ch ** -0.5)
+    sd[h + "conv_seg.bias"] = normal(nc, std=0.1)
+    return sd
+
+
+def backbone_checkpoint_from(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The 'checkpoints/dinov2_converted.pth'-style dict the reference's __init__ loads
+    (Lora_encoder_decoder.py:28-36): plain backbone keys, no LoRA tensors."""
+    out = {}
+    p = "backbone.base_model.model."
+    for k, v in sd.items():
+        if k.startswith(p) and "lora_" not in k:
+            out[k[len(p):].replace(".base_layer", "")] = v
+    return out
+
+
+def synthetic_images(n: int, H: int, W: int, seed: int = 1234) -> torch.Tensor:
+    """uint8 BGR [n,3,H,W]: uniform noise low-pass filtered (8x8 average, bilinear back up) plus a
+    little per-pixel noise, so neighbouring windows differ smoothly and pixels are not all alike."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    hs, ws = max(H // 8, 1), max(W // 8, 1)
+    coarse = torch.rand(n, 3, hs, ws, generator=g) * 255.0
+    img = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=False)
+    img = img + (torch.rand(n, 3, H, W, generator=g) - 0.5) * 32.0
+    return img.clamp_(0, 255).round_().to(torch.uint8)
+
+
+def synthetic_labels(n: int, H: int, W: int, num_classes: int = 19, seed: int = 4321, ignore_frac: float = 0.05) -> torch.Tensor:
+    """uint8 [n,H,W]: piecewise-constant class map (16x16 blocks) with ~5 % ignore (255) pixels."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    hs, ws = (H + 15) // 16, (W + 15) // 16
+    blocks = torch.randint(0, num_classes, (n, hs, ws), generator=g)
+    lab = blocks.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :H, :W].contiguous()
+    ign = torch.rand(n, H, W, generator=g) < ignore_frac
+    lab[ign] = 255
+    return lab.to(torch.uint8)
