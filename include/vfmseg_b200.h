@@ -38,6 +38,11 @@ const char* vfm_last_error(void);
 int vfm_abi_version(void);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
 long long vfm_launch_count(void);
+/* Per-launch timing for bench.py's roofline leg: while enabled every kernel launch is bracketed by
+ * CUDA events on its own stream. vfm_prof_report synchronises the device and writes one
+ * "name,launches,total_ms\n" line per kernel family into buf (host), then clears the records. */
+int vfm_prof_enable(int on);
+int vfm_prof_report(char* buf /*host*/, size_t buf_bytes);
 /* 0 when the current CUDA device can run this library (compute capability 10.x). */
 int vfm_device_check(void);
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "vfm_abi_version": (_i, []),
     "vfm_launch_count": (_ll, []),
     "vfm_device_check": (_i, []),
+    "vfm_prof_enable": (_i, [_i]),
+    "vfm_prof_report": (_i, [C.c_char_p, _sz]),
     "vfm_gemm_bias_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_bias_gelu_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_bias_ls_residual": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -6,6 +6,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "attention_sm100.cuh"
 #include "elementwise.cuh"
@@ -32,6 +37,31 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (expr);                                                                    \
     if (e_ != cudaSuccess) return fail(VFM_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
   } while (0)
+
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launch stream ----
+struct ProfRec { const char* name; cudaEvent_t start, stop; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+
+// Brackets one kernel launch: counts it and, when profiling is on, records start/stop events.
+struct LaunchScope {
+  const char* name; cudaStream_t st; cudaEvent_t start = nullptr, stop = nullptr;
+  LaunchScope(const char* n, cudaStream_t s) : name(n), st(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_pool.empty()) { start = g_prof_pool.back().first; stop = g_prof_pool.back().second; g_prof_pool.pop_back(); }
+    else if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) { start = stop = nullptr; return; }
+    cudaEventRecord(start, st);
+  }
+  ~LaunchScope() {
+    if (!start) return;
+    cudaEventRecord(stop, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back({name, start, stop});
+  }
+};
 
 #define VFM_LAUNCH_CHECK(name)                                                                  \
   do {                                                                                          \
@@ -109,7 +139,10 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   const int grid = tiles < sms ? tiles : sms;
   // K tail (K % 64 != 0) is covered by TMA zero fill of both operands.
   const int K_pad = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K * GEMM_BLOCK_K;
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K_pad, epi);
+  {
+    LaunchScope scope(name, st);
+    kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K_pad, epi);
+  }
   VFM_LAUNCH_CHECK(name);
   return VFM_OK;
 }
@@ -127,6 +160,39 @@ extern "C" {
 const char* vfm_last_error(void) { return g_err; }
 int vfm_abi_version(void) { return VFM_ABI_VERSION; }
 long long vfm_launch_count(void) { return g_launches.load(); }
+
+int vfm_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return VFM_OK;
+}
+
+// Synchronises the device, folds all recorded launches into "name,count,total_ms" lines, clears the records.
+int vfm_prof_report(char* buf, size_t buf_bytes) {
+  if (!buf || buf_bytes == 0) return fail(VFM_ERR_INVALID, "prof_report: null buffer");
+  VFM_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+      auto& a = agg[r.name];
+      a.first += 1;
+      a.second += ms;
+    }
+    g_prof_pool.emplace_back(r.start, r.stop);
+  }
+  g_prof_recs.clear();
+  std::string out;
+  char line[160];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s,%lld,%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (out.size() + 1 > buf_bytes) return fail(VFM_ERR_INVALID, "prof_report: buffer too small (%zu needed)", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return VFM_OK;
+}
 
 int vfm_device_check(void) {
   int dev = 0, major = 0;
@@ -204,8 +270,11 @@ int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int he
   const int q_tiles = (seq_len + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
   const long long grid = static_cast<long long>(n_seq) * heads * q_tiles;
   if (grid > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention_fwd: grid too large");
-  attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, S(stream)>>>(tq, BF(out), seq_len,
-                                                                                              heads, q_tiles);
+  {
+    LaunchScope scope("attention_fwd", S(stream));
+    attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, S(stream)>>>(tq, BF(out), seq_len,
+                                                                                                heads, q_tiles);
+  }
   VFM_LAUNCH_CHECK("attention_fwd");
   return VFM_OK;
 }
@@ -223,12 +292,15 @@ int vfm_patch_gather(const void* img, int is_u8, const VfmPixelNorm* nrm, int im
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  if (is_u8)
-    patch_gather_kernel<uint8_t><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
-        reinterpret_cast<const uint8_t*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
-  else
-    patch_gather_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
-        reinterpret_cast<const float*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
+{
+    LaunchScope scope("patch_gather", S(stream));
+    if (is_u8)
+      patch_gather_kernel<uint8_t><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
+          reinterpret_cast<const uint8_t*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
+    else
+      patch_gather_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(
+          reinterpret_cast<const float*>(img), img_h, img_w, reinterpret_cast<const int4*>(crops), n_crops, gh, gw, pn, BF(out));
+  }
   VFM_LAUNCH_CHECK("patch_gather");
   return VFM_OK;
 }
@@ -236,7 +308,10 @@ int vfm_patch_gather(const void* img, int is_u8, const VfmPixelNorm* nrm, int im
 int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops, int tokens, int C, void* stream) {
   if (!x || !cls_token || !pos) return fail(VFM_ERR_INVALID, "cls_rows: null");
   const int n = n_crops * C;
-  cls_rows_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(x, cls_token, pos, n_crops, tokens, C);
+{
+    LaunchScope scope("cls_rows", S(stream));
+    cls_rows_kernel<<<(n + 255) / 256, 256, 0, S(stream)>>>(x, cls_token, pos, n_crops, tokens, C);
+  }
   VFM_LAUNCH_CHECK("cls_rows");
   return VFM_OK;
 }
@@ -247,10 +322,13 @@ int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* o
   if (C % 128 || C < 128 || C > 1024) return fail(VFM_ERR_INVALID, "layernorm: C must be a multiple of 128 in [128,1024] (C=%d)", C);
   const int grid = (M + 7) / 8;
   cudaStream_t st = S(stream);
-  switch (C / 128) {
-#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps); break;
-    VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
-#undef VFM_LN_CASE
+{
+    LaunchScope scope("layernorm", st);
+    switch (C / 128) {
+  #define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps); break;
+      VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
+  #undef VFM_LN_CASE
+    }
   }
   VFM_LAUNCH_CHECK("layernorm");
   return VFM_OK;
@@ -260,7 +338,10 @@ int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const floa
                        int groups, float eps, int relu, void* stream) {
   if (!in || !out || !gamma || !beta || n_crops <= 0 || P <= 0 || groups <= 0 || C % groups || (C / groups) % 8)
     return fail(VFM_ERR_INVALID, "groupnorm_relu: bad args (C/groups must be a multiple of 8)");
-  groupnorm_relu_kernel<<<n_crops * groups, 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, P, C, groups, eps, relu);
+{
+    LaunchScope scope("groupnorm_relu", S(stream));
+    groupnorm_relu_kernel<<<n_crops * groups, 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, P, C, groups, eps, relu);
+  }
   VFM_LAUNCH_CHECK("groupnorm_relu");
   return VFM_OK;
 }
@@ -274,12 +355,15 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
   const long long cap = static_cast<long long>(sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   const size_t smem = sizeof(int2) * n_crops;
-  if (nc <= 19)
-    slide_merge_argmax_kernel<19><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
-        lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
-  else
-    slide_merge_argmax_kernel<32><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
-        lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
+{
+    LaunchScope scope("slide_merge_argmax", S(stream));
+    if (nc <= 19)
+      slide_merge_argmax_kernel<19><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
+          lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
+    else
+      slide_merge_argmax_kernel<32><<<static_cast<unsigned>(blocks), 256, smem, S(stream)>>>(
+          lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
+  }
   VFM_LAUNCH_CHECK("slide_merge_argmax");
   return VFM_OK;
 }
@@ -294,8 +378,11 @@ int vfm_confusion_matrix(const uint8_t* pred, const uint8_t* label, long long n,
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  confusion_matrix_kernel<<<static_cast<unsigned>(blocks), 256, sizeof(int) * (nc + 1) * nc, S(stream)>>>(
-      pred, label, n, nc, ignore_index, reinterpret_cast<unsigned long long*>(cm));
+{
+    LaunchScope scope("confusion_matrix", S(stream));
+    confusion_matrix_kernel<<<static_cast<unsigned>(blocks), 256, sizeof(int) * (nc + 1) * nc, S(stream)>>>(
+        pred, label, n, nc, ignore_index, reinterpret_cast<unsigned long long*>(cm));
+  }
   VFM_LAUNCH_CHECK("confusion_matrix");
   return VFM_OK;
 }
