@@ -209,17 +209,23 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(W):
         step_resident(i)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local) if rank == 0 else None
     cm.zero_()
     l0 = lib.vfm_launch_count()
     ms_total = timed(step_resident, K)
     launches = lib.vfm_launch_count() - l0
     clocks = sampler.stop() if sampler else None
     cm_value = cm.clone()
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_total / K, "images_per_s": world * B * K / (ms_total / 1e3), "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- e2e: host uint8 images in, host labels + confusion matrix out, through the public segmentor call
     in_dev = torch.empty_like(pool_dev[0])
@@ -310,14 +316,15 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--images-per-step", type=int, default=2)
     ap.add_argument("--crops-per-pass", type=int, default=36)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: resident-input leg only, warm-up as given (not a bench number)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
+    if args.warmup < 3 and args.impl == "b200" and not args.quick:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -1,0 +1,175 @@
+"""CPU: host-side logic — registry/config drop-in surface, state-dict naming (peft layout), slide grid,
+weight folding, C-ABI symbol table, metric reduction. No GPU compute is issued."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import vfmseg_b200
+from oracle import torch_ref
+from vfmseg_b200 import _C, engine, synthetic
+from vfmseg_b200.dg_metrics import DGIoUMetric, areas_from_confusion, total_area_to_metrics
+from vfmseg_b200.registry import BACKBONES, METRICS, MODELS, Registry
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_registry_surface_matches_reference_usage():
+    assert BACKBONES is MODELS   # mmseg.models.builder.BACKBONES is MODELS
+    for name in ("DinoVisionTransformer", "LinearHead", "LoraBackboneEncoderDecoder", "SegDataPreProcessor"):
+        assert MODELS.get(name) is not None
+    assert METRICS.get("DGIoUMetric") is DGIoUMetric
+    r = Registry("x")
+
+    @r.register_module()
+    class Foo:
+        def __init__(self, a, b=2):
+            self.a, self.b = a, b
+    f = r.build(dict(type="Foo", a=1))
+    assert (f.a, f.b) == (1, 2)
+    with pytest.raises(KeyError):
+        r.build(dict(type="Nope"))
+    with pytest.raises(KeyError):
+        r.register_module(name="Foo")(type("Bar", (), {}))
+
+
+def test_reference_config_builds_and_state_dict_names_match_peft_layout():
+    cfg = synthetic.tiny_config()
+    model = MODELS.build(dict(cfg))
+    sd = synthetic.synthetic_state_dict(cfg, seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert unexpected == [] and missing == []
+    keys = set(model.state_dict())
+    assert "backbone.base_model.model.blocks.0.attn.qkv.base_layer.weight" in keys
+    assert "backbone.base_model.model.blocks.0.attn.qkv.lora_A.default.weight" in keys
+    assert "backbone.base_model.model.blocks.3.attn.qkv.lora_B.default.weight" in keys
+    assert "decode_head.fusion_conv.conv.weight" in keys and "decode_head.fusion_conv.gn.bias" in keys
+    assert "decode_head.output_upscaling.1.running_var" in keys and "decode_head.conv_seg.bias" in keys
+    assert "decode_head.fusion_conv.conv.bias" not in keys   # mmcv ConvModule: no conv bias when a norm follows
+    assert model.align_corners is False and model.num_classes == 19 and model.out_channels == 19
+    assert model.test_cfg.mode == "slide" and model.test_cfg.crop_size == [64, 64]
+    # the plain-backbone checkpoint route of Lora_encoder_decoder.py:28-36
+    m2 = MODELS.build(dict(cfg))
+    m2.load_pretrained_backbone(synthetic.backbone_checkpoint_from(sd), ["qkv"])
+    a = m2.state_dict()["backbone.base_model.model.blocks.1.attn.qkv.base_layer.weight"]
+    assert torch.equal(a, sd["backbone.base_model.model.blocks.1.attn.qkv.base_layer.weight"])
+    assert m2.state_dict()["backbone.base_model.model.blocks.1.attn.qkv.lora_B.default.weight"].abs().max() == 0  # peft init
+
+
+def test_full_size_config_has_reference_shapes():
+    cfg = synthetic.model_config()
+    model = MODELS.build(dict(cfg))
+    n = sum(p.numel() for p in model.backbone.parameters())
+    assert abs(n - 304.2e6 - 24 * 32 * (1024 + 3072)) < 1.0e6   # 304.2 M backbone + LoRA r=32
+    sdk = model.state_dict()
+    assert sdk["backbone.base_model.model.pos_embed"].shape == (1, 1025, 1024)
+    assert sdk["decode_head.fusion_conv.conv.weight"].shape == (1024, 4096, 1, 1)
+    assert sdk["decode_head.output_upscaling.0.weight"].shape == (1024, 512, 2, 2)
+    assert sdk["decode_head.conv_seg.weight"].shape == (19, 256, 1, 1)
+
+
+def test_no_cpu_fallback():
+    cfg = synthetic.tiny_config()
+    model = MODELS.build(dict(cfg))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.predict_labels(torch.zeros(1, 3, 64, 64, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.backbone(torch.zeros(1, 3, 64, 64))
+
+
+def test_slide_boxes_agree_with_oracle():
+    for (H, W, c, s) in [(1024, 2048, 512, 341), (1024, 2048, 512, 320), (80, 112, 64, 43), (512, 512, 512, 341), (600, 700, 512, 341)]:
+        ours = engine.slide_boxes(H, W, (c, c), (s, s))
+        ref = [(b[0], b[2]) for b in torch_ref.slide_boxes(H, W, (c, c), (s, s))]
+        assert ours == ref
+    b = engine.slide_boxes(1024, 2048, (512, 512), (341, 341))
+    cover = np.zeros((1024, 2048), dtype=np.int32)
+    for y, x in b:
+        cover[y:y + 512, x:x + 512] += 1
+    vals, counts = np.unique(cover, return_counts=True)
+    assert dict(zip(vals.tolist(), counts.tolist())) == {1: 524288, 2: 1048576, 4: 524288}
+
+
+def test_pos_embed_interpolation_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    pe = torch.randn(1, 17, 32, generator=g)
+    assert torch.equal(engine._interp_pos_embed(pe, 4, 4), pe[0])
+    for gh, gw in [(4, 6), (8, 4), (2, 2)]:
+        ours = engine._interp_pos_embed(pe, gh, gw)
+        ref = torch_ref.interpolate_pos_encoding(pe, gh * gw, gh * 16, gw * 16, 16)[0]
+        assert torch.equal(ours, ref)
+
+
+def test_abi_header_and_binding_agree_and_library_exports_every_symbol():
+    hdr = (ROOT / "include" / "vfmseg_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vfm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_C.SIGNATURES), declared ^ set(_C.SIGNATURES)
+    lib = _C.load()           # built by __graft_entry__.build(); dlopen works without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.vfm_abi_version() == 1
+    assert lib.vfm_launch_count() >= 0
+    assert ctypes.sizeof(_C.VfmBlockParams) == 14 * 8
+    # argument validation happens before any CUDA call
+    assert lib.vfm_layernorm(None, None, None, None, 0, 1024, 1e-6, None) == -1
+    assert b"layernorm" in lib.vfm_last_error()
+    assert lib.vfm_gemm_cls_nchw(None, 0, None, 0, None, None, 40, 1, 1, 64, None) == -1
+
+
+def test_metric_reduction_matches_oracle_and_accepts_reference_records():
+    rng = np.random.default_rng(0)
+    nc = 19
+    m = DGIoUMetric(dataset_keys=["citys", "bdd"], ignore_index=255)
+    m.dataset_meta = dict(classes=list(range(nc)))
+    recs, ref_records = [], []
+    for i in range(5):
+        pred = rng.integers(0, nc, (64, 96))
+        gt = rng.integers(0, nc + 1, (64, 96))
+        gt[gt == nc] = 255
+        cm = torch.from_numpy(torch_ref.confusion_matrix_np(pred, gt, nc, 255))
+        key = "citys" if i % 2 == 0 else "bdd"
+        recs.append([key, cm])
+        ai, au, ap, al = torch_ref.intersect_and_union(torch.from_numpy(pred), torch.from_numpy(gt), nc, 255)
+        ref_records.append([key, ai, au, ap, al])
+        got = [a.numpy() for a in areas_from_confusion(cm, nc)]
+        assert all(np.array_equal(g, r.numpy().astype(np.int64)) for g, r in zip(got, (ai, au, ap, al)))
+    ours = m.compute_metrics(recs)
+    theirs = m.compute_metrics(ref_records)     # the reference's own record layout
+    assert ours == theirs
+    for key in ("citys", "bdd"):
+        tot = [sum(r[i] for r in ref_records if r[0] == key) for i in range(1, 5)]
+        want = torch_ref.total_area_to_metrics(*[t.numpy() for t in tot])
+        for k in ("mIoU", "mAcc", "aAcc"):
+            assert ours[f"{key}_{k}"] == pytest.approx(want[k], abs=1e-6)
+    assert ours["mean_mIoU"] == pytest.approx((ours["citys_mIoU"] + ours["bdd_mIoU"]) / 2)
+    s = total_area_to_metrics(np.array([0, 5]), np.array([0, 10]), np.array([0, 7]), np.array([0, 8]))
+    assert s["mIoU"] == 50.0   # nanmean skips the 0/0 class, like the reference
+
+
+def test_weight_folding_matches_oracle_semantics():
+    """LoRA merge, q-scale fold and BatchNorm fold are constant folds of the reference arithmetic."""
+    cfg = synthetic.tiny_config()
+    sd = synthetic.synthetic_state_dict(cfg, seed=3)
+    bb, hd = torch_ref.split_state_dict(sd)
+    C = 256
+    x = torch.randn(5, C)
+    want = torch_ref._qkv(x, bb, "blocks.0.attn.qkv", 2.0)
+    w = bb["blocks.0.attn.qkv.base_layer.weight"] + 2.0 * bb["blocks.0.attn.qkv.lora_B.default.weight"] @ bb["blocks.0.attn.qkv.lora_A.default.weight"]
+    got = x @ w.t() + bb["blocks.0.attn.qkv.base_layer.bias"]
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    # ConvT + eval BN fold as used by PackedLinearHead
+    import torch.nn.functional as F
+    f = torch.randn(2, C, 4, 4)
+    y = F.conv_transpose2d(f, hd["output_upscaling.0.weight"], hd["output_upscaling.0.bias"], stride=2)
+    y = F.batch_norm(y, hd["output_upscaling.1.running_mean"], hd["output_upscaling.1.running_var"], hd["output_upscaling.1.weight"],
+                     hd["output_upscaling.1.bias"], False, 0.0, 1e-5)
+    s = hd["output_upscaling.1.weight"] / torch.sqrt(hd["output_upscaling.1.running_var"] + 1e-5)
+    w1 = (hd["output_upscaling.0.weight"] * s.view(1, -1, 1, 1)).permute(2, 3, 1, 0).reshape(4 * (C // 2), C)
+    b1 = ((hd["output_upscaling.0.bias"] - hd["output_upscaling.1.running_mean"]) * s + hd["output_upscaling.1.bias"]).repeat(4)
+    tok = f.permute(0, 2, 3, 1).reshape(-1, C) @ w1.t() + b1            # [n*h*w, 4*Cout], col = (dy*2+dx)*Cout + co
+    got = tok.view(2, 4, 4, 2, 2, C // 2).permute(0, 5, 1, 3, 2, 4).reshape(2, C // 2, 8, 8)
+    torch.testing.assert_close(got, y, rtol=1e-4, atol=1e-4)
