@@ -12,8 +12,11 @@
 //   S = Q K^T     tcgen05.mma SS, fp32 S in TMEM cols [0,128)
 //   softmax       4 warps, one query row per thread (TMEM lane); online max/sum in registers;
 //                 P written back to TMEM as packed bf16 (cols [128,192))
-//   O_j = P V     tcgen05.mma TS (A = P from TMEM, B = V tile MN-major), fp32 in cols [192,256)
-//   O += O_j      running output in registers, rescaled by exp2(m_old - m_new)
+//   O += P V      tcgen05.mma TS (A = P from TMEM, B = V tile MN-major), fp32 accumulator in cols [192,256);
+//                 O stays in TMEM for the whole KV loop and is rescaled lazily (only when the running
+//                 max grows by more than 2^8), so the steady-state tile costs no O traffic at all
+//   The score MMA of tile j+1 is issued as soon as every softmax thread holds S_j in registers, so
+//   it runs underneath the exponentials of tile j.
 // 256 TMEM columns and ~82 KB smem per CTA, so two CTAs share an SM and overlap each other's
 // MMA and softmax phases.
 //
@@ -45,22 +48,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + 2 * ATT_KV_STAGES) * ATT_TILE_BYTES);
   uint64_t* q_full = bars;                          // TMA -> MMA
   uint64_t* kv_full = bars + 1;                     // [stages] TMA -> MMA
-  uint64_t* kv_empty = bars + 1 + ATT_KV_STAGES;    // [stages] MMA (PV done) -> TMA
-  uint64_t* s_full = bars + 1 + 2 * ATT_KV_STAGES;  // MMA -> softmax   (S_j ready)
-  uint64_t* p_full = s_full + 1;                    // softmax -> MMA   (P_j written, O_{j-1} drained)
-  uint64_t* o_full = s_full + 2;                    // MMA -> softmax   (O_j = P_j V_j ready)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 3);
+  uint64_t* kv_empty = bars + 1 + ATT_KV_STAGES;    // [stages] MMA (PV_j done) -> TMA
+  uint64_t* s_full = bars + 1 + 2 * ATT_KV_STAGES;  // MMA -> softmax   (S_j in TMEM)
+  uint64_t* s_free = s_full + 1;                    // softmax -> MMA   (S_j copied to registers)
+  uint64_t* p_full = s_full + 2;                    // softmax -> MMA   (P_j in TMEM, O rescaled if needed)
+  uint64_t* pv_done = s_full + 3;                   // MMA -> softmax   (O += P_j V_j finished)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work unit
   const int unit = blockIdx.x;
   const int qt = unit % q_tiles;
   const int head = (unit / q_tiles) % heads;
   const int seq = unit / (q_tiles * heads);
   const int C = heads * ATT_D;
-  const int row0 = seq * seq_len;  // first row of this sequence in the packed qkv matrix
+  const int row0 = seq * seq_len;
   const int kv_tiles = (seq_len + ATT_BLOCK_KV - 1) / ATT_BLOCK_KV;
 
   if (warp == 0 && lane == 0) {
@@ -68,8 +71,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
@@ -94,11 +98,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Issue order: S_0, [S_1, PV_0], [S_2, PV_1], ... so the score MMA of tile j+1 runs while the softmax
+    // warps exponentiate tile j. A commit covers every earlier MMA, so s_full(j+1) also implies PV_{j-1} done.
     if (lane == 0) {
-      // S: M=128 (queries), N=kv width, K-major A and B.  PV: M=128, N=64 (d), B = V is MN-major.
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);   // B = V is MN-major
       const uint32_t tmem_s = tmem_base + ATT_COL_S, tmem_p = tmem_base + ATT_COL_P, tmem_o = tmem_base + ATT_COL_O;
-      auto kv_width = [&](int j) {  // keys in tile j, rounded up to a multiple of 32 (masked in softmax)
+      auto kv_width = [&](int j) {  // keys in tile j rounded up to 32 (the excess is masked by the softmax)
         int w = seq_len - j * ATT_BLOCK_KV;
         w = w > ATT_BLOCK_KV ? ATT_BLOCK_KV : w;
         return (w + 31) & ~31;
@@ -115,25 +120,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
-      int stage = 0; uint32_t phase = 0;
       for (int j = 0; j < kv_tiles; ++j) {
-        // P_j is in TMEM (and O_{j-1} has been drained): O_j = P_j V_j
-        mbar_wait(p_full, j & 1);
+        const int stage = j % ATT_KV_STAGES;
+        if (j + 1 < kv_tiles) {
+          const int nstage = (j + 1) % ATT_KV_STAGES;
+          mbar_wait(&kv_full[nstage], ((j + 1) / ATT_KV_STAGES) & 1);
+          mbar_wait(s_free, j & 1);          // every softmax thread holds S_j in registers
+          tc_fence_after();
+          issue_s(j + 1, nstage);
+        }
+        mbar_wait(p_full, j & 1);            // P_j stored (and O rescaled when the running max jumped)
         tc_fence_after();
         const uint64_t dv = make_sw128_desc(smem_u32(smem_v + stage * ATT_TILE_BYTES));
         const int ksteps = kv_width(j) / 16;
         for (int k = 0; k < ksteps; ++k) {
           // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
-          umma_ts(tmem_o, tmem_p + 8 * k, dv + 128 * k, idesc_pv, k != 0);
+          umma_ts(tmem_o, tmem_p + 8 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
         }
-        tc_commit(&kv_empty[stage]);  // K_j and V_j are free once PV_j (and S_j before it) finished
-        tc_commit(o_full);
-        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
-        if (j + 1 < kv_tiles) {
-          mbar_wait(&kv_full[stage], phase);
-          tc_fence_after();
-          issue_s(j + 1, stage);
-        }
+        tc_commit(&kv_empty[stage]);
+        tc_commit(pv_done);
       }
     }
   } else {
@@ -144,95 +149,97 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
     const uint32_t tmem_p = tmem_base + lane_base + ATT_COL_P;
     const uint32_t tmem_o = tmem_base + lane_base + ATT_COL_O;
     constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kRescaleThreshold = 8.0f;   // in log2 units: P stays <= 2^8 relative to the reference max
 
-    float o[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // m_ref: the max (times log2e) that P and the O accumulator in TMEM are currently relative to.
+    float m_ref = -INFINITY, l_run = 0.f;
 
     for (int j = 0; j < kv_tiles; ++j) {
       int valid = seq_len - j * ATT_BLOCK_KV;
       valid = valid > ATT_BLOCK_KV ? ATT_BLOCK_KV : valid;
-      const int chunks = (valid + 31) >> 5;
+      const int chunks = (valid + 31) >> 5;   // warp-uniform
 
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max of this tile
+      uint32_t s[128];
+      if (chunks > 0) tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      if (chunks > 1) tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      if (chunks > 2) tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+      if (chunks > 3) tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                   // the tensor core may overwrite S with tile j+1 now
+
+      if (valid < ATT_BLOCK_KV) {            // tail tile only: mask keys past the sequence end
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
+      }
       float m_tile = -INFINITY;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + c * 32, r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if (c * 32 + i < valid) m_tile = fmaxf(m_tile, s);
-        }
-      }
-      // drain O_{j-1} before P_j may trigger the MMA that overwrites it
+      for (int i = 0; i < 128; ++i) m_tile = fmaxf(m_tile, __uint_as_float(s[i]));
+      m_tile *= kLog2e;
+
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);     // O and the P buffer are quiescent
         tc_fence_after();
+        const bool jump = m_tile > m_ref + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, jump)) { // rare after the first tiles: rescale O in TMEM
+          const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;
+          if (jump) { m_ref = m_tile; l_run *= alpha; }
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(tmem_o + c * 16, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < ATT_D / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tmem_o + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(tmem_o + c * 16, r);
+          }
         }
+      } else {
+        m_ref = m_tile;
       }
-      const float m_new = fmaxf(m_run, m_tile);  // finite: every tile has >= 1 valid key
-      const float alpha = fast_exp2((m_run - m_new) * kLog2e);
-      m_run = m_new;
-      l_run *= alpha;
-      if (alpha != 1.f) {
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o[i] *= alpha;
-      }
-      // pass 2: p = exp(s - m), row sum, pack to bf16, store as the A operand of the PV MMA
-      const float mb = m_new * kLog2e;
+
       float l_tile = 0.f;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * i]), kLog2e, -mb));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), kLog2e, -mb));
-          if (c * 32 + 2 * i >= valid) p0 = 0.f;
-          if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-          l_tile += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < 4; ++c) {
+        if (c < chunks) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i]), kLog2e, -m_ref));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), kLog2e, -m_ref));
+            l_tile += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(tmem_p + c * 16, pk);
         }
-        tmem_st16(tmem_p + c * 16, pk);
       }
       l_run += l_tile;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // last tile's O
-    mbar_wait(o_full, (kv_tiles - 1) & 1);
+    mbar_wait(pv_done, (kv_tiles - 1) & 1);
     tc_fence_after();
+    const int q_idx = qt * ATT_BLOCK_Q + quad * 32 + lane;
+    const float inv = 1.f / l_run;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + q_idx) * C + head * ATT_D);
 #pragma unroll
     for (int c = 0; c < ATT_D / 32; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_o + c * 32, r);
       tmem_ld_wait();
+      if (q_idx < seq_len) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
-    }
-    const int q_idx = qt * ATT_BLOCK_Q + quad * 32 + lane;
-    if (q_idx < seq_len) {
-      const float inv = 1.f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row0 + q_idx) * C + head * ATT_D);
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
 #pragma unroll
-      for (int i = 0; i < ATT_D / 8; ++i)
-        dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                            pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * i + t]) * inv;
+          dst[c * 4 + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
     }
   }
 
