@@ -24,7 +24,14 @@ def peaks():
     return 1590.0, 6650.0
 
 
-def timeit(fn, iters=10, warmup=3, flush=None):
+ONLY = ""
+WARMUP = 3
+
+
+def timeit(fn, iters=10, warmup=None, flush=None, label=""):
+    if ONLY and ONLY not in label:
+        return None, None
+    warmup = WARMUP if warmup is None else warmup
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -46,7 +53,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--crops", type=int, default=18)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring filter on the kernel label (profiling aid)")
+    ap.add_argument("--warmup", type=int, default=3)
     args = ap.parse_args()
+    global ONLY, WARMUP
+    ONLY, WARMUP = args.only, args.warmup
     tf_peak, gb_peak = peaks()
     dev = "cuda"
     T, C, H, heads = 1025, 1024, 4096, 16
@@ -57,6 +68,8 @@ def main():
     res = []
 
     def rec(name, ms, best, flops=None, bytes_=None):
+        if ms is None:
+            return
         d = {"kernel": name, "ms_median": round(ms, 4), "ms_best": round(best, 4)}
         if flops:
             d["tflops"] = round(flops / ms / 1e9, 1)
@@ -72,19 +85,19 @@ def main():
     wproj = bf(C, C); bp = f32(C); g = f32(C)
     w1 = bf(H, C); b1 = f32(H); w2 = bf(C, H)
     x = f32(M, C)
-    ms, best = timeit(lambda: ops.gemm_bias_bf16(a, wqkv, bq), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.gemm_bias_bf16(a, wqkv, bq), args.iters, flush=flush, label="gemm qkv  [M,1024]x[3072,1024]")
     rec("gemm qkv  [M,1024]x[3072,1024]", ms, best, 2.0 * M * 3 * C * C)
-    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_(x, a, wproj, bp, g), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_(x, a, wproj, bp, g), args.iters, flush=flush, label="gemm proj [M,1024]x[1024,1024] +residual")
     rec("gemm proj [M,1024]x[1024,1024] +residual", ms, best, 2.0 * M * C * C)
-    ms, best = timeit(lambda: ops.gemm_bias_gelu_bf16(a, w1, b1), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.gemm_bias_gelu_bf16(a, w1, b1), args.iters, flush=flush, label="gemm fc1  [M,1024]x[4096,1024] +gelu")
     rec("gemm fc1  [M,1024]x[4096,1024] +gelu", ms, best, 2.0 * M * H * C)
-    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_(x, a4, w2, bp, g), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_(x, a4, w2, bp, g), args.iters, flush=flush, label="gemm fc2  [M,4096]x[1024,4096] +residual")
     rec("gemm fc2  [M,4096]x[1024,4096] +residual", ms, best, 2.0 * M * H * C)
     qkv = bf(M, 3 * C)
-    ms, best = timeit(lambda: ops.attention_fwd(qkv, args.crops, T, heads), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.attention_fwd(qkv, args.crops, T, heads), args.iters, flush=flush, label="attention 16 heads S=1025 d=64")
     rec("attention 16 heads S=1025 d=64", ms, best, 4.0 * args.crops * heads * T * T * 64)
     lw, lb = f32(C), f32(C)
-    ms, best = timeit(lambda: ops.layernorm(x, lw, lb, 1e-6), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.layernorm(x, lw, lb, 1e-6), args.iters, flush=flush, label="layernorm [M,1024] f32->bf16")
     rec("layernorm [M,1024] f32->bf16", ms, best, None, M * C * 6.0)
     # tail
     boxes = []
@@ -93,12 +106,12 @@ def main():
             boxes.append((y1, x1))
     bt = torch.tensor(boxes, dtype=torch.int32, device=dev)
     low = f32(18, 19, 128, 128)
-    ms, best = timeit(lambda: ops.slide_merge_argmax(low, bt, 1, (512, 512), (1024, 2048)), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.slide_merge_argmax(low, bt, 1, (512, 512), (1024, 2048)), args.iters, flush=flush, label="slide_merge_argmax 1024x2048")
     rec("slide_merge_argmax 1024x2048", ms, best, None, low.numel() * 4.0 + 1024 * 2048)
     pred = torch.randint(0, 19, (1024 * 2048,), device=dev, dtype=torch.uint8)
     lab = torch.randint(0, 19, (1024 * 2048,), device=dev, dtype=torch.uint8)
     cm = torch.zeros(20, 19, dtype=torch.int64, device=dev)
-    ms, best = timeit(lambda: ops.confusion_matrix_(cm, pred, lab, 19), args.iters, flush=flush)
+    ms, best = timeit(lambda: ops.confusion_matrix_(cm, pred, lab, 19), args.iters, flush=flush, label="confusion_matrix 2M px (random labels)")
     rec("confusion_matrix 2M px (random labels)", ms, best, None, 2.0 * 1024 * 2048)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "bench_kernels.json").write_text(json.dumps(res, indent=1))

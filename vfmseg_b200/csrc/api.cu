@@ -114,34 +114,49 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, class Epi>
+template <int BLOCK_N, int CTA_GROUP, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi, cudaStream_t st,
                 const char* name) {
   if (!A || !W) return fail(VFM_ERR_INVALID, "%s: null operand", name);
   if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0)
     return fail(VFM_ERR_INVALID, "%s: need M,N,K > 0, N %% 32 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", name, M, N, K);
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTA_GROUP>;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, lda, GEMM_BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&tb, W, N, K, ldw, BLOCK_N);
+  rc = make_tmap(&tb, W, N, K, ldw, Cfg::kBRows);
   if (rc) return rc;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, Epi>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, CTA_GROUP, Epi>;
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
     VFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int m_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  constexpr int TILE_M = GEMM_BLOCK_M * CTA_GROUP;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int tiles = m_tiles * n_tiles;
   int sms = sm_count();
   if (sms <= 0) return fail(VFM_ERR_CUDA, "%s: no CUDA device", name);
-  const int grid = tiles < sms ? tiles : sms;
+  const int max_groups = sms / CTA_GROUP;
+  const int groups = tiles < max_groups ? tiles : max_groups;
   // K tail (K % 64 != 0) is covered by TMA zero fill of both operands.
   const int K_pad = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K * GEMM_BLOCK_K;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * CTA_GROUP);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA_GROUP;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   {
     LaunchScope scope(name, st);
-    kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, M, N, K_pad, epi);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K_pad, epi);
+    if (e != cudaSuccess) return fail(VFM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
   }
   VFM_LAUNCH_CHECK(name);
   return VFM_OK;
@@ -205,15 +220,15 @@ int vfm_device_check(void) {
 int vfm_gemm_bias_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
                        int N, int K, void* stream) {
   if (!out || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_bf16: bad out/ldo");
-  EpiBiasBf16 e{BF(out), ldo, bias, N};
-  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16");
+  EpiBiasBf16 e{BF(out), ldo, bias};
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16");
 }
 
 int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
                             int M, int N, int K, void* stream) {
   if (!out || !bias || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_gelu_bf16: bad out/bias/ldo");
   EpiBiasGeluBf16 e{BF(out), ldo, bias};
-  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_gelu_bf16");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_gelu_bf16");
 }
 
 int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
@@ -223,14 +238,14 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
   if (tap && ((tap_ld % 8) || (tap_col0 % 8) || tokens_per_crop <= 0))
     return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual: bad tap layout");
   EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, tokens_per_crop > 0 ? tokens_per_crop : 1};
-  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual");
 }
 
 int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
                          int patches, int M, int N, int K, void* stream) {
   if (!x || !bias || !pos || patches <= 0 || (M % patches)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
   EpiPatchEmbed e{x, N, bias, pos, patches};
-  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
 }
 
 int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int c_out,
@@ -238,7 +253,7 @@ int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const
   if (!out || !bias || c_out <= 0 || (c_out % 32) || h <= 0 || w <= 0 || (M % (h * w)))
     return fail(VFM_ERR_INVALID, "gemm_convt2x2_gelu: bad args (c_out %% 32 == 0, M %% (h*w) == 0)");
   EpiConvT2x2Gelu e{BF(out), bias, c_out, h, w};
-  return launch_gemm<256>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu");
 }
 
 int vfm_gemm_cls_nchw(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int num_classes,
@@ -246,14 +261,14 @@ int vfm_gemm_cls_nchw(const void* A, int lda, const void* W, int ldw, const floa
   if (!out || !bias || num_classes <= 0 || num_classes > 32 || pix_per_crop <= 0 || (M % pix_per_crop))
     return fail(VFM_ERR_INVALID, "gemm_cls_nchw: bad args (num_classes <= 32, M %% pix_per_crop == 0)");
   EpiClsNCHW e{out, bias, num_classes, pix_per_crop};
-  return launch_gemm<32>(A, lda, W, ldw, M, 32, K, e, S(stream), "gemm_cls_nchw");
+  return launch_gemm<32, 1>(A, lda, W, ldw, M, 32, K, e, S(stream), "gemm_cls_nchw");
 }
 
 int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bias, float* out, int ldo, int M, int N,
                  int K, void* stream) {
   if (!out || (ldo % 4)) return fail(VFM_ERR_INVALID, "gemm_f32: bad out/ldo");
   EpiF32 e{out, ldo, bias};
-  return launch_gemm<256>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_f32");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_f32");
 }
 
 int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream) {
