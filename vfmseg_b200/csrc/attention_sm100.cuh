@@ -83,55 +83,63 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp converged, one elected lane issues) =====================
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_2d(smem_q, &tmap_qkv, q_full, head * ATT_D, row0 + qt * ATT_BLOCK_Q);
-      int stage = 0; uint32_t phase = 0;
-      for (int j = 0; j < kv_tiles; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int j = 0; j < kv_tiles; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
         tma_load_2d(smem_k + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], C + head * ATT_D, row0 + j * ATT_BLOCK_KV);
         tma_load_2d(smem_v + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], 2 * C + head * ATT_D, row0 + j * ATT_BLOCK_KV);
-        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (warp converged, one elected lane issues) =====================
     // Issue order: S_0, [S_1, PV_0], [S_2, PV_1], ... so the score MMA of tile j+1 runs while the softmax
     // warps exponentiate tile j. A commit covers every earlier MMA, so s_full(j+1) also implies PV_{j-1} done.
-    if (lane == 0) {
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);   // B = V is MN-major
-      const uint32_t tmem_s = tmem_base + ATT_COL_S, tmem_p = tmem_base + ATT_COL_P, tmem_o = tmem_base + ATT_COL_O;
-      auto kv_width = [&](int j) {  // keys in tile j rounded up to 32 (the excess is masked by the softmax)
-        int w = seq_len - j * ATT_BLOCK_KV;
-        w = w > ATT_BLOCK_KV ? ATT_BLOCK_KV : w;
-        return (w + 31) & ~31;
-      };
-      auto issue_s = [&](int j, int stage) {
-        const uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, kv_width(j), 0, 0);
-        const uint64_t dq = make_sw128_desc(smem_u32(smem_q));
-        const uint64_t dk = make_sw128_desc(smem_u32(smem_k + stage * ATT_TILE_BYTES));
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);   // B = V is MN-major
+    const uint32_t tmem_s = tmem_base + ATT_COL_S, tmem_p = tmem_base + ATT_COL_P, tmem_o = tmem_base + ATT_COL_O;
+    const uint64_t dq = make_sw128_desc(smem_u32(smem_q));
+    const uint64_t dk0 = make_sw128_desc(smem_u32(smem_k));
+    const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
+    auto kv_width = [&](int j) {  // keys in tile j rounded up to 32 (the excess is masked by the softmax)
+      int w = seq_len - j * ATT_BLOCK_KV;
+      w = w > ATT_BLOCK_KV ? ATT_BLOCK_KV : w;
+      return (w + 31) & ~31;
+    };
+    auto issue_s = [&](int j, int stage) {   // called by the elected lane only
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, kv_width(j), 0, 0);
+      const uint64_t dk = dk0 + static_cast<uint64_t>(stage * (ATT_TILE_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        tc_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      for (int j = 0; j < kv_tiles; ++j) {
-        const int stage = j % ATT_KV_STAGES;
-        if (j + 1 < kv_tiles) {
-          const int nstage = (j + 1) % ATT_KV_STAGES;
-          mbar_wait(&kv_full[nstage], ((j + 1) / ATT_KV_STAGES) & 1);
-          mbar_wait(s_free, j & 1);          // every softmax thread holds S_j in registers
-          tc_fence_after();
-          issue_s(j + 1, nstage);
-        }
-        mbar_wait(p_full, j & 1);            // P_j stored (and O rescaled when the running max jumped)
+      for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+      tc_commit(s_full);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one_sync()) issue_s(0, 0);
+    __syncwarp();
+    for (int j = 0; j < kv_tiles; ++j) {
+      const int stage = j % ATT_KV_STAGES;
+      if (j + 1 < kv_tiles) {
+        const int nstage = (j + 1) % ATT_KV_STAGES;
+        mbar_wait(&kv_full[nstage], ((j + 1) / ATT_KV_STAGES) & 1);
+        mbar_wait(s_free, j & 1);          // every softmax thread holds S_j in registers
         tc_fence_after();
-        const uint64_t dv = make_sw128_desc(smem_u32(smem_v + stage * ATT_TILE_BYTES));
+        if (elect_one_sync()) issue_s(j + 1, nstage);
+        __syncwarp();
+      }
+      mbar_wait(p_full, j & 1);            // P_j stored (and O rescaled when the running max jumped)
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t dv = dv0 + static_cast<uint64_t>(stage * (ATT_TILE_BYTES >> 4));
         const int ksteps = kv_width(j) / 16;
         for (int k = 0; k < ksteps; ++k) {
           // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
@@ -140,6 +148,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16
         tc_commit(&kv_empty[stage]);
         tc_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ===================== softmax + output (warps 2..5) =====================

@@ -94,11 +94,13 @@ struct EpiResidual {
   static constexpr int kMode = EPI_F32;
   float* x; int ldx; const float* bias; const float* gamma;
   __nv_bfloat16* tap; int tap_ld; int tap_col0; int tokens_per_crop;
+  static constexpr bool kNeedsOld = true;   // all 32 old values of a chunk are fetched before the first store
   struct Col { float b, g; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col), __ldg(gamma + col)}; }
-  __device__ __forceinline__ void elem(int row, int col, float v, const Col& c) const {
+  __device__ __forceinline__ float load_old(int row, int col) const { return x[static_cast<size_t>(row) * ldx + col]; }
+  __device__ __forceinline__ void elem(int row, int col, float v, float old, const Col& c) const {
     float* p = x + static_cast<size_t>(row) * ldx + col;
-    const float o = *p + c.g * (v + c.b);
+    const float o = old + c.g * (v + c.b);
     *p = o;
     if (tap != nullptr) {
       const int crop = row / tokens_per_crop, tok = row - crop * tokens_per_crop;   // warp-uniform
@@ -112,9 +114,11 @@ struct EpiResidual {
 struct EpiPatchEmbed {
   static constexpr int kMode = EPI_F32;
   float* x; int ldx; const float* bias; const float* pos; int patches;
+  static constexpr bool kNeedsOld = false;
   struct Col { float b; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col)}; }
-  __device__ __forceinline__ void elem(int row, int col, float v, const Col& c) const {
+  __device__ __forceinline__ float load_old(int, int) const { return 0.f; }
+  __device__ __forceinline__ void elem(int row, int col, float v, float, const Col& c) const {
     const int crop = row / patches, p = row - crop * patches;
     const size_t xrow = static_cast<size_t>(crop) * (patches + 1) + 1 + p;
     x[xrow * ldx + col] = v + c.b + __ldg(pos + static_cast<size_t>(1 + p) * ldx + col);
@@ -163,9 +167,11 @@ struct EpiClsNCHW {
 struct EpiF32 {
   static constexpr int kMode = EPI_F32;
   float* out; int ldo; const float* bias;
+  static constexpr bool kNeedsOld = false;
   struct Col { float b; };
   __device__ __forceinline__ Col col_setup(int col) const { return {bias ? __ldg(bias + col) : 0.f}; }
-  __device__ __forceinline__ void elem(int row, int col, float v, const Col& c) const {
+  __device__ __forceinline__ float load_old(int, int) const { return 0.f; }
+  __device__ __forceinline__ void elem(int row, int col, float v, float, const Col& c) const {
     out[static_cast<size_t>(row) * ldo + col] = v + c.b;
   }
 };
@@ -206,7 +212,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], CTA_GROUP); mbar_init(&empty_bar[s], 1); }
+    // full: one arrival (the leader producer's expect_tx); the peer CTA contributes only transaction bytes
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * Cfg::kEpiSplit * CTA_GROUP); }
     fence_barrier_init();
   }
@@ -218,33 +225,37 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its own W rows) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-        const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M;
-        const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // whole warp converged; one elected lane issues
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int a_row = m_blk * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M;
+      const int b_row = n_blk * BLOCK_N + static_cast<int>(cta_rank) * Cfg::kBRows;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           if constexpr (CTA_GROUP == 2) {
-            // transaction bytes of both CTAs land on the leader's barrier
+            // transaction bytes of both CTAs land on the leader's barrier (its tx-count may dip below zero
+            // until the leader's expect_tx of the same phase arrives; the pending arrival keeps the phase open)
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, a_row);
             tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, b_row);
-            if (!leader) mbar_arrive_leader(&full_bar[stage]);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * GEMM_BLOCK_K, a_row);
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * GEMM_BLOCK_K, b_row);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    // ===================== MMA issuer (leader CTA only; whole warp converged, one elected lane issues) ==========
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
+      const uint64_t da0 = make_sw128_desc(smem_u32(smem_a));
+      const uint64_t db0 = make_sw128_desc(smem_u32(smem_b));
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -254,17 +265,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_sw128_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = make_sw128_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if (elect_one_sync()) {
+            // stage offset and the +32 B per UMMA_K step both go into the (addr >> 4) field of the descriptor
+            const uint64_t da = da0 + static_cast<uint64_t>(stage * (Cfg::kABytes >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k) {
-            // +32 B per UMMA_K inside the 128-B swizzle span -> +2 in the (addr >> 4) field
-            umma_ss<CTA_GROUP>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
+              umma_ss<CTA_GROUP>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            tc_commit<CTA_GROUP>(&empty_bar[stage]);                         // frees the slot in both CTAs
+            if (kb == k_blocks - 1) tc_commit<CTA_GROUP>(&tmem_full[acc]);   // accumulator ready in both CTAs
           }
-          tc_commit<CTA_GROUP>(&empty_bar[stage]);     // frees the slot in both CTAs
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit<CTA_GROUP>(&tmem_full[acc]);         // accumulator ready in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -302,10 +315,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (col0 < N) {   // warp-uniform
               if constexpr (Epi::kMode == EPI_F32) {
                 const auto cc = epi.col_setup(col0 + lane);
-#pragma unroll 8
+                float old[32];
+                if constexpr (Epi::kNeedsOld) {
+#pragma unroll
+                  for (int rr = 0; rr < 32; ++rr) old[rr] = (row_base + rr < M) ? epi.load_old(row_base + rr, col0 + lane) : 0.f;
+                }
+#pragma unroll
                 for (int rr = 0; rr < 32; ++rr) {
                   const int row = row_base + rr;
-                  if (row < M) epi.elem(row, col0 + lane, stg[rr * GEMM_STAGE_LD + lane], cc);
+                  if (row < M) epi.elem(row, col0 + lane, stg[rr * GEMM_STAGE_LD + lane], Epi::kNeedsOld ? old[rr] : 0.f, cc);
                 }
               } else {
                 const int l16 = lane & 15, hi = lane >> 4;

@@ -19,6 +19,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// True in exactly one lane of a fully converged warp. Role loops run with the whole warp converged and only the
+// issue instructions (TMA, tcgen05.mma, tcgen05.commit) predicated on this, so their operands stay in uniform
+// registers; running the loop inside `if (lane == 0)` instead made ptxas wrap every UTCHMMA in an ELECT / R2UR /
+// BRA.U.ANY sequence and the single-thread issue loop (~850 clk per k-block) became the GEMM bottleneck.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -96,9 +110,11 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
-// Arrive (count 1) on the leader CTA's copy of `bar`.
+// Arrive (count 1) on the leader CTA's copy of `bar`. Relaxed: the callers publish no generic-proxy memory
+// through it (TMEM reads are already complete after tcgen05.wait::ld + tcgen05.fence::before_thread_sync), and a
+// release at cluster scope costs a full membar per call.
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
 
