@@ -44,7 +44,8 @@ MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
 # algorithmic FLOPs (2*M*N*K), SURVEY.md §8d
 FLOP_PER_CROP = {
     "gemm_bias_bf16": 24 * 2 * TOKENS * 1024 * 3072 + 2 * 1024 * 4096 * 1024,          # qkv x24 + head fusion conv
-    "gemm_bias_ls_residual": 24 * (2 * TOKENS * 1024 * 1024 + 2 * TOKENS * 1024 * 4096),  # proj + fc2
+    "gemm_bias_ls_residual": 24 * 2 * TOKENS * 1024 * 1024 + 20 * 2 * TOKENS * 1024 * 4096,  # proj x24 + fc2 x20 (TMA reduce-add)
+    "gemm_bias_ls_residual_tap": 4 * 2 * TOKENS * 1024 * 4096,                                # fc2 of blocks 7/11/15/23 (+ feature tap)
     "gemm_bias_gelu_bf16": 24 * 2 * TOKENS * 4096 * 1024,                                # fc1
     "attention_fwd": 24 * 4 * 16 * TOKENS * TOKENS * 64,                                  # QK^T + PV
     "gemm_patch_embed": 2 * 1024 * 768 * 1024,

@@ -1,0 +1,29 @@
+"""Debug: per-phase cycle counts of the GEMM epilogue (needs the -DVFM_EPI_TIMING build)."""
+import ctypes, sys
+from pathlib import Path
+import torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from vfmseg_b200 import _C, build
+build.LIB_PATH = ROOT / "vfmseg_b200" / "lib" / "libvfmseg_b200_dbg.so"
+_C.LIB_PATH = build.LIB_PATH
+from vfmseg_b200 import ops
+lib = _C.load()
+dev = "cuda"
+M, C, H = 18450, 1024, 4096
+bf = lambda *s: (torch.randn(*s, device=dev) * 0.05).to(torch.bfloat16)
+f32 = lambda *s: torch.randn(*s, device=dev)
+a, a4 = bf(M, C), bf(M, H)
+cases = {
+    "qkv": lambda: ops.gemm_bias_bf16(a, bf(3 * C, C), f32(3 * C)),
+    "proj": lambda: ops.gemm_bias_ls_residual_(f32(M, C), a, bf(C, C), f32(C), f32(C)),
+    "fc1": lambda: ops.gemm_bias_gelu_bf16(a, bf(H, C), f32(H)),
+    "fc2": lambda: ops.gemm_bias_ls_residual_(f32(M, C), a4, bf(C, H), f32(C), f32(C)),
+}
+out = (ctypes.c_ulonglong * 5)()
+for name, fn in cases.items():
+    fn(); lib.vfm_debug_epi(out)
+    fn(); lib.vfm_debug_epi(out)
+    v = list(out)
+    tiles = max(v[4], 1)
+    print(f"{name}: per tile (cycles, warp 4 avg): wait_full {v[0]/tiles:.0f}  tmem_ld {v[1]/tiles:.0f}  transpose {v[2]/tiles:.0f}  elem+global {v[3]/tiles:.0f}  tiles {tiles}")

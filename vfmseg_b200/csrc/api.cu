@@ -86,18 +86,27 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int make_tmap_ex(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols, CUtensorMapDataType dt, uint32_t esize);
+
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}; 128-B swizzle.
 int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap_ex(m, ptr, rows, cols, ld, box_rows, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+
+// row-major [rows, cols] tensor of `esize`-byte elements; box rows x box_cols with box_cols * esize == 128 B.
+int make_tmap_ex(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols, CUtensorMapDataType dt, uint32_t esize) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) != 0)
-    return fail(VFM_ERR_INVALID, "TMA operand must be 16-byte aligned with ld %% 8 == 0 (ptr=%p ld=%llu)", ptr,
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * esize) % 16) != 0)
+    return fail(VFM_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte row pitch (ptr=%p ld=%llu)", ptr,
                 static_cast<unsigned long long>(ld));
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
@@ -114,9 +123,11 @@ int sm_count() {
   return n;
 }
 
+struct OutDesc { const void* ptr = nullptr; int ld = 0; };   // destination of the TMA-store epilogues
+
 template <int BLOCK_N, int CTA_GROUP, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi, cudaStream_t st,
-                const char* name) {
+                const char* name, OutDesc od = OutDesc()) {
   if (!A || !W) return fail(VFM_ERR_INVALID, "%s: null operand", name);
   if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0)
     return fail(VFM_ERR_INVALID, "%s: need M,N,K > 0, N %% 32 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", name, M, N, K);
@@ -126,6 +137,12 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   if (rc) return rc;
   rc = make_tmap(&tb, W, N, K, ldw, Cfg::kBRows);
   if (rc) return rc;
+  CUtensorMap tout = ta;   // placeholder for epilogues that store with plain instructions
+  if constexpr (Epi::kMode == EPI_TMA_BF16) {
+    if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
+  } else if constexpr (Epi::kMode == EPI_TMA_RED_F32) {
+    if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4))) return rc;
+  }
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, CTA_GROUP, Epi>;
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
@@ -155,7 +172,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   cfg.numAttrs = 1;
   {
     LaunchScope scope(name, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K_pad, epi);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, M, N, K_pad, epi);
     if (e != cudaSuccess) return fail(VFM_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
   }
   VFM_LAUNCH_CHECK(name);
@@ -209,6 +226,17 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
   return VFM_OK;
 }
 
+#ifdef VFM_EPI_TIMING
+// debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)
+extern "C" int vfm_debug_epi(unsigned long long* out5) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out5, vfm::g_epi_dbg, 5 * sizeof(unsigned long long));
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(vfm::g_epi_dbg, z, sizeof(z));
+  return 0;
+}
+#endif
+
 int vfm_device_check(void) {
   int dev = 0, major = 0;
   VFM_CUDA(cudaGetDevice(&dev));
@@ -220,15 +248,15 @@ int vfm_device_check(void) {
 int vfm_gemm_bias_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
                        int N, int K, void* stream) {
   if (!out || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_bf16: bad out/ldo");
-  EpiBiasBf16 e{BF(out), ldo, bias};
-  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16");
+  EpiTmaBf16<false> e{bias};
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16", OutDesc{out, ldo});
 }
 
 int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
                             int M, int N, int K, void* stream) {
   if (!out || !bias || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_gelu_bf16: bad out/bias/ldo");
-  EpiBiasGeluBf16 e{BF(out), ldo, bias};
-  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_gelu_bf16");
+  EpiTmaBf16<true> e{bias};
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_gelu_bf16", OutDesc{out, ldo});
 }
 
 int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
@@ -237,8 +265,12 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
   if (!x || !bias || !gamma || (ldx % 4)) return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual: bad x/bias/gamma/ldx");
   if (tap && ((tap_ld % 8) || (tap_col0 % 8) || tokens_per_crop <= 0))
     return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual: bad tap layout");
+  if (!tap) {   // no feature tap: the residual update is a TMA fp32 reduce-add, x is never read by the SM
+    EpiTmaResidual e{bias, gamma};
+    return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual", OutDesc{x, ldx});
+  }
   EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, tokens_per_crop > 0 ? tokens_per_crop : 1};
-  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual");
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_tap");
 }
 
 int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,

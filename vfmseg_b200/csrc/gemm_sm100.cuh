@@ -26,18 +26,31 @@
 // shared-memory tile and then works column-per-lane: one coalesced 128-byte line per instruction, and per-column
 // constants (bias, LayerScale gamma) are loaded once per lane instead of once per element.
 #pragma once
+#include <type_traits>
+
 #include "sm100_ptx.cuh"
 
 namespace vfm {
+
+#ifdef VFM_EPI_TIMING
+__device__ unsigned long long g_epi_dbg[8];   // [0]=wait tmem_full, [1]=tcgen05.ld, [2]=transpose, [3]=elementwise+global, [4]=tiles
+#define VFM_TICK(var) const long long var = clock64()
+#define VFM_ACC(i, a, b) dbg[i] += static_cast<unsigned long long>((b) - (a))
+#else
+#define VFM_TICK(var)
+#define VFM_ACC(i, a, b)
+#endif
 
 constexpr int GEMM_BLOCK_M = 128;   // rows per CTA
 constexpr int GEMM_BLOCK_K = 64;    // 64 bf16 = one 128-B swizzle span
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_STAGE_LD = 33;   // padded row stride (words) of the per-warp 32x32 transpose tile
+// per-warp 32x32 fp32 transpose tile, XOR-swizzled (word (r, c) lives at r*32 + (c ^ r)): conflict-free for the
+// row-per-thread writes and for both column-per-lane read patterns, and exactly the 4 KB of one TMA box
+__device__ __forceinline__ int stg_idx(int r, int c) { return r * 32 + (c ^ r); }
 
-enum EpiMode { EPI_F32 = 0, EPI_BF16X2 = 1, EPI_DIRECT = 2 };
+enum EpiMode { EPI_F32 = 0, EPI_BF16X2 = 1, EPI_DIRECT = 2, EPI_TMA_BF16 = 3, EPI_TMA_RED_F32 = 4 };
 
 template <int BLOCK_N, int CTA_GROUP>
 struct GemmCfg {
@@ -45,7 +58,7 @@ struct GemmCfg {
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 32 * GEMM_STAGE_LD * 4;
+  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 4096;   // per warp: 32x32 fp32 transpose tile or one 4 KB TMA box
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiStageBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;   // 2 accumulator stages
@@ -87,6 +100,42 @@ struct EpiBiasGeluBf16 {        // out = bf16(gelu_erf(acc + bias))  (fc1; mlp.p
   }
 };
 
+// TMA-store epilogues: math stays row-per-thread in registers, the 32-row fragment is written to a
+// SWIZZLE_128B shared-memory box with conflict-free 16-byte stores and one elected lane hands it to the TMA
+// engine, which clips the M / N tails. No per-element global instructions at all.
+template <bool kGelu>
+struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf GELU (fc1) or identity (qkv, fusion conv)
+  static constexpr int kMode = EPI_TMA_BF16;
+  const float* bias;            // may be null when !kGelu
+  __device__ __forceinline__ void apply(int col0, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+      if constexpr (kGelu) {
+        v[4 * i] = gelu_erf(v[4 * i]); v[4 * i + 1] = gelu_erf(v[4 * i + 1]);
+        v[4 * i + 2] = gelu_erf(v[4 * i + 2]); v[4 * i + 3] = gelu_erf(v[4 * i + 3]);
+      }
+    }
+  }
+};
+
+// x += gamma * (acc + bias) as a TMA fp32 reduce-add: the SM never reads the residual stream
+// (block.py:112-113 + layer_scale.py:27 for the 44 of 48 residual GEMMs that do not emit a feature tap).
+struct EpiTmaResidual {
+  static constexpr int kMode = EPI_TMA_RED_F32;
+  const float* bias; const float* gamma;
+  __device__ __forceinline__ void apply(int col0, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0) + i);
+      v[4 * i] = __fmul_rn(g.x, v[4 * i] + b.x); v[4 * i + 1] = __fmul_rn(g.y, v[4 * i + 1] + b.y);
+      v[4 * i + 2] = __fmul_rn(g.z, v[4 * i + 2] + b.z); v[4 * i + 3] = __fmul_rn(g.w, v[4 * i + 3] + b.w);
+    }
+  }
+};
+
 // x += gamma * (acc + bias) on the fp32 residual stream (block.py:112-113 with LayerScale,
 // layer_scale.py:27); optionally snapshots the new residual as a bf16 feature tap with the cls
 // row dropped (dino_v2.py:261-267) into a token-major [n_crops*patches, tap_ld] buffer.
@@ -100,7 +149,7 @@ struct EpiResidual {
   __device__ __forceinline__ float load_old(int row, int col) const { return x[static_cast<size_t>(row) * ldx + col]; }
   __device__ __forceinline__ void elem(int row, int col, float v, float old, const Col& c) const {
     float* p = x + static_cast<size_t>(row) * ldx + col;
-    const float o = old + c.g * (v + c.b);
+    const float o = __fadd_rn(old, __fmul_rn(c.g, v + c.b));   // unfused, bit-identical to the TMA reduce-add path
     *p = o;
     if (tap != nullptr) {
       const int crop = row / tokens_per_crop, tok = row - crop * tokens_per_crop;   // warp-uniform
@@ -180,7 +229,7 @@ struct EpiF32 {
 template <int BLOCK_N, int CTA_GROUP, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    int M, int N, int K, Epi epi) {
+                    const __grid_constant__ CUtensorMap tmap_out, int M, int N, int K, Epi epi) {
   using Cfg = GemmCfg<BLOCK_N, CTA_GROUP>;
   constexpr int kStages = Cfg::kStages;
   constexpr int TILE_M = GEMM_BLOCK_M * CTA_GROUP;
@@ -188,6 +237,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  // epilogue staging, 1024-B aligned (SWIZZLE_128B boxes): stage bytes are a multiple of 1024
   float* epi_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiStageBytes);
   uint64_t* full_bar = bars;                   // [kStages]  TMA -> MMA      (leader's copy is the live one)
@@ -287,21 +337,66 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 4) >> 2;
     if (half < Cfg::kEpiSplit) {
       constexpr int kColsPerSplit = BLOCK_N / Cfg::kEpiSplit;
-      float* stg = epi_stage + (warp - 4) * (32 * GEMM_STAGE_LD);
+      float* stg = epi_stage + (warp - 4) * 1024;   // 4096 B per warp
       int acc = 0; uint32_t acc_phase = 0;
+#ifdef VFM_EPI_TIMING
+      unsigned long long dbg[5] = {0, 0, 0, 0, 0};
+#endif
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        VFM_TICK(t_w0);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        VFM_TICK(t_w1);
+        VFM_ACC(0, t_w0, t_w1);
+#ifdef VFM_EPI_TIMING
+        dbg[4] += 1;
+#endif
         const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M + quad * 32;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerSplit;
 #pragma unroll 1
         for (int c = 0; c < kColsPerSplit; c += 32) {
           uint32_t r[32];
+          VFM_TICK(t0);
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
+          VFM_TICK(t1);
+          VFM_ACC(1, t0, t1);
           const int col0 = n_blk * BLOCK_N + half * kColsPerSplit + c;
-          if constexpr (Epi::kMode == EPI_DIRECT) {
+          if constexpr (Epi::kMode == EPI_TMA_BF16 || Epi::kMode == EPI_TMA_RED_F32) {
+            if (col0 < N) {   // warp-uniform
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+              epi.apply(col0, v);
+              uint8_t* box = reinterpret_cast<uint8_t*>(stg);
+              uint8_t* rowp = box + lane * 128;
+              const int sw = lane & 7;   // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+              if constexpr (Epi::kMode == EPI_TMA_RED_F32) {
+                tma_store_wait_read<0>();        // previous box of this warp has been read by the TMA engine
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (elect_one_sync()) { tma_reduce_add_2d(&tmap_out, box, col0, row_base); tma_store_commit(); }
+              } else {
+                const int hbox = (c >> 5) & 1;   // even chunk -> left 64 B of the 128-B rows, odd chunk -> right 64 B
+                if (hbox == 0) { tma_store_wait_read<0>(); __syncwarp(); }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(rowp + (((hbox * 4 + j) ^ sw) << 4)) =
+                      make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                if (hbox == 1 || col0 + 32 >= N) {
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (elect_one_sync()) { tma_store_2d(&tmap_out, box, col0 - hbox * 32, row_base); tma_store_commit(); }
+                }
+              }
+            }
+          } else if constexpr (Epi::kMode == EPI_DIRECT) {
             if (row_base + lane < M && col0 < N) {
               float v[32];
 #pragma unroll
@@ -310,34 +405,49 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg[lane * GEMM_STAGE_LD + i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) stg[stg_idx(lane, i)] = __uint_as_float(r[i]);
             __syncwarp();
+            VFM_TICK(t2);
+            VFM_ACC(2, t1, t2);
             if (col0 < N) {   // warp-uniform
+              // Fast path (every tile but the M tail): no per-row predicate, so the fully unrolled loops carry no
+              // branches and the shared-memory reads / global loads of all rows are in flight together.
+              const bool full = row_base + 32 <= M;
               if constexpr (Epi::kMode == EPI_F32) {
                 const auto cc = epi.col_setup(col0 + lane);
-                float old[32];
-                if constexpr (Epi::kNeedsOld) {
+                auto body = [&](auto check) {
+                  constexpr bool kCheck = decltype(check)::value;
+                  float old[32];
+                  if constexpr (Epi::kNeedsOld) {
 #pragma unroll
-                  for (int rr = 0; rr < 32; ++rr) old[rr] = (row_base + rr < M) ? epi.load_old(row_base + rr, col0 + lane) : 0.f;
-                }
+                    for (int rr = 0; rr < 32; ++rr)
+                      old[rr] = (!kCheck || row_base + rr < M) ? epi.load_old(row_base + rr, col0 + lane) : 0.f;
+                  }
 #pragma unroll
-                for (int rr = 0; rr < 32; ++rr) {
-                  const int row = row_base + rr;
-                  if (row < M) epi.elem(row, col0 + lane, stg[rr * GEMM_STAGE_LD + lane], Epi::kNeedsOld ? old[rr] : 0.f, cc);
-                }
+                  for (int rr = 0; rr < 32; ++rr) {
+                    if (!kCheck || row_base + rr < M)
+                      epi.elem(row_base + rr, col0 + lane, stg[stg_idx(rr, lane)], Epi::kNeedsOld ? old[rr] : 0.f, cc);
+                  }
+                };
+                if (full) body(std::false_type{}); else body(std::true_type{});
               } else {
                 const int l16 = lane & 15, hi = lane >> 4;
                 const auto cc = epi.col_setup(col0 + 2 * l16);
-#pragma unroll 8
-                for (int it = 0; it < 16; ++it) {
-                  const int rr = 2 * it + hi;
-                  const int row = row_base + rr;
-                  const float v0 = stg[rr * GEMM_STAGE_LD + 2 * l16], v1 = stg[rr * GEMM_STAGE_LD + 2 * l16 + 1];
-                  if (row < M) epi.elem2(row, col0 + 2 * l16, v0, v1, cc);
-                }
+                auto body = [&](auto check) {
+                  constexpr bool kCheck = decltype(check)::value;
+#pragma unroll
+                  for (int it = 0; it < 16; ++it) {
+                    const int rr = 2 * it + hi;
+                    const float v0 = stg[stg_idx(rr, 2 * l16)], v1 = stg[stg_idx(rr, 2 * l16 + 1)];
+                    if (!kCheck || row_base + rr < M) epi.elem2(row_base + rr, col0 + 2 * l16, v0, v1, cc);
+                  }
+                };
+                if (full) body(std::false_type{}); else body(std::true_type{});
               }
             }
             __syncwarp();
+            VFM_TICK(t3);
+            VFM_ACC(3, t2, t3);
           }
         }
         tc_fence_before();
@@ -347,6 +457,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if constexpr (Epi::kMode == EPI_TMA_BF16 || Epi::kMode == EPI_TMA_RED_F32) tma_store_wait<0>();
+#ifdef VFM_EPI_TIMING
+      if (lane == 0 && warp == 4) for (int i = 0; i < 5; ++i) atomicAdd(&g_epi_dbg[i], dbg[i]);
+#endif
     }
   }
 
