@@ -227,6 +227,18 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
 }
 
 #ifdef VFM_EPI_TIMING
+extern "C" int vfm_debug_att_trace(long long* out192) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out192, vfm::g_att_trace, 16 * 12 * sizeof(long long));
+  return 0;
+}
+extern "C" int vfm_debug_att(unsigned long long* out7) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out7, vfm::g_att_dbg, 7 * sizeof(unsigned long long));
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(vfm::g_att_dbg, z, sizeof(z));
+  return 0;
+}
 // debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)
 extern "C" int vfm_debug_epi(unsigned long long* out5) {
   cudaDeviceSynchronize();

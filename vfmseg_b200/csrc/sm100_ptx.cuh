@@ -297,6 +297,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax for
+// 2^f (relative error 1.0e-4, 20x below bf16 resolution), exponent patched in with an integer add. Used for a
+// fraction of the softmax exponentials so the 16/clk/SM MUFU unit is not the only pipe doing them.
+// Valid for x in [-125, 127]; the caller guarantees x <= ~8 and clamps below.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05500826f, 0.24220958f);
+  p = fmaf(p, f, 0.69328285f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
