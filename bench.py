@@ -64,19 +64,21 @@ def peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.proc = None
         self.gpu = gpu_index
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, t_start: float = None, t_end: float = None) -> dict:
+        """Summarise the samples whose timestamp falls inside [t_start, t_end] (the timed region)."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,6 +93,10 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
+                if t_start is not None:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_start - 0.05 or ts > t_end + 0.05:
+                        continue
                 sm.append(float(f[1]))
                 smax = float(f[2])
             except ValueError:
@@ -98,8 +104,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        sm_load = sorted(sm)[len(sm) // 2:] if sm else []   # upper half ~ samples under load
-        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
 
@@ -168,6 +173,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _C.load()
     _C.check(lib.vfm_device_check())
+    sampler = ClockSampler(local) if rank == 0 else None   # started early: nvidia-smi takes ~1 s to emit its first line
 
     B, K, W = args.images_per_step, args.steps, args.warmup
     cfg = synthetic.model_config(stride=(STRIDE, STRIDE), crop_size=(CROP, CROP))
@@ -210,15 +216,16 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(W):
         step_resident(i)
     torch.cuda.synchronize()
     cm.zero_()
     l0 = lib.vfm_launch_count()
+    t_wall0 = time.time()
     ms_total = timed(step_resident, K)
+    t_wall1 = time.time()
     launches = lib.vfm_launch_count() - l0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     cm_value = cm.clone()
 
     if args.quick:

@@ -119,6 +119,11 @@ int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops
 int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int C,
                   float eps, void* stream);
 
+/* Same, and additionally stores bf16(x) of every non-cls row into tap[(row - crop - 1), tap_col0 + c] (the feature tap
+ * of dino_v2.py:261-267, taken where the residual stream is read anyway). out may be NULL (tap only). */
+int vfm_layernorm_tap(const float* x, const float* gamma, const float* beta, void* out, int M, int C,
+                      float eps, void* tap, int tap_ld, int tap_col0, int tokens_per_crop, void* stream);
+
 /* GroupNorm(groups, C) (+ReLU) over bf16 token-major [n_crops*P, C]. linear_head.py:36-40. */
 int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const float* beta,
                        int n_crops, int P, int C, int groups, float eps, int relu, void* stream);

@@ -63,6 +63,7 @@ SIGNATURES = {
     "vfm_patch_gather": (_i, [_p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i, _p, _p]),
     "vfm_cls_rows": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vfm_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),
+    "vfm_layernorm_tap": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _i, _i, _i, _p]),
     "vfm_groupnorm_relu": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "vfm_slide_merge_argmax": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "vfm_confusion_matrix": (_i, [_p, _p, _ll, _i, _i, _p, _p]),

@@ -281,14 +281,14 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
     EpiTmaResidual e{bias, gamma};
     return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual", OutDesc{x, ldx});
   }
-  EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, tokens_per_crop > 0 ? tokens_per_crop : 1};
+  EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, FastDiv(tokens_per_crop > 0 ? tokens_per_crop : 1)};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_tap");
 }
 
 int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
                          int patches, int M, int N, int K, void* stream) {
   if (!x || !bias || !pos || patches <= 0 || (M % patches)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
-  EpiPatchEmbed e{x, N, bias, pos, patches};
+  EpiPatchEmbed e{x, N, bias, pos, FastDiv(patches)};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
 }
 
@@ -296,7 +296,7 @@ int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const
                            int h, int w, int M, int K, void* stream) {
   if (!out || !bias || c_out <= 0 || (c_out % 32) || h <= 0 || w <= 0 || (M % (h * w)))
     return fail(VFM_ERR_INVALID, "gemm_convt2x2_gelu: bad args (c_out %% 32 == 0, M %% (h*w) == 0)");
-  EpiConvT2x2Gelu e{BF(out), bias, c_out, h, w};
+  EpiConvT2x2Gelu e{BF(out), bias, c_out, h, w, FastDiv(h * w), FastDiv(w)};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu");
 }
 
@@ -304,7 +304,7 @@ int vfm_gemm_cls_nchw(const void* A, int lda, const void* W, int ldw, const floa
                       int pix_per_crop, int M, int K, void* stream) {
   if (!out || !bias || num_classes <= 0 || num_classes > 32 || pix_per_crop <= 0 || (M % pix_per_crop))
     return fail(VFM_ERR_INVALID, "gemm_cls_nchw: bad args (num_classes <= 32, M %% pix_per_crop == 0)");
-  EpiClsNCHW e{out, bias, num_classes, pix_per_crop};
+  EpiClsNCHW e{out, bias, num_classes, FastDiv(pix_per_crop)};
   return launch_gemm<32, 1>(A, lda, W, ldw, M, 32, K, e, S(stream), "gemm_cls_nchw");
 }
 
@@ -375,22 +375,32 @@ int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops
   return VFM_OK;
 }
 
-int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
-                  void* stream) {
-  if (!x || !gamma || !beta || !out || M <= 0) return fail(VFM_ERR_INVALID, "layernorm: bad args");
+int vfm_layernorm_tap(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                      void* tap, int tap_ld, int tap_col0, int tokens_per_crop, void* stream) {
+  if (!x || M <= 0) return fail(VFM_ERR_INVALID, "layernorm: bad args");
+  if (!out && !tap) return fail(VFM_ERR_INVALID, "layernorm: neither an output nor a tap was given");
+  if (out && (!gamma || !beta)) return fail(VFM_ERR_INVALID, "layernorm: null gamma/beta");
   if (C % 128 || C < 128 || C > 1024) return fail(VFM_ERR_INVALID, "layernorm: C must be a multiple of 128 in [128,1024] (C=%d)", C);
+  if (tap && ((tap_ld % 8) || (tap_col0 % 8) || tokens_per_crop <= 0)) return fail(VFM_ERR_INVALID, "layernorm: bad tap layout");
   const int grid = (M + 7) / 8;
   cudaStream_t st = S(stream);
-{
+  const FastDiv fd(tokens_per_crop > 0 ? tokens_per_crop : 1);
+  {
     LaunchScope scope("layernorm", st);
     switch (C / 128) {
-  #define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps); break;
+#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps, BF(tap), tap_ld, tap_col0, fd); break;
       VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
-  #undef VFM_LN_CASE
+#undef VFM_LN_CASE
     }
   }
   VFM_LAUNCH_CHECK("layernorm");
   return VFM_OK;
+}
+
+int vfm_layernorm(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                  void* stream) {
+  if (!out) return fail(VFM_ERR_INVALID, "layernorm: null output");
+  return vfm_layernorm_tap(x, gamma, beta, out, M, C, eps, nullptr, 0, 0, 1, stream);
 }
 
 int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const float* beta, int n_crops, int P, int C,
@@ -485,23 +495,29 @@ int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const Vfm
   if ((rc = vfm_patch_gather(img, is_u8, nrm, img_h, img_w, crops, n_crops, gh, gw, hid, stream))) return rc;
   if ((rc = vfm_gemm_patch_embed(hid, 768, p->patch_w, 768, p->patch_b, p->pos_embed, x, P, n_crops * P, C, 768, stream))) return rc;
   if ((rc = vfm_cls_rows(x, p->cls_token, p->pos_embed, n_crops, T, C, stream))) return rc;
+  // Feature taps (residual stream after block tap_blocks[i]) are emitted by the NEXT LayerNorm pass, which reads x
+  // anyway, so all 48 residual GEMMs use the TMA reduce-add epilogue; a tap after the last block gets a tap-only pass.
   int next_tap = 0;
   for (int l = 0; l < p->depth; ++l) {
     const VfmBlockParams& b = p->blocks[l];
-    if ((rc = vfm_layernorm(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, stream))) return rc;
+    void* tap = nullptr;
+    int tap_col0 = 0;
+    if (l > 0 && next_tap < p->n_taps && p->tap_blocks[next_tap] == l - 1) {
+      tap = taps;
+      tap_col0 = next_tap * C;
+      ++next_tap;
+    }
+    if ((rc = vfm_layernorm_tap(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, tap, p->n_taps * C, tap_col0, T, stream))) return rc;
     if ((rc = vfm_gemm_bias_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, 3 * C, M, 3 * C, C, stream))) return rc;
     if ((rc = vfm_attention_fwd(qkv, att, n_crops, T, p->heads, stream))) return rc;
     if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, b.ls1, x, C, nullptr, 0, 0, T, M, C, C, stream))) return rc;
     if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
     if ((rc = vfm_gemm_bias_gelu_bf16(xn, C, b.fc1_w, C, b.fc1_b, hid, Hd, M, Hd, C, stream))) return rc;
-    void* tap = nullptr;
-    int tap_col0 = 0;
-    if (next_tap < p->n_taps && p->tap_blocks[next_tap] == l) {
-      tap = taps;
-      tap_col0 = next_tap * C;
-      ++next_tap;
-    }
-    if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, tap, p->n_taps * C, tap_col0, T, M, C, Hd, stream))) return rc;
+    if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, nullptr, 0, 0, T, M, C, Hd, stream))) return rc;
+  }
+  if (next_tap < p->n_taps && p->tap_blocks[next_tap] == p->depth - 1) {
+    if ((rc = vfm_layernorm_tap(x, nullptr, nullptr, nullptr, M, C, p->ln_eps, taps, p->n_taps * C, next_tap * C, T, stream))) return rc;
+    ++next_tap;
   }
   if (next_tap != p->n_taps) return fail(VFM_ERR_INVALID, "vit_forward: tap_blocks must be ascending and < depth");
   return VFM_OK;

@@ -72,10 +72,14 @@ __global__ void cls_rows_kernel(float* __restrict__ x, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the channel dim of the fp32 residual stream, bf16 out (block.py:63,75 with
 // eps = 1e-6 from dino_v2.py:104). One warp per row, row held in registers, two-pass variance.
+// Optionally also snapshots the un-normalised row as a bf16 feature tap with the cls row dropped
+// (dino_v2.py:261-267): the residual stream is read here anyway, so the tap costs only its own write and every
+// residual GEMM can use the TMA reduce-add epilogue. `out` may be null (tap only, after the last block).
 template <int ITERS>  // C = 128 * ITERS
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ out, int M, float eps) {
+                 __nv_bfloat16* __restrict__ out, int M, float eps, __nv_bfloat16* __restrict__ tap, int tap_ld,
+                 int tap_col0, FastDiv tokens_per_crop) {
   constexpr int C = 128 * ITERS;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -88,6 +92,17 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     v[i] = xr[i * 32 + lane];
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
+  if (tap != nullptr) {
+    int crop, tok;
+    tokens_per_crop.divmod(row, crop, tok);
+    if (tok != 0) {
+      uint2* trow = reinterpret_cast<uint2*>(tap + static_cast<size_t>(row - crop - 1) * tap_ld + tap_col0);
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i)
+        trow[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+  }
+  if (out == nullptr) return;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s * (1.f / C);

@@ -142,7 +142,7 @@ struct EpiTmaResidual {
 struct EpiResidual {
   static constexpr int kMode = EPI_F32;
   float* x; int ldx; const float* bias; const float* gamma;
-  __nv_bfloat16* tap; int tap_ld; int tap_col0; int tokens_per_crop;
+  __nv_bfloat16* tap; int tap_ld; int tap_col0; FastDiv tokens_per_crop;
   static constexpr bool kNeedsOld = true;   // all 32 old values of a chunk are fetched before the first store
   struct Col { float b, g; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col), __ldg(gamma + col)}; }
@@ -152,7 +152,8 @@ struct EpiResidual {
     const float o = __fadd_rn(old, __fmul_rn(c.g, v + c.b));   // unfused, bit-identical to the TMA reduce-add path
     *p = o;
     if (tap != nullptr) {
-      const int crop = row / tokens_per_crop, tok = row - crop * tokens_per_crop;   // warp-uniform
+      int crop, tok;
+      tokens_per_crop.divmod(row, crop, tok);   // warp-uniform
       if (tok != 0) tap[static_cast<size_t>(row - crop - 1) * tap_ld + tap_col0 + col] = __float2bfloat16_rn(o);
     }
   }
@@ -162,14 +163,15 @@ struct EpiResidual {
 // GEMM row = crop * patches + p; the cls row is written by a separate tiny kernel).
 struct EpiPatchEmbed {
   static constexpr int kMode = EPI_F32;
-  float* x; int ldx; const float* bias; const float* pos; int patches;
+  float* x; int ldx; const float* bias; const float* pos; FastDiv patches;
   static constexpr bool kNeedsOld = false;
   struct Col { float b; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col)}; }
   __device__ __forceinline__ float load_old(int, int) const { return 0.f; }
   __device__ __forceinline__ void elem(int row, int col, float v, float, const Col& c) const {
-    const int crop = row / patches, p = row - crop * patches;
-    const size_t xrow = static_cast<size_t>(crop) * (patches + 1) + 1 + p;
+    int crop, p;
+    patches.divmod(row, crop, p);
+    const size_t xrow = static_cast<size_t>(crop) * (patches.d + 1) + 1 + p;
     x[xrow * ldx + col] = v + c.b + __ldg(pos + static_cast<size_t>(1 + p) * ldx + col);
   }
 };
@@ -179,7 +181,7 @@ struct EpiPatchEmbed {
 // destination row = crop*4hw + (2y+dy)*2w + (2x+dx), destination column = co.
 struct EpiConvT2x2Gelu {
   static constexpr int kMode = EPI_BF16X2;
-  __nv_bfloat16* out; const float* bias; int c_out; int h; int w;
+  __nv_bfloat16* out; const float* bias; int c_out; int h; int w; FastDiv div_hw, div_w;
   struct Col { float b0, b1; int co, dy, dx; };
   __device__ __forceinline__ Col col_setup(int col) const {
     const float2 b = __ldg(reinterpret_cast<const float2*>(bias + col));
@@ -188,8 +190,9 @@ struct EpiConvT2x2Gelu {
   }
   __device__ __forceinline__ void elem2(int row, int col, float v0, float v1, const Col& c) const {
     const int hw = h * w;
-    const int crop = row / hw, rem = row - crop * hw;
-    const int y = rem / w, xx = rem - y * w;
+    int crop, rem, y, xx;
+    div_hw.divmod(row, crop, rem);
+    div_w.divmod(rem, y, xx);
     const size_t orow = static_cast<size_t>(crop) * (4 * hw) + static_cast<size_t>(2 * y + c.dy) * (2 * w) + (2 * xx + c.dx);
     *reinterpret_cast<uint32_t*>(out + orow * c_out + c.co) = pack_bf16x2(gelu_erf(v0 + c.b0), gelu_erf(v1 + c.b1));
   }
@@ -200,14 +203,16 @@ struct EpiConvT2x2Gelu {
 // consecutive pixels, so row-per-thread stores are already one coalesced 128-B line per class.
 struct EpiClsNCHW {
   static constexpr int kMode = EPI_DIRECT;
-  float* out; const float* bias; int num_classes; int pix_per_crop;
+  float* out; const float* bias; int num_classes; FastDiv pix_per_crop;
   __device__ __forceinline__ void direct(int row, int col0, const float (&v)[32]) const {
-    const int crop = row / pix_per_crop, pix = row - crop * pix_per_crop;
-    float* base = out + static_cast<size_t>(crop) * num_classes * pix_per_crop + pix;
+    int crop, pix;
+    pix_per_crop.divmod(row, crop, pix);
+    const int ppc = pix_per_crop.d;
+    float* base = out + static_cast<size_t>(crop) * num_classes * ppc + pix;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int cls = col0 + i;
-      if (cls < num_classes) base[static_cast<size_t>(cls) * pix_per_crop] = v[i] + __ldg(bias + cls);
+      if (cls < num_classes) base[static_cast<size_t>(cls) * ppc] = v[i] + __ldg(bias + cls);
     }
   }
 };

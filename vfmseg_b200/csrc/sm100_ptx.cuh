@@ -287,6 +287,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, u
 }
 
 // ---------------------------------------------------------------- small math
+// Division by a runtime constant without a divide (CUTLASS FastDivmod scheme): valid for 0 <= n < 2^31.
+struct FastDiv {
+  uint32_t mul, shr; int d;
+  __host__ FastDiv() : mul(0), shr(0), d(1) {}
+  __host__ explicit FastDiv(int div) : mul(0), shr(0), d(div) {
+    if (div > 1) {
+      uint32_t lg = 0;
+      while ((1u << lg) < static_cast<uint32_t>(div)) ++lg;
+      const uint32_t p = 31 + lg;
+      mul = static_cast<uint32_t>(((1ull << p) + static_cast<uint64_t>(div) - 1) / static_cast<uint64_t>(div));
+      shr = p - 32;
+    }
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * d; }
+};
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
