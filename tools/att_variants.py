@@ -8,7 +8,8 @@ lib = sys.argv[1]
 build.LIB_PATH = ROOT / "vfmseg_b200" / "lib" / lib
 _C.LIB_PATH = build.LIB_PATH
 from vfmseg_b200 import ops
-qkv = (torch.randn(18 * 1025, 3072, device="cuda")).to(torch.bfloat16)
+qkv = (torch.randn(18 * 1025, 3072, device="cuda") * 0.7).to(torch.bfloat16)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = ops.attention_fwd(qkv, 18, 1025, 16)
 q, k, v = qkv.float().view(18, 1025, 3, 16, 64).permute(2, 0, 3, 1, 4)
 ref = ((q[:2] @ k[:2].transpose(-1, -2)).softmax(-1) @ v[:2]).transpose(1, 2).reshape(2 * 1025, 1024)
@@ -18,5 +19,5 @@ torch.cuda.synchronize()
 ts = []
 for _ in range(10):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(); ops.attention_fwd(qkv, 18, 1025, 16); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+    flush.zero_(); s.record(); ops.attention_fwd(qkv, 18, 1025, 16); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
 print(lib, "median ms", sorted(ts)[5], "max abs err", err)

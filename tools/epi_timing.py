@@ -28,19 +28,15 @@ for name, fn in cases.items():
     tiles = max(v[4], 1)
     print(f"{name}: per tile (cycles, warp 4 avg): wait_full {v[0]/tiles:.0f}  tmem_ld {v[1]/tiles:.0f}  transpose {v[2]/tiles:.0f}  elem+global {v[3]/tiles:.0f}  tiles {tiles}")
 
-out7 = (ctypes.c_ulonglong * 7)()
 qkv = bf(M, 3 * C)
 for _ in range(2):
-    ops.attention_fwd(qkv, 18, 1025, 16); lib.vfm_debug_att(out7)
-v = list(out7); n = max(v[6], 1)
-print(f"attention per CTA (cycles, warp 2): wait_s_full {v[0]/n:.0f}  load_S {v[1]/n:.0f}  mask+max {v[2]/n:.0f}  wait_pv+rescale {v[3]/n:.0f}  exp+storeP {v[4]/n:.0f}  loop_total {v[5]/n:.0f}  CTAs {n}")
-
+    ops.attention_fwd(qkv, 18, 1025, 16)
 tr = (ctypes.c_longlong * 192)()
 lib.vfm_debug_att_trace(tr)
 t = [[tr[j * 12 + e] for e in range(12)] for j in range(16)]
-t0 = min(v for row in t[:9] for v in row[:9] if v > 0)
-names = ["S_issued(mma)", "p_full_seen(mma)", "PV_issued(mma)", "wait_s(sm)", "s_ready(sm)", "S_loaded(sm)", "max_done(sm)", "pv_ready(sm)", "exp_done(sm)"]
+t0 = min(v for row in t[:16] for v in row[3:9] if v > 0)
+names = ["-", "-", "-", "wait_s(sm)", "s_ready(sm)", "S_loaded(sm)", "max_done(sm)", "P_buf_free(sm)", "exp_done(sm)"]
 print("event timeline of CTA 300 (cycles from first event):")
 print("tile " + " ".join(f"{n:>17s}" for n in names))
-for j in range(9):
+for j in range(16):
     print(f"{j:4d} " + " ".join(f"{(t[j][e]-t0) if t[j][e] > 0 else -1:17d}" for e in range(9)))

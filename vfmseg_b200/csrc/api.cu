@@ -232,13 +232,6 @@ extern "C" int vfm_debug_att_trace(long long* out192) {
   cudaMemcpyFromSymbol(out192, vfm::g_att_trace, 16 * 12 * sizeof(long long));
   return 0;
 }
-extern "C" int vfm_debug_att(unsigned long long* out7) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out7, vfm::g_att_dbg, 7 * sizeof(unsigned long long));
-  unsigned long long z[8] = {0};
-  cudaMemcpyToSymbol(vfm::g_att_dbg, z, sizeof(z));
-  return 0;
-}
 // debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)
 extern "C" int vfm_debug_epi(unsigned long long* out5) {
   cudaDeviceSynchronize();
@@ -319,7 +312,7 @@ int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int he
   if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_fwd: bad args");
   const int C = heads * ATT_D;
   CUtensorMap tq;
-  int rc = make_tmap(&tq, qkv, static_cast<uint64_t>(n_seq) * seq_len, 3 * C, 3 * C, ATT_BLOCK_KV);
+  int rc = make_tmap(&tq, qkv, static_cast<uint64_t>(n_seq) * seq_len, 3 * C, 3 * C, 64);   // 64-row boxes (K/V tiles; Q = two boxes)
   if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
