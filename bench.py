@@ -154,7 +154,7 @@ def run_reference_arm(args):
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -230,7 +230,7 @@ def run_b200_arm(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms_total / K, "images_per_s": world * B * K / (ms_total / 1e3), "gpu_launches": int(launches)}))
+            emit({"quick": True, "ms_per_step": ms_total / K, "images_per_s": world * B * K / (ms_total / 1e3), "gpu_launches": int(launches)})
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -315,13 +315,36 @@ def run_b200_arm(args):
             "flop_per_image": FLOP_PER_IMAGE,
             "check": {"confusion_total": int(cm_value.sum()), "expected_if_all_pool_batches_seen": None},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route everything that libraries print on stdout (e.g. the "NCCL version ..." banner) to stderr; the single
+    JSON line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj: dict):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

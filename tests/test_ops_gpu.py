@@ -150,8 +150,10 @@ def test_groupnorm_relu(ops):
     _close(out, ref, 1e-2, 1e-2, "groupnorm_relu")
 
 
-def test_convt_and_cls(ops):
-    n, h, w, Cin, Cout = 2, 8, 8, 256, 128
+@pytest.mark.parametrize("n,h,w,Cin,Cout", [(2, 8, 8, 256, 128),      # manual pixel-shuffle epilogue
+                                           (2, 32, 32, 256, 128),    # 4-D TMA store epilogue (w % 32 == 0)
+                                           (3, 64, 64, 128, 64)])
+def test_convt_and_cls(ops, n, h, w, Cin, Cout):
     x = _rand(n * h * w, Cin, seed=26, dtype=torch.bfloat16)
     wt = _rand(Cin, Cout, 2, 2, scale=Cin ** -0.5, seed=27)  # ConvTranspose2d weight [Cin, Cout, 2, 2]
     bias = _rand(Cout, seed=28)

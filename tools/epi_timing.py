@@ -20,10 +20,18 @@ cases = {
     "fc1": lambda: ops.gemm_bias_gelu_bf16(a, bf(H, C), f32(H)),
     "fc2": lambda: ops.gemm_bias_ls_residual_(f32(M, C), a4, bf(C, H), f32(C), f32(C)),
 }
+Mp = 36 * 1024
+ap = bf(Mp, 768)
+cases["patch_embed"] = lambda: ops.gemm_patch_embed(ap, bf(C, 768), f32(C), f32(1025, C), 36, 1024)
+cases["convt1"] = lambda: ops.gemm_convt2x2_gelu(bf(Mp, C), bf(2048, C), f32(2048), 512, 32, 32)
+cases["convt2"] = lambda: ops.gemm_convt2x2_gelu(bf(4 * Mp, 512), bf(1024, 512), f32(1024), 256, 64, 64)
 out = (ctypes.c_ulonglong * 5)()
 for name, fn in cases.items():
     fn(); lib.vfm_debug_epi(out)
-    fn(); lib.vfm_debug_epi(out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); lib.vfm_debug_epi(out)
+    print(f"{name}: {e0.elapsed_time(e1):.3f} ms (includes operand allocation)")
     v = list(out)
     tiles = max(v[4], 1)
     print(f"{name}: per tile (cycles, warp 4 avg): wait_full {v[0]/tiles:.0f}  tmem_ld {v[1]/tiles:.0f}  transpose {v[2]/tiles:.0f}  elem+global {v[3]/tiles:.0f}  tiles {tiles}")

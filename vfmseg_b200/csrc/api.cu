@@ -113,6 +113,22 @@ int make_tmap_ex(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, 
   return VFM_OK;
 }
 
+// bf16 ConvT output [n_rows_out (= crops*2h), 2w, c_out] as the 4-D tensor (co, dx, x, R); box {64, 1, 32, 1}, 128-B swizzle.
+int make_tmap_convt(CUtensorMap* m, const void* ptr, uint64_t R_total, uint64_t w, uint64_t c_out) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(VFM_ERR_INVALID, "TMA operand must be 16-byte aligned");
+  cuuint64_t dims[4] = {c_out, 2, w, R_total};
+  cuuint64_t strides[3] = {c_out * 2, 2 * c_out * 2, 2 * w * c_out * 2};   // bytes, dims 1..3
+  cuuint32_t box[4] = {64, 1, 32, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (%d)", static_cast<int>(r));
+  return VFM_OK;
+}
+
 int sm_count() {
   static int n = [] {
     int dev = 0, v = 0;
@@ -123,7 +139,7 @@ int sm_count() {
   return n;
 }
 
-struct OutDesc { const void* ptr = nullptr; int ld = 0; };   // destination of the TMA-store epilogues
+struct OutDesc { const void* ptr = nullptr; int ld = 0; int convt_w = 0; int convt_rows = 0; };   // destination of the TMA-store epilogues
 
 template <int BLOCK_N, int CTA_GROUP, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi, cudaStream_t st,
@@ -139,7 +155,11 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   if (rc) return rc;
   CUtensorMap tout = ta;   // placeholder for epilogues that store with plain instructions
   if constexpr (Epi::kMode == EPI_TMA_BF16) {
-    if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
+    if constexpr (Epi::kStore4D) {
+      if ((rc = make_tmap_convt(&tout, od.ptr, od.convt_rows, od.convt_w, od.ld))) return rc;
+    } else {
+      if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
+    }
   } else if constexpr (Epi::kMode == EPI_TMA_RED_F32) {
     if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4))) return rc;
   }
@@ -289,6 +309,12 @@ int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const
                            int h, int w, int M, int K, void* stream) {
   if (!out || !bias || c_out <= 0 || (c_out % 32) || h <= 0 || w <= 0 || (M % (h * w)))
     return fail(VFM_ERR_INVALID, "gemm_convt2x2_gelu: bad args (c_out %% 32 == 0, M %% (h*w) == 0)");
+  if (w % 32 == 0 && c_out % 64 == 0) {   // pixel shuffle by the TMA engine (4-D store)
+    EpiTmaConvT e{bias, c_out, h, FastDiv(h * w), FastDiv(w)};
+    OutDesc od;
+    od.ptr = out; od.ld = c_out; od.convt_w = w; od.convt_rows = (M / (h * w)) * 2 * h;
+    return launch_gemm<256, 2>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu", od);
+  }
   EpiConvT2x2Gelu e{BF(out), bias, c_out, h, w, FastDiv(h * w), FastDiv(w)};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, 4 * c_out, K, e, S(stream), "gemm_convt2x2_gelu");
 }

@@ -106,6 +106,7 @@ struct EpiBiasGeluBf16 {        // out = bf16(gelu_erf(acc + bias))  (fc1; mlp.p
 template <bool kGelu>
 struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf GELU (fc1) or identity (qkv, fusion conv)
   static constexpr int kMode = EPI_TMA_BF16;
+  static constexpr bool kStore4D = false;
   const float* bias;            // may be null when !kGelu
   __device__ __forceinline__ void apply(int col0, float (&v)[32]) const {
 #pragma unroll
@@ -117,6 +118,31 @@ struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf 
         v[4 * i + 2] = gelu_erf(v[4 * i + 2]); v[4 * i + 3] = gelu_erf(v[4 * i + 3]);
       }
     }
+  }
+};
+
+// ConvTranspose2d(k=2,s=2) (+ folded BatchNorm) + GELU with the pixel shuffle done by the TMA engine: the output
+// [n*2h*2w, c_out] is described as a 4-D tensor (co, dx, x, R = crop*2h + 2y + dy), so the 32 consecutive x of a
+// warp's fragment (one image row y; needs w % 32 == 0 and c_out % 64 == 0) are one box {64, 1, 32, 1}.
+// linear_head.py:42-48.
+struct EpiTmaConvT {
+  static constexpr int kMode = EPI_TMA_BF16;
+  static constexpr bool kStore4D = true;
+  const float* bias; int c_out; int h; FastDiv div_hw, div_w;
+  __device__ __forceinline__ void apply(int col0, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+      v[4 * i] = gelu_erf(v[4 * i] + b.x); v[4 * i + 1] = gelu_erf(v[4 * i + 1] + b.y);
+      v[4 * i + 2] = gelu_erf(v[4 * i + 2] + b.z); v[4 * i + 3] = gelu_erf(v[4 * i + 3] + b.w);
+    }
+  }
+  __device__ __forceinline__ void coords(int row_base, int col0, int& c0, int& c1, int& c2, int& c3) const {
+    const int quad = col0 / c_out;
+    int crop, rem, y, x0;
+    div_hw.divmod(row_base, crop, rem);
+    div_w.divmod(rem, y, x0);
+    c0 = col0 - quad * c_out; c1 = quad & 1; c2 = x0; c3 = crop * 2 * h + 2 * y + (quad >> 1);
   }
 };
 
@@ -164,15 +190,19 @@ struct EpiResidual {
 struct EpiPatchEmbed {
   static constexpr int kMode = EPI_F32;
   float* x; int ldx; const float* bias; const float* pos; FastDiv patches;
-  static constexpr bool kNeedsOld = false;
+  static constexpr bool kNeedsOld = true;   // "old" = the pos-embed value: all 32 are fetched before the first store
   struct Col { float b; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col)}; }
-  __device__ __forceinline__ float load_old(int, int) const { return 0.f; }
-  __device__ __forceinline__ void elem(int row, int col, float v, float, const Col& c) const {
+  __device__ __forceinline__ float load_old(int row, int col) const {
+    int crop, p;
+    patches.divmod(row, crop, p);
+    return __ldg(pos + static_cast<size_t>(1 + p) * ldx + col);
+  }
+  __device__ __forceinline__ void elem(int row, int col, float v, float pe, const Col& c) const {
     int crop, p;
     patches.divmod(row, crop, p);
     const size_t xrow = static_cast<size_t>(crop) * (patches.d + 1) + 1 + p;
-    x[xrow * ldx + col] = v + c.b + __ldg(pos + static_cast<size_t>(1 + p) * ldx + col);
+    x[xrow * ldx + col] = v + c.b + pe;
   }
 };
 
@@ -397,7 +427,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (hbox == 1 || col0 + 32 >= N) {
                   fence_proxy_async_smem();
                   __syncwarp();
-                  if (elect_one_sync()) { tma_store_2d(&tmap_out, box, col0 - hbox * 32, row_base); tma_store_commit(); }
+                  if (elect_one_sync()) {
+                    if constexpr (Epi::kStore4D) {
+                      int c0, c1, c2, c3;
+                      epi.coords(row_base, col0 - hbox * 32, c0, c1, c2, c3);
+                      tma_store_4d(&tmap_out, box, c0, c1, c2, c3);
+                    } else {
+                      tma_store_2d(&tmap_out, box, col0 - hbox * 32, row_base);
+                    }
+                    tma_store_commit();
+                  }
                 }
               }
             }
