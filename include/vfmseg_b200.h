@@ -92,6 +92,15 @@ int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bi
  * qkv: [n_seq*seq_len, 3*heads*64] bf16 as emitted by the qkv GEMM; out: [n_seq*seq_len, heads*64].
  * Replaces dino_layers/attention.py:58-66 (and the xformers branch :79-84). */
 int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream);
+/* Same, choosing how a sequence is tiled: mode 0 = automatic, 1 = tensor-core tiles over every token, 2 = token 0 of
+ * each sequence (the ViT cls token, dino_v2.py:225) is split off and handled on the CUDA cores so that 1 + 64k
+ * tokens need no partial tile. The result is the same softmax attention in every mode. */
+int vfm_attention_fwd_ex(const void* qkv, void* out, int n_seq, int seq_len, int heads, int mode, void* stream);
+/* Cross attention: q [n_seq*q_len, >= heads*64] (row pitch q_ld), kv [n_seq*kv_len, 2*heads*64] packed (k | v),
+ * out [n_seq*q_len, heads*64] (row pitch out_ld). Replaces the attention core of
+ * rein/models/heads/Transformer.py:113-136 (CrossAttention._forward with a context). */
+int vfm_attention_cross(const void* q, int q_ld, const void* kv, int kv_ld, void* out, int out_ld, int n_seq, int q_len,
+                        int kv_len, int heads, void* stream);
 
 /* ---------------------------------------------------------------- memory-bound operators */
 

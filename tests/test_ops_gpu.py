@@ -117,26 +117,51 @@ def test_layernorm(ops, M, C):
     _close(out, F.layer_norm(x, (C,), g, b, 1e-6), 1e-2, 1e-2, "layernorm")
 
 
-@pytest.mark.parametrize("n_seq,S,heads", [(1, 128, 1), (2, 256, 2), (1, 1025, 16), (3, 1025, 4), (2, 197, 2), (1, 2049, 2)])
-def test_attention(ops, n_seq, S, heads):
-    C = heads * 64
-    qkv = _rand(n_seq * S, 3 * C, seed=21, dtype=torch.bfloat16)
-    out = ops.attention_fwd(qkv, n_seq, S, heads)
+def _attn_ref(qkv, n_seq, S, heads):
     q, k, v = qkv.float().view(n_seq, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
-    _close(out, ref, 2e-2, 2e-2, f"attention S={S} heads={heads}")
+    return ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, heads * 64)
 
 
-def test_attention_peaked(ops):
-    # large-magnitude scores: exercises the online-softmax rescaling
+# mode 0 = automatic, 1 = tensor tiles over every token (ragged tail tiles), 2 = token 0 split off (cls token)
+@pytest.mark.parametrize("n_seq,S,heads,mode", [
+    (1, 128, 1, 1), (2, 256, 2, 1), (1, 1025, 16, 0), (3, 1025, 4, 1), (3, 1025, 4, 2), (2, 197, 2, 1), (2, 197, 2, 2),
+    (1, 2049, 2, 0), (1, 2049, 2, 1), (2, 17, 2, 0), (2, 17, 2, 2), (2, 2, 1, 2), (1, 385, 3, 0), (2, 641, 2, 1)])
+def test_attention(ops, n_seq, S, heads, mode):
+    qkv = _rand(n_seq * S, 3 * heads * 64, seed=21, dtype=torch.bfloat16)
+    out = ops.attention_fwd(qkv, n_seq, S, heads, mode)
+    _close(out, _attn_ref(qkv, n_seq, S, heads), 2e-2, 2e-2, f"attention S={S} heads={heads} mode={mode}")
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_attention_peaked(ops, mode):
+    # large-magnitude scores: exercises the online-softmax rescaling (and the rescaling of the split-off key's weight)
     n_seq, S, heads = 1, 1025, 2
     C = heads * 64
     qkv = _rand(n_seq * S, 3 * C, seed=22, dtype=torch.bfloat16)
     qkv[:, :C] *= 4
-    out = ops.attention_fwd(qkv, n_seq, S, heads)
-    q, k, v = qkv.float().view(n_seq, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
-    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
-    _close(out, ref, 3e-2, 3e-2, "attention peaked")
+    out = ops.attention_fwd(qkv, n_seq, S, heads, mode)
+    _close(out, _attn_ref(qkv, n_seq, S, heads), 3e-2, 3e-2, "attention peaked")
+
+
+def test_attention_modes_agree(ops):
+    # the split-off cls token is the same softmax attention, not an approximation
+    n_seq, S, heads = 2, 1025, 3
+    qkv = _rand(n_seq * S, 3 * heads * 64, seed=31, dtype=torch.bfloat16)
+    a = ops.attention_fwd(qkv, n_seq, S, heads, 1).float()
+    b = ops.attention_fwd(qkv, n_seq, S, heads, 2).float()
+    assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("n_seq,Lq,Lkv,heads", [(2, 1024, 1024, 8), (1, 100, 333, 2), (3, 256, 64, 1)])
+def test_attention_cross(ops, n_seq, Lq, Lkv, heads):
+    C = heads * 64
+    q = _rand(n_seq * Lq, C, seed=32, dtype=torch.bfloat16)
+    kv = _rand(n_seq * Lkv, 2 * C, seed=33, dtype=torch.bfloat16)
+    out = ops.attention_cross(q, kv, n_seq, Lq, Lkv, heads)
+    qf = q.float().view(n_seq, Lq, heads, 64).transpose(1, 2)
+    kf, vf = kv.float().view(n_seq, Lkv, 2, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((qf @ kf.transpose(-1, -2)).softmax(-1) @ vf).transpose(1, 2).reshape(n_seq * Lq, C)
+    _close(out, ref, 2e-2, 2e-2, f"cross attention {Lq}x{Lkv}")
 
 
 def test_groupnorm_relu(ops):

@@ -21,3 +21,19 @@ for _ in range(10):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     flush.zero_(); s.record(); ops.attention_fwd(qkv, 18, 1025, 16); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
 print(lib, "median ms", sorted(ts)[5], "max abs err", err)
+# per-kernel split (CUDA events around each launch, C ABI profiler)
+import ctypes
+lib_ = _C.load()
+lib_.vfm_prof_enable(1)
+for _ in range(10):
+    flush.zero_(); ops.attention_fwd(qkv, 18, 1025, 16)
+buf = ctypes.create_string_buffer(1 << 16)
+lib_.vfm_prof_report(buf, len(buf))
+lib_.vfm_prof_enable(0)
+print(buf.value.decode().strip().replace("\n", " | "))
+for mode in (1, 2):
+    ts = []
+    for _ in range(10):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_(); s.record(); ops.attention_fwd(qkv, 18, 1025, 16, mode); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+    print("mode", mode, "median ms", sorted(ts)[5])

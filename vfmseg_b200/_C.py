@@ -60,6 +60,8 @@ SIGNATURES = {
     "vfm_gemm_cls_nchw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_f32": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_attention_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
+    "vfm_attention_fwd_ex": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "vfm_attention_cross": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "vfm_patch_gather": (_i, [_p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i, _p, _p]),
     "vfm_cls_rows": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vfm_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),

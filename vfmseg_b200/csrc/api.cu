@@ -247,9 +247,9 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
 }
 
 #ifdef VFM_EPI_TIMING
-extern "C" int vfm_debug_att_trace(long long* out192) {
+extern "C" int vfm_debug_att_trace(long long* out384) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out192, vfm::g_att_trace, 16 * 12 * sizeof(long long));
+  cudaMemcpyFromSymbol(out384, vfm::g_att_trace, 16 * 24 * sizeof(long long));
   return 0;
 }
 // debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)
@@ -334,27 +334,76 @@ int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bi
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_f32");
 }
 
-int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream) {
-  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_fwd: bad args");
-  const int C = heads * ATT_D;
-  CUtensorMap tq;
-  int rc = make_tmap(&tq, qkv, static_cast<uint64_t>(n_seq) * seq_len, 3 * C, 3 * C, 64);   // 64-row boxes (K/V tiles; Q = two boxes)
-  if (rc) return rc;
+// Generic launcher: Q [*, q_ld], K [*, k_ld], V [*, v_ld] bf16; sequence s owns rows [s*q_seq_rows, +q_total) of Q/out
+// and [s*kv_seq_rows, +kv_total) of K/V. mode: 0 auto, 1 tensor tiles over every token, 2 extra-token split
+// (token 0 of each sequence handled on the CUDA cores; needs q_total == kv_total).
+static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, int k_ld, int k_col0, const void* v, int v_ld,
+                     int v_col0, void* out, int out_ld, int n_seq, int q_seq_rows, int kv_seq_rows, int q_total,
+                     int kv_total, int heads, int mode, cudaStream_t st) {
+  if (!q || !k || !v || !out || n_seq <= 0 || q_total <= 0 || kv_total <= 0 || heads <= 0)
+    return fail(VFM_ERR_INVALID, "attention: bad args");
+  if (mode < 0 || mode > 2) return fail(VFM_ERR_INVALID, "attention: mode must be 0, 1 or 2");
+  if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
+  bool extra = mode == 2;
+  if (mode == 0) extra = q_total == kv_total && q_total > 64 && ((q_total - 1) % 64) == 0;
+  if (extra && (q_total != kv_total || kv_total < 2)) return fail(VFM_ERR_INVALID, "attention: extra-token mode needs q_total == kv_total >= 2");
+  AttParams p{};
+  p.extra = extra ? 1 : 0;
+  p.q_len = q_total - p.extra; p.kv_len = kv_total - p.extra;
+  p.q_seq_rows = q_seq_rows; p.kv_seq_rows = kv_seq_rows;
+  p.q_row_off = p.extra; p.kv_row_off = p.extra;
+  p.heads = heads;
+  p.q_pairs = (p.q_len + ATT_QT * ATT_BLOCK_Q - 1) / (ATT_QT * ATT_BLOCK_Q);
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+  p.k_ptr = BF(k); p.v_ptr = BF(v); p.k_ld = k_ld; p.v_ld = v_ld;
+  p.out = BF(out); p.out_ld = out_ld;
+  const uint64_t q_rows = static_cast<uint64_t>(n_seq - 1) * q_seq_rows + q_total;
+  const uint64_t kv_rows = static_cast<uint64_t>(n_seq - 1) * kv_seq_rows + kv_total;
+  CUtensorMap tq, tk, tv;   // 64-row boxes (K/V tiles; a Q tile = two boxes)
+  int rc;
+  if ((rc = make_tmap(&tq, q, q_rows, q_col0 + heads * ATT_D, q_ld, 64))) return rc;
+  if ((rc = make_tmap(&tk, k, kv_rows, k_col0 + heads * ATT_D, k_ld, 64))) return rc;
+  if ((rc = make_tmap(&tv, v, kv_rows, v_col0 + heads * ATT_D, v_ld, 64))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
     VFM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     attr_done = true;
   }
-  const int q_tiles = (seq_len + ATT_BLOCK_Q - 1) / ATT_BLOCK_Q;
-  const long long grid = static_cast<long long>(n_seq) * heads * q_tiles;
-  if (grid > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention_fwd: grid too large");
+  long long grid = static_cast<long long>(n_seq) * heads * p.q_pairs;
+  p.n_main = static_cast<int>(grid);
+  p.q_ptr = BF(q); p.q_ld = q_ld;
+  if (extra) {
+    // one appended CTA per (sequence, head) for the extra token's query row; its scratch lives in the same dynamic smem
+    const size_t need = (static_cast<size_t>((kv_total + 3) & ~3) + (ATT_THREADS / 32) * 65) * sizeof(float);
+    if (need > static_cast<size_t>(ATT_SMEM_BYTES)) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
+    grid += static_cast<long long>(n_seq) * heads;
+  }
+  if (grid > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention: grid too large");
   {
-    LaunchScope scope("attention_fwd", S(stream));
-    attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, S(stream)>>>(tq, BF(out), seq_len,
-                                                                                                heads, q_tiles);
+    LaunchScope scope("attention_fwd", st);
+    attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
   }
   VFM_LAUNCH_CHECK("attention_fwd");
   return VFM_OK;
+}
+
+int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream) {
+  return vfm_attention_fwd_ex(qkv, out, n_seq, seq_len, heads, 0, stream);
+}
+
+int vfm_attention_fwd_ex(const void* qkv, void* out, int n_seq, int seq_len, int heads, int mode, void* stream) {
+  const int C = heads * ATT_D;
+  const __nv_bfloat16* base = BF(qkv);
+  return launch_attention(base, 3 * C, 0, base, 3 * C, C, base, 3 * C, 2 * C, out, C, n_seq, seq_len, seq_len, seq_len,
+                          seq_len, heads, mode, S(stream));
+}
+
+int vfm_attention_cross(const void* q, int q_ld, const void* kv, int kv_ld, void* out, int out_ld, int n_seq, int q_len,
+                        int kv_len, int heads, void* stream) {
+  const int C = heads * ATT_D;
+  const __nv_bfloat16* kvb = BF(kv);
+  return launch_attention(q, q_ld, 0, kvb, kv_ld, 0, kvb, kv_ld, C, out, out_ld, n_seq, q_len, kv_len, q_len, kv_len, heads,
+                          1, S(stream));
 }
 
 int vfm_patch_gather(const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w, const int* crops,

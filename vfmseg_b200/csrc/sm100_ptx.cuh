@@ -73,6 +73,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same, for producer / issuer warps that share a scheduler with compute warps: sleep between polls so the spin
+// loop does not take issue slots from them.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 32) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) {
+      printf("vfm: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

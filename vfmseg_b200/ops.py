@@ -98,9 +98,18 @@ def gemm_cls_nchw(a, w32, bias, num_classes, pix_per_crop):
     return out
 
 
-def attention_fwd(qkv, n_seq, seq_len, heads):
+def attention_fwd(qkv, n_seq, seq_len, heads, mode=0):
+    """mode 0 = automatic tiling, 1 = tensor tiles over every token, 2 = token 0 split off (cls token)."""
     out = torch.empty(n_seq * seq_len, heads * 64, device=qkv.device, dtype=torch.bfloat16)
-    _C.call("vfm_attention_fwd", _bf16(qkv), _bf16(out), n_seq, seq_len, heads, _stream())
+    _C.call("vfm_attention_fwd_ex", _bf16(qkv), _bf16(out), n_seq, seq_len, heads, int(mode), _stream())
+    return out
+
+
+def attention_cross(q, kv, n_seq, q_len, kv_len, heads):
+    """q [n_seq*q_len, heads*64], kv [n_seq*kv_len, 2*heads*64] (k | v) -> [n_seq*q_len, heads*64]."""
+    out = torch.empty(n_seq * q_len, heads * 64, device=q.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_cross", _bf16(q), q.stride(0), _bf16(kv), kv.stride(0), _bf16(out), out.stride(0), n_seq, q_len,
+            kv_len, heads, _stream())
     return out
 
 
