@@ -11,12 +11,12 @@ from vfmseg_b200 import ops
 lib = _C.load()
 qkv = (torch.randn(18 * 1025, 3072, device="cuda") * 0.7).to(torch.bfloat16)
 for _ in range(2):
-    ops.attention_fwd(qkv, 18, 1025, 16)
+    ops.attention_fwd(qkv, 18, 1025, 16, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 tr = (ctypes.c_longlong * 384)()
 lib.vfm_debug_att_trace(tr)
 t = [[tr[j * 24 + e] for e in range(24)] for j in range(16)]
 t0 = min(v for row in t for v in row if v > 0)
-names = ["S0:top", "S0:ready", "S0:issued", "PV0:top", "PV0:ready", "PV0:iss", "-", "-",
+names = ["mma:top", "mma:p_ok", "mma:pv_iss", "mma:s_iss", "-", "-", "-", "-",
          "A:wait_s", "A:s_ok", "A:S_ld", "A:max", "A:jchk", "A:arrived", "A:pp_go", "A:exp_end",
          "B:wait_s", "B:s_ok", "B:S_ld", "B:max", "B:jchk", "B:arrived", "B:pp_go", "B:exp_end"]
 print("event timeline of CTA 150 (cycles from first event)")

@@ -43,37 +43,28 @@ namespace vfm {
 constexpr int ATT_BLOCK_Q = 128;
 constexpr int ATT_BLOCK_KV = 64;
 constexpr int ATT_D = 64;
-constexpr int ATT_QT = 2;                                  // query tiles per CTA
-constexpr int ATT_FIRST_SOFTMAX_WARP = 6;                  // warp 0 TMA, warps 1..4 MMA issuers, warp 5 TMEM allocator
-constexpr int ATT_THREADS = 32 * ATT_FIRST_SOFTMAX_WARP + 128 * ATT_QT;   // + 4 softmax warps per query tile
-constexpr int ATT_K_STAGES = 6;                            // K_j is released as soon as both S_tj have executed
-constexpr int ATT_V_STAGES = 6;                            // V_j is held until both O_t += P_tj V_j have executed
-constexpr int ATT_Q_BYTES = ATT_BLOCK_Q * ATT_D * 2;       // 16 KB per query tile
+constexpr int ATT_THREADS = 192;                           // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2..5 softmax
+constexpr int ATT_K_STAGES = 4;                            // K_j is released as soon as S_j = Q K_j^T has executed
+constexpr int ATT_V_STAGES = 4;                            // V_j is held until O += P_j V_j has executed
+constexpr int ATT_Q_BYTES = ATT_BLOCK_Q * ATT_D * 2;       // 16 KB
 constexpr int ATT_KV_BYTES = ATT_BLOCK_KV * ATT_D * 2;     //  8 KB
 constexpr int ATT_ONES_BYTES = ATT_KV_BYTES;               // a V-shaped tile of bf16 1.0 (row sums on the tensor core)
-constexpr int ATT_SMEM_BYTES = ATT_QT * ATT_Q_BYTES + (ATT_K_STAGES + ATT_V_STAGES) * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 512;
-constexpr uint32_t ATT_TMEM_COLS = 512;
-// TMEM columns of query tile t (base + 256 t): S0 [0,64) S1 [64,128) fp32 scores; the packed bf16 probabilities P_b
-// overwrite the first 32 columns of S_b (each thread has its S row in registers by then); O [128,192); L [192,208) =
-// row sums of P, accumulated by a second small MMA against a tile of ones (every column holds the same sum).
-constexpr uint32_t ATT_COL_TILE = 256, ATT_COL_S = 0, ATT_COL_O = 128, ATT_COL_L = 192;
-#ifndef VFM_ATT_BACKOFF
-#define VFM_ATT_BACKOFF 0
-#endif
-#if VFM_ATT_BACKOFF
-#define ATT_WAIT(bar, parity) mbar_wait_backoff(bar, parity)
-#else
-#define ATT_WAIT(bar, parity) mbar_wait(bar, parity)
-#endif
-#ifndef VFM_ATT_PINGPONG
-#define VFM_ATT_PINGPONG 0
+constexpr int ATT_SMEM_BYTES = ATT_Q_BYTES + (ATT_K_STAGES + ATT_V_STAGES) * ATT_KV_BYTES + ATT_ONES_BYTES + 1024 + 256;
+constexpr uint32_t ATT_TMEM_COLS = 256;
+// TMEM columns: S0 [0,64) S1 [64,128) fp32 scores; the packed bf16 probabilities P_b overwrite the first 32 columns of
+// S_b (each thread has its S row in registers by then); O [128,192); L [192,208) = row sums of P, accumulated by a
+// second small MMA against a tile of ones (every column holds the same sum).
+constexpr uint32_t ATT_COL_S = 0, ATT_COL_O = 128, ATT_COL_L = 192;
+
+#ifndef VFM_ATT_POLY
+#define VFM_ATT_POLY 0   // measured: 0 -> 0.169 ms, 4 -> 0.172, 2 -> 0.179, 1 -> 0.195 (18 windows x 16 heads x 1025)
 #endif
 
 struct AttParams {
   int q_len, kv_len;            // body tokens per sequence (handled by the tensor-core tiles)
   int q_seq_rows, kv_seq_rows;  // rows between consecutive sequences in the Q / K,V matrices
   int q_row_off, kv_row_off;    // first body row inside a sequence (1 in extra-token mode)
-  int heads, q_pairs;
+  int heads, q_tiles;
   int q_col0, k_col0, v_col0;   // column of (head 0, d 0) in the Q / K / V matrices
   int extra;                    // 1: row 0 of each K/V sequence is one more key, handled on the CUDA cores
   int n_main;                   // CTAs >= n_main (extra mode only) compute the extra token's QUERY row on the CUDA cores
@@ -126,7 +117,7 @@ __device__ __forceinline__ void attention_extra_query(const AttParams& p, int se
   }
   // Keys are visited in batches of kIt * kWarps * 4; all loads of a batch are issued before the first use (indices
   // past the end are clamped, their results discarded), so a batch costs one memory round trip, not kIt.
-  constexpr int kIt = 10;
+  constexpr int kIt = 8;
   // scores (already in log2 units)
   float m = -INFINITY;
   for (int base = 0; base < kv_total; base += kIt * kWarps * 4) {
@@ -203,23 +194,25 @@ __device__ __forceinline__ void attention_extra_query(const AttParams& p, int se
   }
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem + ATT_QT * ATT_Q_BYTES;
+  uint8_t* smem_k = smem + ATT_Q_BYTES;
   uint8_t* smem_v = smem_k + ATT_K_STAGES * ATT_KV_BYTES;
   uint8_t* smem_ones = smem_v + ATT_V_STAGES * ATT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ATT_ONES_BYTES);
   uint64_t* q_full = bars;                          // TMA -> MMA, softmax (extra key)
   uint64_t* k_full = bars + 1;                      // [K stages] TMA -> MMA
-  uint64_t* k_empty = k_full + ATT_K_STAGES;        // [K stages] MMA (both S_j executed) -> TMA
+  uint64_t* k_empty = k_full + ATT_K_STAGES;        // [K stages] MMA (S_j executed) -> TMA
   uint64_t* v_full = k_empty + ATT_K_STAGES;        // [V stages] TMA -> MMA
-  uint64_t* v_empty = v_full + ATT_V_STAGES;        // [V stages] MMA (both PV_j executed) -> TMA
-  uint64_t* tile_bars = v_empty + ATT_V_STAGES;     // per query tile: s_full[2], p_full[2], pv_done[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_bars + 6 * ATT_QT);
+  uint64_t* v_empty = v_full + ATT_V_STAGES;        // [V stages] MMA (PV_j executed) -> TMA
+  uint64_t* s_full = v_empty + ATT_V_STAGES;        // [2] MMA -> softmax   (S_j in TMEM buffer j % 2)
+  uint64_t* p_full = s_full + 2;                    // [2] softmax -> MMA   (P_j in the columns of S_j)
+  uint64_t* pv_done = s_full + 4;                   // [2] MMA -> softmax   (O += P_j V_j executed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,30 +223,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     return;
   }
   const int unit = blockIdx.x;
-  const int pair = unit % p.q_pairs;
-  const int head = (unit / p.q_pairs) % p.heads;
-  const int seq = unit / (p.q_pairs * p.heads);
-  const int q_row0 = seq * p.q_seq_rows + p.q_row_off + pair * (ATT_QT * ATT_BLOCK_Q);   // first query row of tile 0
+  const int qt = unit % p.q_tiles;
+  const int head = (unit / p.q_tiles) % p.heads;
+  const int seq = unit / (p.q_tiles * p.heads);
+  const int q_row0 = seq * p.q_seq_rows + p.q_row_off + qt * ATT_BLOCK_Q;   // first query row of this tile
   const int kv_row0 = seq * p.kv_seq_rows + p.kv_row_off;
   const int kv_tiles = (p.kv_len + ATT_BLOCK_KV - 1) / ATT_BLOCK_KV;
-  // tile 0 always holds at least one query; tile 1 may lie entirely past the end of the sequence
-  const bool two = pair * (ATT_QT * ATT_BLOCK_Q) + ATT_BLOCK_Q < p.q_len;
-  const int n_act = two ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < ATT_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], n_act); }
-    for (int s = 0; s < ATT_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], n_act); }
-    for (int t = 0; t < ATT_QT; ++t)
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(&tile_bars[6 * t + s], 1); mbar_init(&tile_bars[6 * t + 2 + s], 128); mbar_init(&tile_bars[6 * t + 4 + s], 1);
-      }
+    for (int s = 0; s < ATT_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < ATT_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 4); mbar_init(&pv_done[s], 1); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < ATT_ONES_BYTES / 16; i += ATT_THREADS)
     reinterpret_cast<uint4*>(smem_ones)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   fence_proxy_async_smem();   // the tensor core reads the ones tile through the async proxy
@@ -264,17 +251,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer (warp converged, one elected lane issues) =====================
-    if (elect_one_sync()) {   // Q tiles = two 64-row boxes each
-      mbar_arrive_expect_tx(q_full, n_act * ATT_Q_BYTES);
-      for (int t = 0; t < n_act; ++t) {
-        tma_load_2d(smem_q + t * ATT_Q_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0 + t * ATT_BLOCK_Q);
-        tma_load_2d(smem_q + t * ATT_Q_BYTES + ATT_KV_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0 + t * ATT_BLOCK_Q + 64);
-      }
+    if (elect_one_sync()) {   // Q tile = two 64-row boxes
+      mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_2d(smem_q, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0);
+      tma_load_2d(smem_q + ATT_KV_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0 + 64);
     }
     __syncwarp();
     auto load_k = [&](int j) {
       const int st = j % ATT_K_STAGES;
-      ATT_WAIT(&k_empty[st], ((j / ATT_K_STAGES) & 1) ^ 1);
+      mbar_wait(&k_empty[st], ((j / ATT_K_STAGES) & 1) ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&k_full[st], ATT_KV_BYTES);
         tma_load_2d(smem_k + st * ATT_KV_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, kv_row0 + j * ATT_BLOCK_KV);
@@ -283,7 +268,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     };
     auto load_v = [&](int j) {
       const int st = j % ATT_V_STAGES;
-      ATT_WAIT(&v_empty[st], ((j / ATT_V_STAGES) & 1) ^ 1);
+      mbar_wait(&v_empty[st], ((j / ATT_V_STAGES) & 1) ^ 1);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(&v_full[st], ATT_KV_BYTES);
         tma_load_2d(smem_v + st * ATT_KV_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, kv_row0 + j * ATT_BLOCK_KV);
@@ -297,236 +282,228 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (j + 2 < kv_tiles) load_k(j + 2);
       load_v(j);
     }
-  } else if (warp < ATT_FIRST_SOFTMAX_WARP) {
-    // ===================== MMA issuers (warps converged, one elected lane issues) =====================
-    // warp 1 + t: S_tj = Q_t K_j^T for query tile t;  warp 3 + t: O_t += P_tj V_j.  Four independent issue streams:
-    // one warp doing all four (wait p_full -> 4 MMAs -> commit -> wait k_full -> 4 MMAs -> commit, twice per key tile)
-    // took ~2250 clk per key tile against 650 clk of tensor-pipe work, because every mbarrier wait, fence and
-    // tcgen05.commit of the chain sat on one warp's critical path (profiles/r1_attention_timeline.txt (3)).
-    // S and P are double-buffered per query tile, so neither the exponentials of tile j+1 nor the PV MMA of tile j
-    // ever wait for each other.
-    const int role = warp - 1;            // 0,1 = S issuer of tile 0,1; 2,3 = PV issuer of tile 0,1; 4 = idle
-    const int t = role & 1;
-    uint64_t* s_full = &tile_bars[6 * t];
-    uint64_t* p_full = s_full + 2;
-    uint64_t* pv_done = s_full + 4;
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp converged, one elected lane issues) =====================
+    // S is double-buffered and issued two tiles ahead, so the exponentials of tile j+1 never wait for the PV MMA of
+    // tile j. Issue order:  S_0, S_1, [PV_0, S_2], [PV_1, S_3], ...  — tcgen05.mma executes in issue order, which is
+    // what lets P_j live in the columns of S_j: S_{j+2} cannot overwrite them before PV_j has read them.
+    // (Issuing S_{j+2} early, right after the softmax warps have copied S_j to registers, with a separate single P
+    // buffer, measured SLOWER: 0.177 vs 0.167 ms — the S MMAs then compete with the exponential phase.)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);   // B = V is MN-major
+    constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BLOCK_Q, 16, 0, 1);       // B = ones, 16 identical columns
+    const uint32_t tmem_o = tmem_base + ATT_COL_O;
+    const uint32_t tmem_l = tmem_base + ATT_COL_L;
+    const uint64_t dq = make_sw128_desc(smem_u32(smem_q));
+    const uint64_t dk0 = make_sw128_desc(smem_u32(smem_k));
+    const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
+    const uint64_t d1 = make_sw128_desc(smem_u32(smem_ones));
     auto kv_width = [&](int j) {  // keys in tile j rounded up to 32 (the excess is masked by the softmax)
       int w = p.kv_len - j * ATT_BLOCK_KV;
       w = w > ATT_BLOCK_KV ? ATT_BLOCK_KV : w;
       return (w + 31) & ~31;
     };
-    if (role < 2 && t < n_act) {
-      const uint64_t dq = make_sw128_desc(smem_u32(smem_q + t * ATT_Q_BYTES));
-      const uint64_t dk0 = make_sw128_desc(smem_u32(smem_k));
-      ATT_WAIT(q_full, 0);
-      for (int j = 0; j < kv_tiles; ++j) {
-        const int st = j % ATT_K_STAGES;
-        if (t == 0) ATT_TRACE(j, 0);
-        // S buffer j % 2 was copied to registers before p_full(j-2); waiting for PV_{j-2} instead also tells the
-        // softmax (through s_full(j)) that P buffer j % 2 is free again: one wait per tile there, not two.
-        if (j >= 2) ATT_WAIT(&pv_done[j & 1], ((j - 2) >> 1) & 1);
-        ATT_WAIT(&k_full[st], (j / ATT_K_STAGES) & 1);
-        tc_fence_after();
-        if (t == 0) ATT_TRACE(j, 1);
-        if (elect_one_sync()) {
-          const uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, kv_width(j), 0, 0);
-          const uint64_t dk = dk0 + static_cast<uint64_t>(st * (ATT_KV_BYTES >> 4));
-          const uint32_t tmem_s = tmem_base + t * ATT_COL_TILE + ATT_COL_S + (j & 1) * 64;
+    auto issue_s = [&](int j) {   // whole warp; waits for K_j, then the elected lane issues
+      const int st = j % ATT_K_STAGES;
+      mbar_wait(&k_full[st], (j / ATT_K_STAGES) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, kv_width(j), 0, 0);
+        const uint64_t dk = dk0 + static_cast<uint64_t>(st * (ATT_KV_BYTES >> 4));
+        const uint32_t tmem_s = tmem_base + ATT_COL_S + (j & 1) * 64;
 #pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          tc_commit(&k_empty[st]);       // K_j can be overwritten as soon as every S_tj has executed (count = tiles)
-          tc_commit(&s_full[j & 1]);
-        }
-        __syncwarp();
-        if (t == 0) ATT_TRACE(j, 2);
+        for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(&k_empty[st]);       // K_j can be overwritten as soon as S_j has executed
+        tc_commit(&s_full[j & 1]);
       }
-    } else if (role >= 2 && role < 4 && t < n_act) {
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);   // B = V is MN-major
-      constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BLOCK_Q, 16, 0, 1);       // B = ones, 16 identical columns
-      const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
-      const uint64_t d1 = make_sw128_desc(smem_u32(smem_ones));
-      const uint32_t tmem_o = tmem_base + t * ATT_COL_TILE + ATT_COL_O;
-      const uint32_t tmem_l = tmem_base + t * ATT_COL_TILE + ATT_COL_L;
-      for (int j = 0; j < kv_tiles; ++j) {
-        const int b = j & 1;
-        const int st = j % ATT_V_STAGES;
-        if (t == 0) ATT_TRACE(j, 3);
-        ATT_WAIT(&v_full[st], (j / ATT_V_STAGES) & 1);
-        ATT_WAIT(&p_full[b], (j >> 1) & 1);   // P_tj stored (and O_t rescaled when the running max jumped)
-        tc_fence_after();
-        if (t == 0) ATT_TRACE(j, 4);
-        if (elect_one_sync()) {
-          const uint64_t dv = dv0 + static_cast<uint64_t>(st * (ATT_KV_BYTES >> 4));
-          const uint32_t tmem_p = tmem_base + t * ATT_COL_TILE + ATT_COL_S + b * 64;
-          const int ksteps = kv_width(j) / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
-            umma_ts(tmem_o, tmem_p + 8 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
-          }
-          for (int k = 0; k < ksteps; ++k) umma_ts(tmem_l, tmem_p + 8 * k, d1 + 128 * k, idesc_l, (j | k) != 0);
-          tc_commit(&v_empty[st]);       // count = tiles
-          tc_commit(&pv_done[b]);
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    if (kv_tiles > 1) issue_s(1);
+    for (int j = 0; j < kv_tiles; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int st = j % ATT_V_STAGES;
+      ATT_TRACE(j, 0);
+      mbar_wait(&v_full[st], (j / ATT_V_STAGES) & 1);
+      mbar_wait(&p_full[b], ph);         // P_j stored (and O rescaled when the running max jumped); S_j is in registers
+      tc_fence_after();
+      ATT_TRACE(j, 1);
+      if (elect_one_sync()) {
+        const uint64_t dv = dv0 + static_cast<uint64_t>(st * (ATT_KV_BYTES >> 4));
+        const uint32_t tmem_p = tmem_base + ATT_COL_S + b * 64;
+        const int ksteps = kv_width(j) / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
+          umma_ts(tmem_o, tmem_p + 8 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
         }
-        __syncwarp();
-        if (t == 0) ATT_TRACE(j, 5);
+        for (int k = 0; k < ksteps; ++k) umma_ts(tmem_l, tmem_p + 8 * k, d1 + 128 * k, idesc_l, (j | k) != 0);
+        tc_commit(&v_empty[st]);
+        tc_commit(&pv_done[b]);
       }
+      __syncwarp();
+      ATT_TRACE(j, 2);
+      if (j + 2 < kv_tiles) issue_s(j + 2);
+      ATT_TRACE(j, 3);
     }
   } else {
-    // ===================== softmax + output: one warpgroup per query tile, one query row per thread ==============
-    const int t = (warp - ATT_FIRST_SOFTMAX_WARP) >> 2;
+    // ===================== softmax + output (warps 2..5): one query row per thread =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const bool pingpong = VFM_ATT_PINGPONG && two;
-    if (t < n_act) {
-      const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t tmem_tile = tmem_base + lane_base + t * ATT_COL_TILE;
-      const uint32_t tmem_o = tmem_tile + ATT_COL_O;
-      uint64_t* s_full = &tile_bars[6 * t];
-      uint64_t* p_full = s_full + 2;
-      uint64_t* pv_done = s_full + 4;
-      constexpr float kLog2e = 1.4426950408889634f;
-      constexpr float kRescaleThreshold = 24.0f;  // in log2 units: P stays <= 2^24 relative to the reference max (P is
-                                                  // bf16 and O/l are fp32: range, not precision, is what a large P costs)
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_tile = tmem_base + lane_base;
+    const uint32_t tmem_o = tmem_tile + ATT_COL_O;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kRescaleThreshold = 24.0f;  // in log2 units: P stays <= 2^24 relative to the reference max (P is
+                                                // bf16 and O/l are fp32: range, not precision, is what a large P costs)
 
-      // m_ref: the max (times log2e) that P and the O accumulator in TMEM are currently relative to.
-      float m_ref = -INFINITY, w_extra = 0.f;
-      if (p.extra) {
-        // the extra key: s = q_row . k_extra on the CUDA cores; it starts the running softmax with weight 1
-        mbar_wait(q_full, 0);
-        const uint8_t* qrow = smem_q + t * ATT_Q_BYTES + row * 128;
-        const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + head * ATT_D);
-        float acc0 = 0.f, acc1 = 0.f;
+    // m_ref: the max (times log2e) that P and the O accumulator in TMEM are currently relative to.
+    float m_ref = -INFINITY, w_extra = 0.f;
+    if (p.extra) {
+      // the extra key: s = q_row . k_extra on the CUDA cores; it starts the running softmax with weight 1
+      mbar_wait(q_full, 0);
+      const uint8_t* qrow = smem_q + row * 128;
+      const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + head * ATT_D);
+      float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
-          const uint4 kv = __ldg(kx + c);
-          acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
-          acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
-          acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
-          acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
-        }
-        m_ref = (acc0 + acc1) * kLog2e;
-        w_extra = 1.f;
+      for (int c = 0; c < 8; ++c) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
+        const uint4 kv = __ldg(kx + c);
+        acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
+        acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
+        acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
+        acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
       }
-      if (pingpong && t == 1) named_bar_arrive(1, 256);   // tile 0 runs its first exponential phase first
+      m_ref = (acc0 + acc1) * kLog2e;
+      w_extra = 1.f;
+    }
 
-      for (int j = 0; j < kv_tiles; ++j) {
-        const int b = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        int valid = p.kv_len - j * ATT_BLOCK_KV;
-        valid = valid > ATT_BLOCK_KV ? ATT_BLOCK_KV : valid;
-        const int chunks = (valid + 31) >> 5;   // warp-uniform: 1 or 2
-        const uint32_t tmem_s = tmem_tile + ATT_COL_S + b * 64;
-        const uint32_t tmem_p = tmem_s;   // P_j overwrites the first half of S_j
+    for (int j = 0; j < kv_tiles; ++j) {
+      const int b = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      int valid = p.kv_len - j * ATT_BLOCK_KV;
+      valid = valid > ATT_BLOCK_KV ? ATT_BLOCK_KV : valid;
+      const int chunks = (valid + 31) >> 5;   // warp-uniform: 1 or 2
+      const uint32_t tmem_s = tmem_tile + ATT_COL_S + b * 64;
 
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 0);
-        mbar_wait(&s_full[b], ph);
-        tc_fence_after();
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 1);
-        uint32_t s[64];
-        tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        if (chunks > 1) tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld_wait();
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 2);
-
-        if (valid < ATT_BLOCK_KV) {            // tail tile only: mask keys past the sequence end
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= valid) s[i] = 0xff800000u;  // -inf
-        }
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-#pragma unroll
-        for (int i = 0; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
-        const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 3);
-
-        {
-          const bool jump = m_tile > m_ref + kRescaleThreshold;   // always true for j == 0 without an extra key
-          if (__any_sync(0xffffffffu, jump)) { // rare after the first tiles: rescale O in TMEM
-            const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
-            if (jump) { m_ref = m_tile; w_extra *= alpha; }
-            if (j > 0) {
-              // every PV up to tile j-1 must have executed before O is touched (pv_done[(j-1)%2] is the newest phase
-              // of that barrier)
-              mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-              tc_fence_after();
-#pragma unroll 1
-              for (int c = 0; c < ATT_D / 16 + 1; ++c) {   // O and, right behind it, the row sums L
-                uint32_t r[16];
-                tmem_ld16(tmem_o + c * 16, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                tmem_st16(tmem_o + c * 16, r);
-              }
-            }
-          }
-        }
-        // P buffer b was last read by PV_{j-2}, which executed before S_j (see the MMA issue order): no wait needed
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 4);
-        if (pingpong) named_bar_sync(1 + t, 256);
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 6);
-
-        // P = exp2(s log2e - m_ref), truncated to bf16 by the PRMT that packs two of them; the row sum of exactly those
-        // bf16 values comes from the tensor core (L += P * ones), so P / l is an exact softmax of the weights the PV MMA
-        // uses, and the CUDA cores spend 2.5 instructions per element (FFMA, MUFU, half a PRMT) instead of 4.5 — the
-        // FMA/ALU pipes issue one warp instruction every 2 clk, which, not the MUFU pipe, bounded the previous version.
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < chunks) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float e0 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i]), kLog2e, -m_ref));
-              const float e1 = fast_exp2(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), kLog2e, -m_ref));
-              pk[i] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
-            }
-            tmem_st16(tmem_p + c * 16, pk);
-          }
-        }
-        if (pingpong) named_bar_arrive(1 + (t ^ 1), 256);
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 7);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[b]);
-        if (quad == 2) ATT_TRACE(j, 8 * t + 8 + 5);
-      }
-      if (pingpong && t == 0) named_bar_sync(1, 256);   // consume tile 1's last hand-over
-      // the last PV implies all earlier ones (commits are ordered)
-      mbar_wait(&pv_done[(kv_tiles - 1) & 1], ((kv_tiles - 1) >> 1) & 1);
+      if (quad == 2) ATT_TRACE(j, 8);
+      mbar_wait(&s_full[b], ph);
       tc_fence_after();
-      const int q_idx = pair * (ATT_QT * ATT_BLOCK_Q) + t * ATT_BLOCK_Q + row;   // body index of this thread's query
-      float inv;
-      {
-        uint32_t r[16];
-        tmem_ld16(tmem_tile + ATT_COL_L, r);
-        tmem_ld_wait();
-        inv = 1.f / (__uint_as_float(r[0]) + w_extra);
+      if (quad == 2) ATT_TRACE(j, 9);
+      uint32_t s[64];
+      tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      if (chunks > 1) tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
+      if (quad == 2) ATT_TRACE(j, 10);
+
+      if (valid < ATT_BLOCK_KV) {            // tail tile only: mask keys past the sequence end
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
-      const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + head * ATT_D);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + head * ATT_D);
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
 #pragma unroll
-      for (int c = 0; c < ATT_D / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_o + c * 32, r);
-        tmem_ld_wait();
-        if (q_idx < p.q_len) {
+      for (int i = 0; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s[i]));
+      const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+      if (quad == 2) ATT_TRACE(j, 11);
+
+      {
+        const bool jump = m_tile > m_ref + kRescaleThreshold;   // always true for j == 0 without an extra key
+        if (__any_sync(0xffffffffu, jump)) { // rare after the first tiles: rescale O in TMEM
+          const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
+          if (jump) { m_ref = m_tile; w_extra *= alpha; }
+          if (j > 0) {
+            // every PV up to tile j-1 must have executed before O is touched (pv_done[(j-1)%2] is the newest phase
+            // of that barrier)
+            mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < ATT_D / 16 + 1; ++c) {   // O and, right behind it, the row sums L
+              uint32_t r[16];
+              tmem_ld16(tmem_o + c * 16, r);
+              tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]);
-            if (p.extra) {
-              const uint4 xv = __ldg(vx + c * 4 + i);
-              v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
-              v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
-              v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
-              v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
+              for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st16(tmem_o + c * 16, r);
             }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] *= inv;
-            dst[c * 4 + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
+        }
+      }
+      if (quad == 2) ATT_TRACE(j, 12);
+
+      // P = exp2(s log2e - m_ref), truncated to bf16 by the PRMT that packs two of them; the row sum of exactly those
+      // bf16 values comes from the tensor core (L += P * ones), so P / l is an exact softmax of the weights the PV MMA
+      // uses, and the CUDA cores spend 2.5 instructions per element (FFMA, MUFU, half a PRMT).
+      // Software-pipelined by hand: the pair (2k, 2k+1) is packed kExpDist pairs after its exponentials were issued.
+      // ptxas otherwise puts each PRMT right behind its two MUFU.EX2 and the warp then waits out the full MUFU latency
+      // (~40 clk) for every pair. The PRMT selector carries a data dependence on a LATER exponential (its sign bit,
+      // always 0), which ptxas cannot hoist over.
+      constexpr int kExpDist = 4;
+      constexpr int kPolyEvery = VFM_ATT_POLY;   // 0: all exponentials on the MUFU pipe; n: one in 2n on the FMA pipe
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < chunks) {
+          uint32_t pk[16];
+          uint32_t* sc = &s[c * 32];
+#pragma unroll
+          for (int i = 0; i < 16 + kExpDist; ++i) {
+            if (i < 16) {
+              sc[2 * i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(sc[2 * i]), kLog2e, -m_ref)));
+              // every kPolyEvery-th pair computes its odd element on the FMA/ALU pipes (degree-3 polynomial, relative
+              // error 1e-4, 40x below bf16 resolution): the MUFU pipe (16 ex2/clk/SM) is the busiest unit of this kernel
+              const float x1 = fmaf(__uint_as_float(sc[2 * i + 1]), kLog2e, -m_ref);
+              sc[2 * i + 1] = __float_as_uint(kPolyEvery != 0 && (i % (kPolyEvery ? kPolyEvery : 1)) == 0 ? poly_exp2(x1) : fast_exp2(x1));
+            }
+            if (i >= kExpDist) {
+              const int k = i - kExpDist;
+              const uint32_t sel = i < 16 ? __umulhi(sc[2 * i], 2u) + 0x7632u : 0x7632u;   // 0x7632 + sign bit (= 0)
+              pk[k] = __byte_perm(sc[2 * k], sc[2 * k + 1], sel);
+            }
+          }
+          tmem_st16(tmem_s + c * 16, pk);   // P_j overwrites the first half of S_j (last read by this thread itself)
+        }
+      }
+      if (quad == 2) ATT_TRACE(j, 15);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);   // one arrival per warp
+      if (quad == 2) ATT_TRACE(j, 13);
+    }
+    // the last PV implies all earlier ones (commits are ordered)
+    mbar_wait(&pv_done[(kv_tiles - 1) & 1], ((kv_tiles - 1) >> 1) & 1);
+    tc_fence_after();
+    const int q_idx = qt * ATT_BLOCK_Q + row;   // body index of this thread's query
+    float inv;
+    {
+      uint32_t r[16];
+      tmem_ld16(tmem_tile + ATT_COL_L, r);
+      tmem_ld_wait();
+      inv = 1.f / (__uint_as_float(r[0]) + w_extra);
+    }
+    const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + head * ATT_D);
+    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + head * ATT_D);
+#pragma unroll
+    for (int c = 0; c < ATT_D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + c * 32, r);
+      tmem_ld_wait();
+      if (q_idx < p.q_len) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]);
+          if (p.extra) {
+            const uint4 xv = __ldg(vx + c * 4 + i);
+            v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
+            v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
+            v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
+            v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= inv;
+          dst[c * 4 + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
       }
     }
@@ -534,7 +511,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
   }
