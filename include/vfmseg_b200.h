@@ -208,6 +208,40 @@ int vfm_linear_head_forward(const VfmLinearHeadParams* p /*host*/, const void* t
                             int gh, int gw, float* lowres, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* ---------------------------------------------------------------- coarse-to-fine path (MsVFMEncoderDecoder + VFMHead)
+ * Stage 0 of ms_inference yields coarse logits low0 [n_img, nc, lh, lw] (fp32) for the whole down-scaled image; the
+ * reference upsamples them to the full image and slices "context" windows (Ms_VFM_encoder_decoder.py:417,443). These
+ * entry points sample low0 with the same bilinear (align_corners=False) arithmetic instead of storing that field. */
+
+/* resize(inputs, size=(h, w), bilinear) of the network input, Ms_VFM_encoder_decoder.py:413, fused with mmseg
+ * SegDataPreProcessor when the input is uint8 (configs/_base_/models/lora_dinov2_ms_masked.py:5-13). out: fp32 [B,3,h,w]. */
+int vfm_image_resize_norm(const void* img, int is_u8, const VfmPixelNorm* nrm, int B, int H, int W, float* out, int h, int w,
+                          void* stream);
+/* counts[b * n_crops + k] = #pixels of window k of image b with max softmax(context) > thr
+ * (Ms_VFM_encoder_decoder.py:446-448; the host compares count / (crop_h*crop_w) with test_cfg.conf). boxes: {y1, x1}. */
+int vfm_ms_confidence(const float* low0, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh, int lw, int H,
+                      int W, int n_img, float thr, int* counts, void* stream);
+/* GEMM operand of VFMHead.seg_logits_embed[0] (Conv2d(nc, C/4, 2, 2), VFMHead.py:38-39) for the refined windows:
+ * context window -> resize to (ctx_h, ctx_w) (VFMHead.py:63-67) -> 2x2 patches; out bf16 [n_ref*ctx_h/2*ctx_w/2, kpad],
+ * column = cin*4 + dy*2 + dx, zero padded. crops: n_ref x {image, y1, x1, 0}. */
+int vfm_ms_context_im2col(const float* low0, const int* crops, int n_ref, int nc, int crop_h, int crop_w, int lh, int lw, int H,
+                          int W, int ctx_h, int ctx_w, void* out, int kpad, void* stream);
+/* GEMM operand of a Conv2d(C, C', 2, 2) over token-major bf16 activations [n*h*w, C] (VFMHead.py:42):
+ * out [n*h/2*w/2, 4C], column = (dy*2+dx)*C + c. */
+int vfm_space_to_depth2(const void* in, void* out, int n, int h, int w, int C, void* stream);
+/* GroupNorm(groups, C) + activation over token-major bf16 [n*P, C], any channels-per-group; act 0 none / 1 ReLU /
+ * 2 exact-erf GELU; out bf16, or fp32 when out_f32 (VFMHead.py:30-32,40-47; Transformer.py:91-92,247). */
+int vfm_groupnorm_act(const void* in, void* out, int out_f32, const float* gamma, const float* beta, int n, int P, int C, int groups,
+                      float eps, int act, void* stream);
+/* GEGLU, Transformer.py:52-59: in bf16 [M, 2I] = (x | gate) -> out bf16 [M, I] = x * gelu(gate). */
+int vfm_geglu(const void* in, void* out, long long M, int I, void* stream);
+int vfm_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* Stage-1 merge of ms_inference (Ms_VFM_encoder_decoder.py:449-461) + argmax: windows with ref_index >= 0 contribute
+ * refined[ref_index] ([nc, rh, rw] resized to the window), the others the context value; sum / count; first max wins. */
+int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_index, const int* boxes, int n_crops, int nc,
+                        int crop_h, int crop_w, int lh, int lw, int rh, int rw, int H, int W, int n_img, uint8_t* labels,
+                        float* logits_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

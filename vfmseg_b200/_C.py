@@ -62,6 +62,14 @@ SIGNATURES = {
     "vfm_attention_fwd": (_i, [_p, _p, _i, _i, _i, _p]),
     "vfm_attention_fwd_ex": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vfm_attention_cross": (_i, [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "vfm_image_resize_norm": (_i, [_p, _i, C.POINTER(VfmPixelNorm), _i, _i, _i, _p, _i, _i, _p]),
+    "vfm_ms_confidence": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p]),
+    "vfm_ms_context_im2col": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "vfm_space_to_depth2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "vfm_groupnorm_act": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "vfm_geglu": (_i, [_p, _p, _ll, _i, _p]),
+    "vfm_cast_f32_bf16": (_i, [_p, _p, _ll, _p]),
+    "vfm_ms_merge_argmax": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "vfm_patch_gather": (_i, [_p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i, _p, _p]),
     "vfm_cls_rows": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vfm_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),

@@ -15,6 +15,7 @@
 #include "attention_sm100.cuh"
 #include "elementwise.cuh"
 #include "gemm_sm100.cuh"
+#include "ms_refine.cuh"
 #include "slide_tail.cuh"
 
 using namespace vfm;
@@ -504,6 +505,136 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
           lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
   }
   VFM_LAUNCH_CHECK("slide_merge_argmax");
+  return VFM_OK;
+}
+
+// ------------------------------------------------------------------------------ coarse-to-fine path (config 3)
+static unsigned grid_for(long long work_items, int per_sm = 16) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+int vfm_image_resize_norm(const void* img, int is_u8, const VfmPixelNorm* nrm, int B, int H, int W, float* out, int h, int w,
+                          void* stream) {
+  if (!img || !out || B <= 0 || H <= 0 || W <= 0 || h <= 0 || w <= 0) return fail(VFM_ERR_INVALID, "image_resize_norm: bad args");
+  if (is_u8 && !nrm) return fail(VFM_ERR_INVALID, "image_resize_norm: uint8 input needs a VfmPixelNorm");
+  PixelNorm pn{};
+  if (nrm) {
+    for (int i = 0; i < 3; ++i) { pn.mean[i] = nrm->mean[i]; pn.inv_std[i] = nrm->inv_std[i]; }
+    pn.flip = nrm->flip;
+  }
+  const unsigned grid = grid_for(static_cast<long long>(B) * 3 * h * w);
+  {
+    LaunchScope scope("image_resize_norm", S(stream));
+    if (is_u8)
+      image_resize_norm_kernel<uint8_t><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const uint8_t*>(img), B, H, W, pn, out, h, w);
+    else
+      image_resize_norm_kernel<float><<<grid, 256, 0, S(stream)>>>(reinterpret_cast<const float*>(img), B, H, W, pn, out, h, w);
+  }
+  VFM_LAUNCH_CHECK("image_resize_norm");
+  return VFM_OK;
+}
+
+int vfm_ms_confidence(const float* low0, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh, int lw, int H,
+                      int W, int n_img, float thr, int* counts, void* stream) {
+  if (!low0 || !boxes || !counts || n_crops <= 0 || nc <= 0 || nc > 32 || n_img <= 0) return fail(VFM_ERR_INVALID, "ms_confidence: bad args");
+  VFM_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * static_cast<size_t>(n_img) * n_crops, S(stream)));
+  const int rows = 4;
+  const unsigned grid = static_cast<unsigned>(n_img) * ((H + rows - 1) / rows);
+  const size_t smem = (sizeof(int) + sizeof(int2)) * n_crops + 8;
+  {
+    LaunchScope scope("ms_confidence", S(stream));
+    if (nc <= 19)
+      ms_confidence_kernel<19><<<grid, 256, smem, S(stream)>>>(low0, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
+                                                               lh, lw, H, W, thr, rows, counts);
+    else
+      ms_confidence_kernel<32><<<grid, 256, smem, S(stream)>>>(low0, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
+                                                               lh, lw, H, W, thr, rows, counts);
+  }
+  VFM_LAUNCH_CHECK("ms_confidence");
+  return VFM_OK;
+}
+
+int vfm_ms_context_im2col(const float* low0, const int* crops, int n_ref, int nc, int crop_h, int crop_w, int lh, int lw, int H,
+                          int W, int ctx_h, int ctx_w, void* out, int kpad, void* stream) {
+  if (!low0 || !crops || !out || n_ref <= 0 || nc <= 0 || (ctx_h & 1) || (ctx_w & 1) || kpad < 4 * nc || (kpad % 8))
+    return fail(VFM_ERR_INVALID, "ms_context_im2col: bad args (kpad >= 4*nc, kpad %% 8 == 0, even context size)");
+  const long long total = static_cast<long long>(n_ref) * (ctx_h / 2) * (ctx_w / 2) * (kpad / 4);
+  {
+    LaunchScope scope("ms_context_im2col", S(stream));
+    ms_context_im2col_kernel<<<grid_for(total), 256, 0, S(stream)>>>(low0, reinterpret_cast<const int4*>(crops), n_ref, nc, crop_h,
+                                                                     crop_w, lh, lw, H, W, ctx_h, ctx_w, BF(out), kpad);
+  }
+  VFM_LAUNCH_CHECK("ms_context_im2col");
+  return VFM_OK;
+}
+
+int vfm_space_to_depth2(const void* in, void* out, int n, int h, int w, int C, void* stream) {
+  if (!in || !out || n <= 0 || (h & 1) || (w & 1) || C <= 0 || (C % 8)) return fail(VFM_ERR_INVALID, "space_to_depth2: bad args (even h, w; C %% 8 == 0)");
+  const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 4 * (C / 8);
+  {
+    LaunchScope scope("space_to_depth2", S(stream));
+    space_to_depth2_kernel<<<grid_for(total), 256, 0, S(stream)>>>(BF(in), BF(out), n, h, w, C);
+  }
+  VFM_LAUNCH_CHECK("space_to_depth2");
+  return VFM_OK;
+}
+
+int vfm_groupnorm_act(const void* in, void* out, int out_f32, const float* gamma, const float* beta, int n, int P, int C, int groups,
+                      float eps, int act, void* stream) {
+  if (!in || !out || !gamma || !beta || n <= 0 || P <= 0 || groups <= 0 || C % groups || act < 0 || act > 2)
+    return fail(VFM_ERR_INVALID, "groupnorm_act: bad args");
+  {
+    LaunchScope scope("groupnorm_act", S(stream));
+    if (out_f32)
+      groupnorm_act_kernel<float><<<n * groups, 256, 0, S(stream)>>>(BF(in), reinterpret_cast<float*>(out), gamma, beta, P, C, groups, eps, act);
+    else
+      groupnorm_act_kernel<__nv_bfloat16><<<n * groups, 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, P, C, groups, eps, act);
+  }
+  VFM_LAUNCH_CHECK("groupnorm_act");
+  return VFM_OK;
+}
+
+int vfm_geglu(const void* in, void* out, long long M, int I, void* stream) {
+  if (!in || !out || M <= 0 || I <= 0 || (I % 8)) return fail(VFM_ERR_INVALID, "geglu: bad args (I %% 8 == 0)");
+  {
+    LaunchScope scope("geglu", S(stream));
+    geglu_kernel<<<grid_for(M * (I / 8)), 256, 0, S(stream)>>>(BF(in), BF(out), M, I);
+  }
+  VFM_LAUNCH_CHECK("geglu");
+  return VFM_OK;
+}
+
+int vfm_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  if (!in || !out || n <= 0 || (n % 4)) return fail(VFM_ERR_INVALID, "cast_f32_bf16: bad args (n %% 4 == 0)");
+  {
+    LaunchScope scope("cast_f32_bf16", S(stream));
+    cast_f32_bf16_kernel<<<grid_for(n / 4), 256, 0, S(stream)>>>(in, BF(out), n / 4);
+  }
+  VFM_LAUNCH_CHECK("cast_f32_bf16");
+  return VFM_OK;
+}
+
+int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_index, const int* boxes, int n_crops, int nc,
+                        int crop_h, int crop_w, int lh, int lw, int rh, int rw, int H, int W, int n_img, uint8_t* labels,
+                        float* logits_out, void* stream) {
+  if (!low0 || !ref_index || !boxes || !labels || n_crops <= 0 || nc <= 0 || nc > 32 || n_img <= 0)
+    return fail(VFM_ERR_INVALID, "ms_merge_argmax: bad args (num_classes <= 32)");
+  const unsigned grid = grid_for(static_cast<long long>(n_img) * H * W, 32);
+  const size_t smem = sizeof(int2) * n_crops;
+  {
+    LaunchScope scope("ms_merge_argmax", S(stream));
+    if (nc <= 19)
+      ms_merge_argmax_kernel<19><<<grid, 256, smem, S(stream)>>>(low0, refined, ref_index, reinterpret_cast<const int2*>(boxes), n_crops,
+                                                                 nc, crop_h, crop_w, lh, lw, rh, rw, H, W, n_img, labels, logits_out);
+    else
+      ms_merge_argmax_kernel<32><<<grid, 256, smem, S(stream)>>>(low0, refined, ref_index, reinterpret_cast<const int2*>(boxes), n_crops,
+                                                                 nc, crop_h, crop_w, lh, lw, rh, rw, H, W, n_img, labels, logits_out);
+  }
+  VFM_LAUNCH_CHECK("ms_merge_argmax");
   return VFM_OK;
 }
 

@@ -182,3 +182,76 @@ def resize_bilinear(low, size):
     boxes = torch.zeros(1, 2, dtype=torch.int32, device=low.device)
     _, logits = slide_merge_argmax(low.contiguous(), boxes, B, tuple(size), tuple(size), want_logits=True)
     return logits
+
+
+# ------------------------------------------------------------------ coarse-to-fine path (config 3)
+def image_resize_norm(img, size, norm: _C.VfmPixelNorm | None = None):
+    """Bilinear (align_corners=False) resize of [B,3,H,W] uint8 (normalised on the fly) or fp32 input -> fp32 [B,3,h,w]."""
+    is_u8 = img.dtype == torch.uint8
+    assert is_u8 or img.dtype == torch.float32
+    B, _, H, W = img.shape
+    out = torch.empty(B, 3, size[0], size[1], device=img.device, dtype=torch.float32)
+    _C.call("vfm_image_resize_norm", _ptr(img), int(is_u8), C.byref(norm) if norm is not None else None, B, H, W, _f32(out),
+            size[0], size[1], _stream())
+    return out
+
+
+def ms_confidence(low0, boxes, crop_hw, out_hw, thr):
+    """int32 [n_img, n_crops]: pixels per window whose max softmax of the upsampled coarse logits exceeds thr."""
+    n_img, nc, lh, lw = low0.shape
+    n_crops = boxes.shape[0]
+    counts = torch.empty(n_img, n_crops, device=low0.device, dtype=torch.int32)
+    _C.call("vfm_ms_confidence", _f32(low0), _ptr(boxes), n_crops, nc, crop_hw[0], crop_hw[1], lh, lw, out_hw[0], out_hw[1],
+            n_img, float(thr), _ptr(counts), _stream())
+    return counts
+
+
+def ms_context_im2col(low0, crops, crop_hw, out_hw, ctx_hw, kpad):
+    n_img, nc, lh, lw = low0.shape
+    n_ref = crops.shape[0]
+    out = torch.empty(n_ref * (ctx_hw[0] // 2) * (ctx_hw[1] // 2), kpad, device=low0.device, dtype=torch.bfloat16)
+    _C.call("vfm_ms_context_im2col", _f32(low0), _ptr(crops), n_ref, nc, crop_hw[0], crop_hw[1], lh, lw, out_hw[0], out_hw[1],
+            ctx_hw[0], ctx_hw[1], _bf16(out), kpad, _stream())
+    return out
+
+
+def space_to_depth2(x, n, h, w):
+    Cc = x.shape[1]
+    out = torch.empty(n * (h // 2) * (w // 2), 4 * Cc, device=x.device, dtype=torch.bfloat16)
+    _C.call("vfm_space_to_depth2", _bf16(x), _bf16(out), n, h, w, Cc, _stream())
+    return out
+
+
+def groupnorm_act(x, gamma, beta, n, groups, eps, act=0, out_f32=False):
+    """act: 0 none, 1 ReLU, 2 GELU(erf). x bf16 [n*P, C]."""
+    R, Cc = x.shape
+    out = torch.empty(R, Cc, device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    _C.call("vfm_groupnorm_act", _bf16(x), _ptr(out), int(out_f32), _f32(gamma), _f32(beta), n, R // n, Cc, groups, float(eps),
+            int(act), _stream())
+    return out
+
+
+def geglu(x):
+    M, I2 = x.shape
+    out = torch.empty(M, I2 // 2, device=x.device, dtype=torch.bfloat16)
+    _C.call("vfm_geglu", _bf16(x), _bf16(out), M, I2 // 2, _stream())
+    return out
+
+
+def cast_f32_bf16(x):
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _C.call("vfm_cast_f32_bf16", _f32(x), _bf16(out), x.numel(), _stream())
+    return out
+
+
+def ms_merge_argmax(low0, refined, ref_index, boxes, crop_hw, out_hw, want_logits=False):
+    """low0 fp32 [n_img,nc,lh,lw]; refined fp32 [n_ref,nc,rh,rw] (or None); ref_index int32 [n_img,n_crops]; boxes int32 [n_crops,2]."""
+    n_img, nc, lh, lw = low0.shape
+    n_crops = boxes.shape[0]
+    H, W = out_hw
+    rh, rw = (refined.shape[2], refined.shape[3]) if refined is not None else (1, 1)
+    labels = torch.empty(n_img, H, W, device=low0.device, dtype=torch.uint8)
+    logits = torch.empty(n_img, nc, H, W, device=low0.device, dtype=torch.float32) if want_logits else None
+    _C.call("vfm_ms_merge_argmax", _f32(low0), _f32(refined), _ptr(ref_index), _ptr(boxes), n_crops, nc, crop_hw[0], crop_hw[1],
+            lh, lw, rh, rw, H, W, n_img, _ptr(labels), _f32(logits), _stream())
+    return labels, logits
