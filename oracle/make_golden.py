@@ -94,9 +94,67 @@ def vitl_crop():
                         lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8))
 
 
+def build_reference_ms(cfg, sd):
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_ms_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not [m for m in missing if "num_batches_tracked" not in m], missing
+    return model.eval()
+
+
+def ms_gate_constants(model, x, cfg):
+    """threshold / conf for the tiny model: random weights never reach the shipped 0.968 / 0.8, so pick a threshold at
+    the median max-softmax and a conf in the widest gap of the per-window fractions — both branches of
+    Ms_VFM_encoder_decoder.py:449-452 run and no decision is borderline."""
+    import torch.nn.functional as F
+    with torch.no_grad():
+        lr = F.interpolate(x, size=(512, 1024), mode="bilinear", align_corners=False)
+        seg = model.whole_inference(lr, [dict(img_shape=x.shape[2:], ori_shape=x.shape[2:])])
+    thr = float(torch.softmax(seg, 1).max(1)[0].median())
+    fr = []
+    for (y1, y2, x1, x2) in torch_ref.slide_boxes(x.shape[2], x.shape[3], cfg["test_cfg"]["crop_size"], cfg["test_cfg"]["stride"]):
+        c = seg[:, :, y1:y2, x1:x2]
+        fr.append((torch.softmax(c, 1).max(1)[0] > thr).float().mean().item())
+    srt = sorted(fr)
+    gaps = [(srt[i + 1] - srt[i], i) for i in range(len(srt) - 1)]
+    g, i = max(gaps[len(gaps) // 4: 3 * len(gaps) // 4 + 1] or gaps)
+    return thr, 0.5 * (srt[i] + srt[i + 1]), fr
+
+
+def tiny_ms():
+    """tiny_ms.npz: MsVFMEncoderDecoder (tiny backbone + LinearHead + VFMHead/MaskTransformerDecoder depth 2),
+    mode ms_slide_inference on one 128x192 image (crop 64 / stride 43 -> 3x4 windows): reference logits, labels, the
+    per-window confidence fractions and refine decisions, and one standalone VFMHead.forward call."""
+    cfg = synthetic.tiny_ms_config()
+    sd = synthetic.synthetic_ms_state_dict(cfg, seed=0)
+    model = build_reference_ms(cfg, sd)
+    img = synthetic.synthetic_images(1, 128, 192, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    thr, conf, fr = ms_gate_constants(model, x, cfg)
+    model.test_cfg["threadshod"], model.test_cfg["conf"] = thr, conf
+    metas = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)]
+    with torch.no_grad():
+        logits = model.inference(x, metas)
+        # standalone head call (VFMHead.forward with the decoder's mask off), window (0, 0)
+        model.aux_decoder.transformer_decoder.mask_enable = False
+        lr = torch.nn.functional.interpolate(x, size=(512, 1024), mode="bilinear", align_corners=False)
+        seg = model.whole_inference(lr, metas)
+        feats = model.extract_feat(x[:, :, :64, :64])
+        head_out = model.aux_decoder(feats, seg[:, :, :64, :64])
+    refined = [f < conf for f in fr]
+    print("tiny_ms thr", thr, "conf", conf, "refined", refined)
+    assert any(refined) and not all(refined)
+    np.savez_compressed(GOLDEN / "tiny_ms.npz", logits=logits.numpy().astype(np.float16), labels=logits.argmax(1).numpy().astype(np.uint8),
+                        threshold=np.float64(thr), conf=np.float64(conf), fracs=np.array(fr), refined=np.array(refined),
+                        head_out=head_out.numpy())
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop"]
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms"]
     for w in which:
         globals()[w]()

@@ -240,6 +240,11 @@ class EncoderDecoder(BaseModule):
         self.train_cfg = ConfigDict(train_cfg or {})
         self.test_cfg = ConfigDict(test_cfg or {})
         self.data_preprocessor_cfg = data_preprocessor
+        if isinstance(data_preprocessor, dict) and "mean" in data_preprocessor:
+            # mmengine BaseModel builds the preprocessor; MsVFMEncoderDecoder.__init__ reads its .mean / .std (:106-107)
+            self.data_preprocessor = types.SimpleNamespace(
+                mean=torch.tensor(data_preprocessor["mean"], dtype=torch.float32).view(-1, 1, 1),
+                std=torch.tensor(data_preprocessor["std"], dtype=torch.float32).view(-1, 1, 1))
 
     def extract_feat(self, inputs):
         return self.backbone(inputs)
@@ -506,6 +511,20 @@ def build_reference_segmentor(model_cfg: dict, backbone_ckpt_path: str):
     cfg = dict(model_cfg)
     cfg["checkpoint"] = backbone_ckpt_path
     cfg.pop("data_preprocessor", None)
+    m = MODELS.build(cfg)
+    m.eval()
+    return m
+
+
+def build_reference_ms_segmentor(model_cfg: dict, backbone_ckpt_path: str):
+    """MODELS.build of the reference's MsVFMEncoderDecoder (LoRABackbone + LinearHead + VFMHead / MaskTransformerDecoder)
+    from a config dict shaped like configs/_base_/models/lora_dinov2_ms_masked.py."""
+    load("models.backbones.dino_v2", "models.backbones.lora_backbone", "models.heads.linear_head", "models.heads.Transformer",
+         "models.heads.VFMHead", "models.segmentors.Ms_VFM_encoder_decoder")
+    import copy
+    cfg = copy.deepcopy(model_cfg)
+    cfg["backbone"]["checkpoint"] = backbone_ckpt_path
+    cfg["train_cfg"] = ConfigDict({k: (ConfigDict(v) if isinstance(v, dict) else v) for k, v in cfg.get("train_cfg", {}).items()})
     m = MODELS.build(cfg)
     m.eval()
     return m

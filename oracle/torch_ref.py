@@ -221,6 +221,107 @@ def postprocess(seg_logits: Tensor) -> Tensor:
     return seg_logits.argmax(dim=1, keepdim=True)
 
 
+# --------------------------------------------------------------------------- coarse-to-fine (config 3)
+def split_ms_state_dict(sd: Dict[str, Tensor]):
+    """MsVFMEncoderDecoder state dict -> (backbone, decode_head, aux_decoder) dicts; prefixes
+    'backbone.model.base_model.model.' (LoRABackbone, lora_backbone.py:23), 'decode_head.', 'aux_decoder.'
+    (Ms_VFM_encoder_decoder.py:112)."""
+    bb, hd, aux = {}, {}, {}
+    for k, v in sd.items():
+        for pre, dst in (("backbone.model.base_model.model.", bb), ("decode_head.", hd), ("aux_decoder.", aux)):
+            if k.startswith(pre):
+                dst[k[len(pre):]] = v
+    return bb, hd, aux
+
+
+def _cross_attention(x: Tensor, context: Tensor, sd, pre: str, heads: int) -> Tensor:
+    """CrossAttention._forward, rein/models/heads/Transformer.py:113-136 (mask=None; MemEffAttention.forward :140-142
+    falls back to it when xformers is absent)."""
+    q = F.linear(x, sd[pre + ".to_q.weight"])
+    k = F.linear(context, sd[pre + ".to_k.weight"])
+    v = F.linear(context, sd[pre + ".to_v.weight"])
+    B, N, inner = q.shape
+    d = inner // heads
+    q, k, v = (t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    sim = torch.einsum("bhid,bhjd->bhij", q, k) * d ** -0.5
+    out = torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+    out = out.permute(0, 2, 1, 3).reshape(B, N, inner)
+    return F.linear(out, sd[pre + ".to_out.0.weight"], sd[pre + ".to_out.0.bias"])
+
+
+def transformer_decoder_forward(query: Tensor, img_feats: Tensor, sd, *, heads: int, depth: int, pre: str = "transformer_decoder") -> Tensor:
+    """MaskTransformerDecoder.forward with mask_enable=False, Transformer.py:270-283 (= TransformerDecoder.forward
+    :242-252): GroupNorm(32, eps 1e-6) of the query (:91-92), tokens, `depth` BasicTransformerBlocks (:173-177: self
+    attention, cross attention on img_feats, GEGLU feed-forward :52-79; nn.LayerNorm eps 1e-5), back to NCHW."""
+    B, C, h, w = img_feats.shape
+    x = F.group_norm(query, 32, sd[pre + ".norm.weight"], sd[pre + ".norm.bias"], 1e-6)
+    x = x.flatten(2).transpose(1, 2)
+    ctx = img_feats.flatten(2).transpose(1, 2)
+    for i in range(depth):
+        b = f"{pre}.transformer_blocks.{i}"
+        ln = lambda t, n: F.layer_norm(t, (C,), sd[f"{b}.{n}.weight"], sd[f"{b}.{n}.bias"], 1e-5)
+        x = _cross_attention(ln(x, "norm1"), ln(x, "norm1"), sd, b + ".attn1", heads) + x
+        x = _cross_attention(ln(x, "norm2"), ctx, sd, b + ".attn2", heads) + x
+        u = F.linear(ln(x, "norm3"), sd[b + ".ff.net.0.proj.weight"], sd[b + ".ff.net.0.proj.bias"])
+        a, gate = u.chunk(2, dim=-1)
+        x = F.linear(a * F.gelu(gate), sd[b + ".ff.net.2.weight"], sd[b + ".ff.net.2.bias"]) + x
+    return x.transpose(1, 2).reshape(B, C, h, w)
+
+
+def vfm_head_forward(feats: Sequence[Tensor], seg_logits: Tensor, sd, *, heads: int, depth: int) -> Tensor:
+    """VFMHead.forward, rein/models/heads/VFMHead.py:61-89: context resized to 4x the feature grid (:63-67), fuse_conv
+    (1x1 conv + GroupNorm(32) + GELU, :28-33), seg_logits_embed (two k2s2 convs + GN + GELU, 1x1 conv + GN, :38-49),
+    decoder(query=img_feats, img_feats=seg_logits_embed) (:82), cls_seg (:87). `sd` holds un-prefixed aux_decoder keys."""
+    h, w = feats[0].shape[2:]
+    ctx = F.interpolate(seg_logits, size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
+    f = F.conv2d(torch.cat(list(feats), dim=1), sd["fuse_conv.0.weight"], sd["fuse_conv.0.bias"])
+    f = F.gelu(F.group_norm(f, 32, sd["fuse_conv.1.weight"], sd["fuse_conv.1.bias"], 1e-5))
+    e = F.conv2d(ctx, sd["seg_logits_embed.0.weight"], sd["seg_logits_embed.0.bias"], stride=2)
+    e = F.gelu(F.group_norm(e, 32, sd["seg_logits_embed.1.weight"], sd["seg_logits_embed.1.bias"], 1e-5))
+    e = F.conv2d(e, sd["seg_logits_embed.3.weight"], sd["seg_logits_embed.3.bias"], stride=2)
+    e = F.gelu(F.group_norm(e, 32, sd["seg_logits_embed.4.weight"], sd["seg_logits_embed.4.bias"], 1e-5))
+    e = F.conv2d(e, sd["seg_logits_embed.6.weight"], sd["seg_logits_embed.6.bias"])
+    e = F.group_norm(e, 32, sd["seg_logits_embed.7.weight"], sd["seg_logits_embed.7.bias"], 1e-5)
+    out = transformer_decoder_forward(f, e, sd, heads=heads, depth=depth)
+    return F.conv2d(out, sd["conv_seg.weight"], sd["conv_seg.bias"])
+
+
+def ms_inference(inputs: Tensor, sd3, cfg, *, crop, stride, threshold: float, conf: float, lr_size=(512, 1024),
+                 return_info: bool = False):
+    """MsVFMEncoderDecoder.ms_inference, rein/models/segmentors/Ms_VFM_encoder_decoder.py:400-466.
+    stage 0 (:413,420): inputs resized to `lr_size` (hard-coded (512, 1024) there), whole_inference, whose
+    predict_by_feat [3P] resizes the head output to metas['img_shape'] = the ORIGINAL image size; the :417 resize at
+    stage 1 is then the identity. stage 1 (:424-461): per window, context = crop of those logits; refine with the aux
+    decoder when mean(max softmax(context) > threshold) < conf (batch mean, :446-449), else reuse the context."""
+    bb, hd, aux = sd3
+    B, _, H, W = inputs.shape
+    vit = dict(depth=cfg["depth"], num_heads=cfg["num_heads"], patch=cfg.get("patch", 16), out_indices=cfg["out_indices"],
+               lora_scale=cfg.get("lora_scale", 1.0))
+    lr = F.interpolate(inputs, size=tuple(lr_size), mode="bilinear", align_corners=False)
+    low0 = linear_head_forward(dino_forward(lr, bb, **vit), hd, groups=cfg.get("groups", 32))
+    seg = F.interpolate(low0, size=(H, W), mode="bilinear", align_corners=False)
+    preds = inputs.new_zeros((B, seg.shape[1], H, W))
+    count = inputs.new_zeros((B, 1, H, W))
+    fracs, refined = [], []
+    for (y1, y2, x1, x2) in slide_boxes(H, W, crop, stride):
+        context = seg[:, :, y1:y2, x1:x2]
+        confidence = (torch.softmax(context, dim=1).max(dim=1)[0] > threshold).float().mean().item()
+        fracs.append(confidence)
+        if confidence < conf:
+            feats = dino_forward(inputs[:, :, y1:y2, x1:x2], bb, **vit)
+            logit = vfm_head_forward(feats, context, aux, heads=cfg["aux_heads"], depth=cfg["aux_depth"])
+            refined.append(True)
+        else:
+            logit = context
+            refined.append(False)
+        logit = F.interpolate(logit, size=(y2 - y1, x2 - x1), mode="bilinear", align_corners=False)
+        preds += F.pad(logit, (int(x1), int(W - x2), int(y1), int(H - y2)))
+        count[:, :, y1:y2, x1:x2] += 1
+    assert (count == 0).sum() == 0
+    out = preds / count
+    return (out, dict(low0=low0, fracs=fracs, refined=refined)) if return_info else out
+
+
 # --------------------------------------------------------------------------- metric (integer/np)
 def intersect_and_union(pred: Tensor, label: Tensor, num_classes: int, ignore_index: int):
     """mmseg IoUMetric.intersect_and_union [3P] as called from rein/dg_metrics.py:50-52:

@@ -38,7 +38,7 @@ def _check_logits(got, ref, what, frac=0.999):
     assert f >= frac, f"{what}: only {f:.5f} of logits within bf16 tolerance (max err {err.max().item():.4g}, rms {rms.item():.4g})"
 
 
-def _check_labels(got_labels, ref_logits, what):
+def _check_labels(got_labels, ref_logits, what, raw_min=0.99, top2_min=0.9999):
     """Label agreement with the reference argmax.
 
     With random-init weights the 19 logits of a pixel are near-tied far more often than in a trained
@@ -67,8 +67,8 @@ def _check_labels(got_labels, ref_logits, what):
         msg.append(f"margin>{k}*rms: kept {mk.float().mean().item():.4f}, agreement {same[mk].float().mean().item():.6f}")
     print("; ".join(msg))
     assert dec >= 0.999, msg[0]
-    assert raw >= 0.99, msg[0]
-    assert runner_up.float().mean().item() >= 0.9999, msg[0]
+    assert raw >= raw_min, msg[0]
+    assert runner_up.float().mean().item() >= top2_min, msg[0]
 
 
 def _oracle_cfg(cfg):

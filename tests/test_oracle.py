@@ -104,3 +104,56 @@ def test_oracle_against_live_reference_modules():
         want = ref.inference(x, meta)
         got = torch_ref.slide_inference(x, torch_ref.split_state_dict(sd), _cfg_of(cfg), crop=(64, 64), stride=(32, 32))
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ coarse-to-fine path (BASELINE config 3)
+def _ms_cfg_of(cfg):
+    bb, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    tr = cfg["aux_head"]["transformer"]
+    return dict(depth=bb["depth"], num_heads=bb["num_heads"], patch=bb["patch_size"], out_indices=tuple(bb["out_indices"]),
+                lora_scale=lc["lora_alpha"] / lc["r"], groups=32, aux_heads=tr["n_heads"], aux_depth=tr["depth"])
+
+
+def test_tiny_ms_against_reference_golden():
+    """oracle ms_inference / vfm_head_forward vs the reference's MsVFMEncoderDecoder + VFMHead (tiny_ms.npz)."""
+    g = np.load(GOLDEN / "tiny_ms.npz")
+    cfg = synthetic.tiny_ms_config()
+    sd3 = torch_ref.split_ms_state_dict(synthetic.synthetic_ms_state_dict(cfg, seed=0))
+    oc = _ms_cfg_of(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 128, 192, seed=1234), MEAN, STD, True)
+    with torch.no_grad():
+        logits, info = torch_ref.ms_inference(x, sd3, oc, crop=(64, 64), stride=(43, 43), threshold=float(g["threshold"]),
+                                              conf=float(g["conf"]), return_info=True)
+    assert info["refined"] == list(g["refined"])
+    np.testing.assert_allclose(np.array(info["fracs"]), g["fracs"], atol=2e-3)
+    np.testing.assert_allclose(logits.numpy(), g["logits"].astype(np.float32), rtol=2e-3, atol=2e-3)   # golden stored as fp16
+    assert (logits.argmax(1).numpy() == g["labels"]).mean() >= 0.999
+    # standalone head
+    with torch.no_grad():
+        seg = torch.nn.functional.interpolate(info["low0"], size=x.shape[2:], mode="bilinear", align_corners=False)
+        feats = torch_ref.dino_forward(x[:, :, :64, :64], sd3[0], depth=oc["depth"], num_heads=oc["num_heads"], patch=16,
+                                       out_indices=oc["out_indices"], lora_scale=oc["lora_scale"])
+        head = torch_ref.vfm_head_forward(feats, seg[:, :, :64, :64], sd3[2], heads=oc["aux_heads"], depth=oc["aux_depth"])
+    np.testing.assert_allclose(head.numpy(), g["head_out"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present (GPU box)")
+def test_ms_oracle_against_live_reference():
+    import tempfile
+    cfg = synthetic.tiny_ms_config(aux_depth=1)
+    sd = synthetic.synthetic_ms_state_dict(cfg, seed=3)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "b.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_ms_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not missing
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 96, 128, seed=5), MEAN, STD, True)
+    thr, conf = 0.09, 0.5
+    model.test_cfg["threadshod"], model.test_cfg["conf"] = thr, conf
+    metas = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)]
+    with torch.no_grad():
+        ref = model.inference(x, metas)
+        got = torch_ref.ms_inference(x, torch_ref.split_ms_state_dict(sd), _ms_cfg_of(cfg), crop=(64, 64), stride=(43, 43),
+                                     threshold=thr, conf=conf)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)

@@ -1,7 +1,9 @@
 from .dino_v2 import DinoVisionTransformer
 from .linear_head import LinearHead
-from .lora import LoraConfig, LoraLinear, PeftModel, get_peft_model
-from .segmentors import LoraBackboneEncoderDecoder, SegDataPreProcessor
+from .lora import LoRABackbone, LoraConfig, LoraLinear, PeftModel, get_peft_model
+from .segmentors import LoraBackboneEncoderDecoder, MsVFMEncoderDecoder, SegDataPreProcessor
+from .vfm_head import MaskTransformerDecoder, TransformerDecoder, VFMHead
 
-__all__ = ["DinoVisionTransformer", "LinearHead", "LoraBackboneEncoderDecoder", "SegDataPreProcessor",
+__all__ = ["DinoVisionTransformer", "LinearHead", "LoraBackboneEncoderDecoder", "SegDataPreProcessor", "MsVFMEncoderDecoder",
+           "VFMHead", "TransformerDecoder", "MaskTransformerDecoder", "LoRABackbone",
            "LoraConfig", "LoraLinear", "PeftModel", "get_peft_model"]

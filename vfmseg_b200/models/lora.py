@@ -78,3 +78,46 @@ class PeftModel(nn.Module):
 
 def get_peft_model(model: nn.Module, config: LoraConfig) -> PeftModel:
     return PeftModel(model, config)
+
+
+
+def _register_lora_backbone():
+    from ..registry import MODELS
+
+    @MODELS.register_module()
+    class LoRABackbone(nn.Module):
+        """rein/models/backbones/lora_backbone.py:10-44: builds the inner backbone from the registry, wraps it with
+        LoRA (state-dict prefix `model.base_model.model.`) and loads the frozen backbone checkpoint with the target
+        modules renamed to `<t>.base_layer` (:27-35)."""
+
+        def __init__(self, backbone, checkpoint=None, Lora_config=None, **kwargs):
+            super().__init__()
+            inner = MODELS.build(backbone)
+            self.Lora_config = LoraConfig(r=Lora_config["r"], lora_alpha=Lora_config["lora_alpha"],
+                                          target_modules=Lora_config["target_modules"],
+                                          lora_dropout=Lora_config.get("lora_dropout", 0.0), bias="none")
+            self.model = get_peft_model(inner, self.Lora_config)
+            if checkpoint is not None:
+                self.load_pretrained_backbone(checkpoint, Lora_config["target_modules"])
+
+        def load_pretrained_backbone(self, checkpoint, target_modules):
+            original = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, str) else checkpoint
+            new = {}
+            for name, weight in original.items():
+                for t in target_modules:
+                    if t in name:
+                        name = name.replace(t, t + ".base_layer")
+                    new[name] = weight
+            self.model.base_model.model.load_state_dict(new, strict=False)
+
+        @property
+        def inner(self):
+            return self.model.base_model.model
+
+        def forward(self, x):
+            return self.model(x)
+
+    return LoRABackbone
+
+
+LoRABackbone = _register_lora_backbone()

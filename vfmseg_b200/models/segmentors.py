@@ -85,6 +85,8 @@ class LoraBackboneEncoderDecoder(nn.Module):
     @property
     def inner_backbone(self):
         b = self.backbone
+        if hasattr(b, "model") and hasattr(b.model, "base_model"):   # LoRABackbone (lora_backbone.py:23)
+            return b.model.base_model.model
         return b.base_model.model if hasattr(b, "base_model") else b
 
     def invalidate(self):
@@ -171,3 +173,81 @@ class LoraBackboneEncoderDecoder(nn.Module):
     def test_step(self, data: dict):
         data = self.data_preprocessor(data, False) if self.data_preprocessor is not None else data
         return self.predict(data["inputs"], data.get("data_samples"))
+
+
+@MODELS.register_module()
+class MsVFMEncoderDecoder(LoraBackboneEncoderDecoder):
+    """rein/models/segmentors/Ms_VFM_encoder_decoder.py:62-130 (constructor) and :278-332, :400-466 (inference):
+    coarse whole-image pass + confidence-gated per-window refinement by the aux decoder (VFMHead).
+    Test modes: 'ms_slide_inference' (the shipped config, configs/_base_/models/lora_dinov2_ms_masked.py:79-86),
+    'hr_slide_inference' (= plain slide) and 'lr_slide_inference' (slide at half resolution, logits upsampled x2).
+    'msfull_slide_inference' leaves the decoder's random feature masking on at test time (:296-329 never clears
+    mask_enable), so it has no deterministic result to match and is not implemented."""
+
+    MODES = ("lr_slide_inference", "hr_slide_inference", "msfull_slide_inference", "ms_slide_inference")
+
+    def __init__(self, backbone, decode_head, aux_head, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None, init_cfg=None, scales=[1], hr_crop_size=None, crop_coord_divisible=1, feature_scale=1,
+                 data_preprocessor=None, debug=False, debug_interval=100, detail_loss=1.0, max_crops_per_pass: int = 36):
+        super().__init__(checkpoint=None, Lora_config=None, backbone=backbone, decode_head=decode_head, neck=neck,
+                         auxiliary_head=auxiliary_head, train_cfg=train_cfg, test_cfg=test_cfg,
+                         data_preprocessor=data_preprocessor, pretrained=pretrained, init_cfg=init_cfg,
+                         max_crops_per_pass=max_crops_per_pass)
+        self.scales = sorted(scales)
+        self.feature_scale = feature_scale
+        self.crop_size = hr_crop_size
+        self.crop_coord_divisible = crop_coord_divisible
+        self.debug = debug
+        self.debug_interval = (self.train_cfg.get("log_config") or {}).get("img_interval", debug_interval)   # :104
+        self.aux_decoder = MODELS.build(aux_head)                                                              # :112
+        self.detail_loss = detail_loss
+
+    # ------------------------------------------------------------------ inference
+    def _ms(self, inputs: torch.Tensor, want_logits: bool, gate: str):
+        from ..vfm_refine import ms_slide
+        dec = self.aux_decoder.transformer_decoder
+        had = getattr(dec, "mask_enable", None)
+        if had is not None:
+            dec.mask_enable = False          # :422-423
+        try:
+            return ms_slide(self.engine(), self.aux_decoder.packed(), self._as_input(inputs), self.test_cfg.crop_size,
+                            self.test_cfg.stride, threshold=self.test_cfg.get("threadshod", 1.0),
+                            conf=self.test_cfg.get("conf", 1.0), lr_size=(512, 1024), want_logits=want_logits, gate=gate)
+        finally:
+            if had is not None:
+                dec.mask_enable = True       # :463-464
+
+    def ms_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        return self._ms(inputs, True, "batch")[1]
+
+    def _lr_slide(self, inputs: torch.Tensor, want_logits: bool):
+        from .. import ops
+        eng = self.engine()
+        x = self._as_input(inputs)
+        B, _, H, W = x.shape
+        h, w = H // 2, W // 2      # resize(scale_factor=0.5), :283
+        lr = ops.image_resize_norm(x, (h, w), eng.pixel_norm if x.dtype == torch.uint8 else None)
+        _, lr_logits, _ = eng.slide(lr, self.test_cfg.crop_size, self.test_cfg.stride, want_logits=True)
+        boxes = torch.zeros(1, 2, dtype=torch.int32, device=x.device)   # resize(scale_factor=2) + argmax, :285
+        return ops.slide_merge_argmax(lr_logits, boxes, B, (2 * h, 2 * w), (2 * h, 2 * w), want_logits=want_logits)
+
+    def inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
+        return self._run(inputs, True, "batch")[1]
+
+    def _run(self, inputs, want_logits: bool, gate: str):
+        mode = self.test_cfg.get("mode", "lr_slide_inference")
+        assert mode in self.MODES, mode
+        if mode == "ms_slide_inference":
+            labels, logits, _ = self._ms(inputs, want_logits, gate)
+            return labels, logits
+        if mode == "hr_slide_inference":
+            labels, logits, _ = self.engine().slide(self._as_input(inputs), self.test_cfg.crop_size, self.test_cfg.stride,
+                                                    want_logits=want_logits)
+            return labels, logits
+        if mode == "lr_slide_inference":
+            return self._lr_slide(inputs, want_logits)
+        raise NotImplementedError("msfull_slide_inference keeps the decoder's random feature mask on at test time")
+
+    def predict_labels(self, inputs: torch.Tensor, want_logits: bool = False):
+        """Throughput path; every image gates its own windows (the reference's batch_size=1 test loop)."""
+        return self._run(inputs, want_logits, "image")

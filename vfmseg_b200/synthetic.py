@@ -145,3 +145,112 @@ def synthetic_labels(n: int, H: int, W: int, num_classes: int = 19, seed: int = 
     ign = torch.rand(n, H, W, generator=g) < ignore_frac
     lab[ign] = 255
     return lab.to(torch.uint8)
+
+
+# ------------------------------------------------------------------ coarse-to-fine configs (BASELINE config 3)
+def ms_model_config(embed_dim=1024, depth=24, num_heads=16, img_size=512, out_indices=(7, 11, 15, 23), num_classes=19,
+                    crop_size=(512, 512), stride=(320, 320), lora_r=32, lora_alpha=32, threshold=0.968, conf=0.8,
+                    aux_channels=256, aux_heads=8, aux_depth=3, mode="ms_slide_inference") -> dict:
+    """A config dict shaped like configs/_base_/models/lora_dinov2_ms_masked.py:3-87 (same `type=` names). `train_cfg`
+    carries the log_config entry tools/test.py:118-119 injects (read by Ms_VFM_encoder_decoder.py:104)."""
+    n = len(out_indices)
+    head_common = dict(in_channels=[embed_dim] * n, in_index=list(range(n)), dropout_ratio=0.1, num_classes=num_classes,
+                       norm_cfg=dict(type="GN", num_groups=32), align_corners=False,
+                       loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0))
+    return dict(
+        type="MsVFMEncoderDecoder",
+        data_preprocessor=dict(type="SegDataPreProcessor", mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375],
+                               size=(1024, 1024), bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
+        backbone=dict(type="LoRABackbone",
+                      backbone=dict(type="DinoVisionTransformer", patch_size=16, embed_dim=embed_dim, depth=depth,
+                                    num_heads=num_heads, mlp_ratio=4, img_size=img_size, ffn_layer="mlp", init_values=1e-05,
+                                    block_chunks=0, qkv_bias=True, proj_bias=True, ffn_bias=True, out_indices=list(out_indices)),
+                      checkpoint=None,
+                      Lora_config=dict(r=lora_r, lora_alpha=lora_alpha, target_modules=["qkv"], lora_dropout=0.1)),
+        decode_head=dict(type="LinearHead", channels=embed_dim // 4, **head_common),
+        aux_head=dict(type="VFMHead",
+                      transformer=dict(type="MaskTransformerDecoder", query_dim=aux_channels, n_heads=aux_heads, d_head=64,
+                                       depth=aux_depth, dropout=0.1, mask_ratio=0.2),
+                      channels=aux_channels, **head_common),
+        detail_loss=1.0, scales=[1, 0.5], hr_crop_size=tuple(crop_size), feature_scale=0.5, crop_coord_divisible=32,
+        train_cfg=dict(log_config=dict(img_interval=100)),
+        test_cfg=dict(mode=mode, threadshod=threshold, conf=conf, lr_img_size=(512, 1024), stride=list(stride),
+                      crop_size=list(crop_size)),
+    )
+
+
+def tiny_ms_config(**kw) -> dict:
+    d = dict(embed_dim=256, depth=4, num_heads=4, img_size=64, out_indices=(0, 1, 2, 3), crop_size=(64, 64), stride=(43, 43),
+             lora_r=8, lora_alpha=16, aux_depth=2)
+    d.update(kw)
+    return ms_model_config(**d)
+
+
+def synthetic_ms_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """State dict of MsVFMEncoderDecoder with the reference's key names: 'backbone.model.base_model.model.*'
+    (LoRABackbone, lora_backbone.py:23), 'decode_head.*', 'aux_decoder.*' (Ms_VFM_encoder_decoder.py:112)."""
+    base_cfg = dict(backbone=cfg["backbone"]["backbone"], decode_head=cfg["decode_head"], Lora_config=cfg["backbone"]["Lora_config"])
+    base = synthetic_state_dict(base_cfg, seed=seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for k, v in base.items():
+        sd[k.replace("backbone.base_model.model.", "backbone.model.base_model.model.", 1)] = v
+    g = torch.Generator(device="cpu").manual_seed(seed + 1000)
+
+    def normal(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    def uniform(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+    def gn(prefix, c):
+        sd[prefix + ".weight"] = uniform(c, lo=0.5, hi=1.5)
+        sd[prefix + ".bias"] = normal(c, std=0.1)
+
+    ah = cfg["aux_head"]
+    tr = ah["transformer"]
+    C, nc = ah["channels"], ah["num_classes"]
+    n_in = sum(ah["in_channels"])
+    inner = tr["n_heads"] * tr["d_head"]
+    a = "aux_decoder."
+    sd[a + "fuse_conv.0.weight"] = normal(C, n_in, 1, 1, std=n_in ** -0.5)
+    sd[a + "fuse_conv.0.bias"] = normal(C, std=0.1)
+    gn(a + "fuse_conv.1", C)
+    sd[a + "seg_logits_embed.0.weight"] = normal(C // 4, nc, 2, 2, std=(4 * nc) ** -0.5)
+    sd[a + "seg_logits_embed.0.bias"] = normal(C // 4, std=0.1)
+    gn(a + "seg_logits_embed.1", C // 4)
+    sd[a + "seg_logits_embed.3.weight"] = normal(C // 2, C // 4, 2, 2, std=C ** -0.5)
+    sd[a + "seg_logits_embed.3.bias"] = normal(C // 2, std=0.1)
+    gn(a + "seg_logits_embed.4", C // 2)
+    sd[a + "seg_logits_embed.6.weight"] = normal(C, C // 2, 1, 1, std=(C // 2) ** -0.5)
+    sd[a + "seg_logits_embed.6.bias"] = normal(C, std=0.1)
+    gn(a + "seg_logits_embed.7", C)
+    t = a + "transformer_decoder."
+    gn(t + "norm", C)
+    sd[t + "mask_token"] = normal(1, C, 1, 1, std=1.0)
+    for i in range(tr["depth"]):
+        b = f"{t}transformer_blocks.{i}."
+        for att, cdim in (("attn1", C), ("attn2", C)):
+            sd[b + att + ".to_q.weight"] = normal(inner, C, std=2.0 * C ** -0.5)    # hot enough for a non-uniform softmax
+            sd[b + att + ".to_k.weight"] = normal(inner, cdim, std=2.0 * cdim ** -0.5)
+            sd[b + att + ".to_v.weight"] = normal(inner, cdim, std=cdim ** -0.5)
+            sd[b + att + ".to_out.0.weight"] = normal(C, inner, std=0.5 * inner ** -0.5)
+            sd[b + att + ".to_out.0.bias"] = normal(C, std=0.02)
+        sd[b + "ff.net.0.proj.weight"] = normal(8 * C, C, std=C ** -0.5)
+        sd[b + "ff.net.0.proj.bias"] = normal(8 * C, std=0.02)
+        sd[b + "ff.net.2.weight"] = normal(C, 4 * C, std=0.5 * (4 * C) ** -0.5)
+        sd[b + "ff.net.2.bias"] = normal(C, std=0.02)
+        for n_ in ("norm1", "norm2", "norm3"):
+            gn(b + n_, C)
+    sd[a + "conv_seg.weight"] = normal(nc, C, 1, 1, std=2.0 * C ** -0.5)
+    sd[a + "conv_seg.bias"] = normal(nc, std=0.1)
+    return sd
+
+
+def ms_backbone_checkpoint_from(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Plain backbone checkpoint (what LoRABackbone.__init__ loads, lora_backbone.py:27-35) from an MsVFM state dict."""
+    out = {}
+    p = "backbone.model.base_model.model."
+    for k, v in sd.items():
+        if k.startswith(p) and "lora_" not in k:
+            out[k[len(p):].replace(".base_layer", "")] = v
+    return out
