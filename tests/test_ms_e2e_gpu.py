@@ -137,3 +137,36 @@ def test_ms_batch_and_modes_vs_oracle():
     model.test_cfg.mode = "msfull_slide_inference"
     with pytest.raises(NotImplementedError):
         model.predict_labels(img.cuda())
+
+
+def test_full_size_ms_properties():
+    """BASELINE config 3 at full size (ViT-L/16, 1024x2048, crop 512 / stride 320 -> 18 windows): size-independent
+    properties of the coarse-to-fine merge. conf = 0 -> no window is refined and the result is exactly the x8 bilinear
+    upsampling of the stage-0 logits; conf > 1 -> every window is refined and the merge equals the plain slide merge
+    of the refined window logits."""
+    import time
+    from vfmseg_b200 import ops, synthetic
+    cfg = synthetic.ms_model_config()
+    model, _ = _build_ms(cfg)
+    img = synthetic.synthetic_images(1, 1024, 2048, seed=11).cuda()
+    model.test_cfg.conf = 0.0
+    labels0, logits0, info0 = model._ms(img, True, "image")
+    assert info0["n_refined"] == 0 and info0["low0"].shape == (1, 19, 128, 256)
+    up = ops.resize_bilinear(info0["low0"], (1024, 2048))
+    assert torch.equal(logits0, up)
+    assert torch.equal(labels0.long(), up.argmax(1))
+    model.test_cfg.conf = 1.5
+    torch.cuda.synchronize()
+    t0 = time.time()
+    labels1, logits1, info1 = model._ms(img, True, "image")
+    torch.cuda.synchronize()
+    print(f"full-size ms_slide_inference, all 18 windows refined: {time.time() - t0:.3f} s (includes first-use allocations)")
+    assert info1["n_refined"] == 18 and info1["refined"].shape == (18, 19, 32, 32)
+    from vfmseg_b200.engine import slide_boxes
+    bx = torch.tensor(slide_boxes(1024, 2048, (512, 512), (320, 320)), dtype=torch.int32).cuda()
+    lab_ref, log_ref = ops.slide_merge_argmax(info1["refined"], bx, 1, (512, 512), (1024, 2048), want_logits=True)
+    assert torch.equal(logits1, log_ref) and torch.equal(labels1, lab_ref)
+    assert torch.isfinite(logits1).all()
+    # the shipped gate constants (0.968 / 0.8): random weights are never that confident -> everything is refined
+    model.test_cfg.conf = 0.8
+    assert model._ms(img, False, "image")[2]["n_refined"] == 18
