@@ -242,6 +242,15 @@ int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_
                         int crop_h, int crop_w, int lh, int lw, int rh, int rw, int H, int W, int n_img, uint8_t* labels,
                         float* logits_out, void* stream);
 
+/* ---------------------------------------------------------------- EVA02 backbone (rein/models/backbones/eva_02.py)
+ * In-place 2-D rotary embedding of the q and k thirds of packed qkv activations [M, 3C] bf16 (VisionRotaryEmbeddingFast
+ * :119-160 applied at :362-369); token 0 of every sequence (cls) is left untouched. cos/sin: fp32 [tokens_per_seq-1, 64]. */
+int vfm_rope_qk(void* qkv, long long M, int C, int heads, int tokens_per_seq, const float* cos_t, const float* sin_t, void* stream);
+/* SwiGLU.forward between its GEMMs (:234-239): in bf16 [M, 2*Hp] = (w1 x | w2 x) -> LayerNorm_H(silu(x1) * x2) -> out bf16
+ * [M, Hp]; H = real hidden width (2730), Hp = padded width (multiple of 8), padding columns written as zeros. */
+int vfm_swiglu_layernorm(const void* in, void* out, const float* gamma, const float* beta, long long M, int H, int Hp, float eps,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

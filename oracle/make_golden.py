@@ -152,9 +152,30 @@ def tiny_ms():
                         head_out=head_out.numpy())
 
 
+def tiny_eva():
+    """tiny_eva.npz: EncoderDecoder(LoRABackbone(EVA2 dim 256 / depth 4 / 4 heads, 4x4 grid), LinearHead), slide inference on
+    one 80x112 image (crop 64 / stride 43): reference logits + the four feature maps of window (0, 0)."""
+    cfg = synthetic.tiny_eva_config()
+    sd = synthetic.synthetic_eva_state_dict(cfg, seed=0)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_eva_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "rope" not in m and "num_batches_tracked" not in m], (missing, unexpected)
+    img = synthetic.synthetic_images(1, 80, 112, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    metas = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)]
+    with torch.no_grad():
+        logits = model.inference(x, metas)
+        feats = model.extract_feat(x[:, :, :64, :64])
+    np.savez_compressed(GOLDEN / "tiny_eva.npz", logits=logits.numpy().astype(np.float16), feats=torch.stack(list(feats)).numpy())
+    print("tiny_eva", logits.shape, logits.std())
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms"]
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva"]
     for w in which:
         globals()[w]()

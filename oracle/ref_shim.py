@@ -383,6 +383,17 @@ class LoraLinear(nn.Module):
         a, b, d = self.lora_A["default"], self.lora_B["default"], self.lora_dropout["default"]
         return result + b(a(d(x))) * self.scaling["default"]
 
+    # peft 0.10.0 tuners_utils.BaseTunerLayer [3P]: `.weight` / `.bias` of a wrapped layer are the BASE layer's tensors.
+    # eva_02.py:337-339 reads `self.q_proj.weight` and calls F.linear itself, so the LoRA adapters peft attaches to
+    # q_proj / k_proj / v_proj never enter the EVA02 forward pass; only `attn.proj` (called as a module, :379) is adapted.
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
 
 class LoraModel(nn.Module):
     def __init__(self, model, config):
@@ -478,6 +489,11 @@ def install():
     tl = mod("timm.models.layers", to_2tuple=lambda x: (x, x) if not isinstance(x, (tuple, list)) else tuple(x),
              trunc_normal_=nn.init.trunc_normal_)
     tl.drop_path = lambda x, p=0.0, training=False: x
+    def _mea(q, k, v, attn_bias=None, p=0.0, scale=None):
+        # xformers.ops.memory_efficient_attention on (B, N, H, D) tensors = softmax(q k^T / sqrt D) v [3P]
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), scale=scale)
+        return o.transpose(1, 2)
+    mod("xformers.ops", memory_efficient_attention=_mea)
     mod("matplotlib", use=lambda *a, **k: None)
     mod("matplotlib.pyplot")
 
@@ -525,6 +541,21 @@ def build_reference_ms_segmentor(model_cfg: dict, backbone_ckpt_path: str):
     cfg = copy.deepcopy(model_cfg)
     cfg["backbone"]["checkpoint"] = backbone_ckpt_path
     cfg["train_cfg"] = ConfigDict({k: (ConfigDict(v) if isinstance(v, dict) else v) for k, v in cfg.get("train_cfg", {}).items()})
+    m = MODELS.build(cfg)
+    m.eval()
+    return m
+
+
+def build_reference_eva_segmentor(model_cfg: dict, backbone_ckpt_path: str):
+    """MODELS.build of the shim EncoderDecoder holding the reference's own LoRABackbone(EVA2) and LinearHead, from a config
+    shaped like configs/_base_/models/lora_eva02_linear.py."""
+    load("models.backbones.eva_02", "models.backbones.lora_backbone", "models.heads.linear_head")
+    if "EncoderDecoder" not in MODELS.module_dict:
+        MODELS.register_module(name="EncoderDecoder", module=EncoderDecoder)
+    import copy
+    cfg = copy.deepcopy(model_cfg)
+    cfg["backbone"]["checkpoint"] = backbone_ckpt_path
+    cfg.pop("data_preprocessor", None)
     m = MODELS.build(cfg)
     m.eval()
     return m

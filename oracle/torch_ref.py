@@ -322,6 +322,76 @@ def ms_inference(inputs: Tensor, sd3, cfg, *, crop, stride, threshold: float, co
     return (out, dict(low0=low0, fracs=fracs, refined=refined)) if return_info else out
 
 
+# --------------------------------------------------------------------------- EVA02 backbone (config 4)
+def eva_rope_tables(head_dim: int, pt_seq_len: int, ft_seq_len: int):
+    """VisionRotaryEmbeddingFast.__init__, rein/models/backbones/eva_02.py:119-156: dim = head_dim // 2 per axis,
+    freqs_for='lang' (theta 10000), positions t = arange(ft) / ft * pt, each frequency repeated twice, (h | w) halves."""
+    dim = head_dim // 2
+    freqs = 1.0 / (10000 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    t = torch.arange(ft_seq_len) / ft_seq_len * pt_seq_len
+    f = torch.einsum("i,f->if", t, freqs).repeat_interleave(2, dim=-1)
+    f2 = torch.cat((f[:, None, :].expand(ft_seq_len, ft_seq_len, dim), f[None, :, :].expand(ft_seq_len, ft_seq_len, dim)), dim=-1)
+    return f2.cos().reshape(-1, 2 * dim), f2.sin().reshape(-1, 2 * dim)
+
+
+def _rotate_half(x: Tensor) -> Tensor:
+    """eva_02.py:54-58: (x0, x1) -> (-x1, x0) on interleaved pairs."""
+    x = x.reshape(*x.shape[:-1], -1, 2)
+    return torch.stack((-x[..., 1], x[..., 0]), dim=-1).reshape(*x.shape[:-2], -1)
+
+
+def eva_forward(x: Tensor, sd: Dict[str, Tensor], *, depth: int, num_heads: int, patch: int = 16, out_indices=(7, 11, 15, 23),
+                lora_scale: float = 1.0, pt_hw_seq_len: int = 16, ln_eps: float = 1e-5):
+    """EVA2.forward_features, rein/models/backbones/eva_02.py:816-849, with Block.forward :486-493 (init_values=None),
+    Attention.forward :331-381 (subln, rope, xattn) and SwiGLU.forward :234-241. `sd` holds un-prefixed backbone keys in
+    peft layout. peft [3P]: `q_proj.weight` of a wrapped layer is the BASE weight, and the reference calls F.linear on it
+    (:337-339), so only attn.proj — called as a module — carries its LoRA update. LayerNorm eps is nn.LayerNorm's 1e-5:
+    EVA2 does not forward its configured norm_layer to Block (:705-727)."""
+    B, _, H, W = x.shape
+    C = sd["cls_token"].shape[-1]
+    d = C // num_heads
+    t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
+    t = torch.cat((sd["cls_token"].expand(B, -1, -1), t), dim=1) + sd["pos_embed"]            # no interpolation (:825-826)
+    cos, sin = eva_rope_tables(d, pt_hw_seq_len, H // patch)
+    outs = []
+    for i in range(depth):
+        p = f"blocks.{i}."
+        h = F.layer_norm(t, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], ln_eps)
+        q = F.linear(h, sd[p + "attn.q_proj.base_layer.weight"], sd[p + "attn.q_bias"])
+        k = F.linear(h, sd[p + "attn.k_proj.base_layer.weight"])
+        v = F.linear(h, sd[p + "attn.v_proj.base_layer.weight"], sd[p + "attn.v_bias"])
+        q, k, v = (u.reshape(B, -1, num_heads, d).permute(0, 2, 1, 3) for u in (q, k, v))
+        q = torch.cat((q[:, :, :1], q[:, :, 1:] * cos + _rotate_half(q[:, :, 1:]) * sin), dim=2)
+        k = torch.cat((k[:, :, :1], k[:, :, 1:] * cos + _rotate_half(k[:, :, 1:]) * sin), dim=2)
+        a = ((q @ k.transpose(-1, -2)) * d ** -0.5).softmax(dim=-1) @ v                       # xformers [3P] default scale
+        a = a.permute(0, 2, 1, 3).reshape(B, -1, C)
+        wp = sd[p + "attn.proj.base_layer.weight"] + lora_scale * (sd[p + "attn.proj.lora_B.default.weight"] @ sd[p + "attn.proj.lora_A.default.weight"])
+        t = t + F.linear(a, wp, sd[p + "attn.proj.base_layer.bias"])
+        h = F.layer_norm(t, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], ln_eps)
+        hid = F.silu(F.linear(h, sd[p + "mlp.w1.weight"], sd[p + "mlp.w1.bias"])) * F.linear(h, sd[p + "mlp.w2.weight"], sd[p + "mlp.w2.bias"])
+        hid = F.layer_norm(hid, (hid.shape[-1],), sd[p + "mlp.ffn_ln.weight"], sd[p + "mlp.ffn_ln.bias"], ln_eps)
+        t = t + F.linear(hid, sd[p + "mlp.w3.weight"], sd[p + "mlp.w3.bias"])
+        if i in out_indices:
+            outs.append(t[:, 1:, :].permute(0, 2, 1).reshape(B, -1, H // patch, W // patch).contiguous())
+    return outs
+
+
+def eva_slide_inference(inputs: Tensor, bb, hd, cfg, *, crop, stride) -> Tensor:
+    """slide_inference (same loop as above) with the EVA02 backbone + LinearHead."""
+    B, _, H, W = inputs.shape
+    preds, count = None, inputs.new_zeros((B, 1, H, W))
+    for (y1, y2, x1, x2) in slide_boxes(H, W, crop, stride):
+        feats = eva_forward(inputs[:, :, y1:y2, x1:x2], bb, depth=cfg["depth"], num_heads=cfg["num_heads"],
+                            out_indices=cfg["out_indices"], lora_scale=cfg["lora_scale"])
+        logit = F.interpolate(linear_head_forward(feats, hd, groups=cfg.get("groups", 32)), size=(y2 - y1, x2 - x1), mode="bilinear",
+                              align_corners=False)
+        if preds is None:
+            preds = inputs.new_zeros((B, logit.shape[1], H, W))
+        preds += F.pad(logit, (int(x1), int(W - x2), int(y1), int(H - y2)))
+        count[:, :, y1:y2, x1:x2] += 1
+    return preds / count
+
+
 # --------------------------------------------------------------------------- metric (integer/np)
 def intersect_and_union(pred: Tensor, label: Tensor, num_classes: int, ignore_index: int):
     """mmseg IoUMetric.intersect_and_union [3P] as called from rein/dg_metrics.py:50-52:

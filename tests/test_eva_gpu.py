@@ -1,0 +1,98 @@
+"""GPU parity of the EVA02 backbone path (BASELINE config 4): RoPE / SwiGLU+LayerNorm kernels against torch, and the
+registered EncoderDecoder(LoRABackbone(EVA2), LinearHead) against the golden vectors produced by the reference's own
+modules (tests/golden/tiny_eva.npz) and the oracle restatement."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_e2e_gpu import _check_labels, _check_logits
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).parent / "golden"
+MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+
+
+def _rand(*shape, scale=1.0, seed=0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+def test_rope_qk():
+    from oracle import torch_ref
+    from vfmseg_b200 import ops
+    n, grid, heads = 2, 4, 3
+    T, C = grid * grid + 1, heads * 64
+    qkv = _rand(n * T, 3 * C, seed=1, dtype=torch.bfloat16)
+    cos, sin = torch_ref.eva_rope_tables(64, 16, grid)
+    got = ops.rope_qk_(qkv.clone(), heads, T, cos.cuda().contiguous(), sin.cuda().contiguous()).float().cpu()
+    x = qkv.float().cpu().view(n, T, 3, heads, 64)
+    ref = x.clone()
+    for w in (0, 1):
+        t = x[:, 1:, w]                                            # [n, P, heads, 64]
+        ref[:, 1:, w] = t * cos[None, :, None, :] + torch_ref._rotate_half(t) * sin[None, :, None, :]
+    ref = ref.view(n * T, 3 * C)
+    assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
+    assert torch.equal(got.view(n, T, 3, heads, 64)[:, 0], x[:, 0])           # cls rows untouched
+    assert torch.equal(got.view(n, T, 3, heads, 64)[:, :, 2], x[:, :, 2])     # v untouched
+
+
+@pytest.mark.parametrize("H", [682, 2730, 96])
+def test_swiglu_layernorm(H):
+    from vfmseg_b200 import ops
+    M, Hp = 70, (H + 7) // 8 * 8
+    x12 = _rand(M, 2 * Hp, seed=2, dtype=torch.bfloat16)
+    g, b = _rand(H, seed=3), _rand(H, seed=4)
+    got = ops.swiglu_layernorm(x12, g, b, H, 1e-5).float()
+    x1, x2 = x12[:, :H].float(), x12[:, Hp:Hp + H].float()
+    ref = F.layer_norm(F.silu(x1) * x2, (H,), g, b, 1e-5)
+    assert ((got[:, :H] - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
+    assert (got[:, H:] == 0).all()
+
+
+def _build_eva(cfg, seed=0):
+    import vfmseg_b200
+    from vfmseg_b200 import synthetic
+    sd = synthetic.synthetic_eva_state_dict(cfg, seed=seed)
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "num_batches_tracked" not in m], (missing, unexpected)
+    return model.cuda().eval(), sd
+
+
+def test_tiny_eva_vs_reference_golden():
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / "tiny_eva.npz")
+    cfg = synthetic.tiny_eva_config()
+    model, _ = _build_eva(cfg)
+    img = synthetic.synthetic_images(1, 80, 112, seed=1234)
+    labels, logits = model.predict_labels(img.cuda(), want_logits=True)
+    ref = torch.from_numpy(g["logits"].astype(np.float32))
+    _check_logits(logits, ref, "tiny EVA02 slide vs reference golden")
+    _check_labels(labels, ref, "tiny EVA02 labels vs reference golden", raw_min=0.985, top2_min=0.999)
+    # backbone contract: four [B, C, h, w] maps of the un-normalised residual stream
+    from oracle import torch_ref
+    x = torch_ref.preprocess(img, MEAN, STD, True)[:, :, :64, :64].contiguous()
+    feats = model.extract_feat(x.cuda())
+    assert len(feats) == 4 and all(f.shape == (1, 256, 4, 4) for f in feats)
+    for i, f in enumerate(feats):
+        _check_logits(f, torch.from_numpy(g["feats"][i]), f"EVA02 tap {i} vs reference golden")
+    # the fixed-grid pos_embed / RoPE only accept the grid the model was built for (eva_02.py:825-826)
+    from vfmseg_b200 import _C
+    with pytest.raises(_C.VfmError):
+        model.extract_feat(torch.zeros(1, 3, 64, 96).cuda())
+
+
+def test_full_size_eva_runs():
+    """BASELINE config 4 shapes (EVA02-L/16, 1024x2048, crop 512 / stride 320): finite logits, batching invariance."""
+    from vfmseg_b200 import synthetic
+    cfg = synthetic.eva_model_config()
+    model, _ = _build_eva(cfg)
+    img = synthetic.synthetic_images(2, 1024, 2048, seed=21).cuda()
+    labels, logits = model.predict_labels(img[:1], want_logits=True)
+    assert torch.isfinite(logits).all() and labels.shape == (1, 1024, 2048)
+    labels2, _ = model.predict_labels(img)
+    assert torch.equal(labels2[0], labels[0])

@@ -157,3 +157,28 @@ def test_ms_oracle_against_live_reference():
         got = torch_ref.ms_inference(x, torch_ref.split_ms_state_dict(sd), _ms_cfg_of(cfg), crop=(64, 64), stride=(43, 43),
                                      threshold=thr, conf=conf)
     np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ EVA02 backbone (BASELINE config 4)
+def _eva_parts(cfg, seed=0):
+    sd = synthetic.synthetic_eva_state_dict(cfg, seed=seed)
+    pre = "backbone.model.base_model.model."
+    bb = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    hd = {k[len("decode_head."):]: v for k, v in sd.items() if k.startswith("decode_head.")}
+    b, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    oc = dict(depth=b["depth"], num_heads=b["num_heads"], out_indices=tuple(b["out_indices"]), lora_scale=lc["lora_alpha"] / lc["r"], groups=32)
+    return sd, bb, hd, oc
+
+
+def test_tiny_eva_against_reference_golden():
+    """oracle eva_forward / slide loop vs the reference's own EVA2 + LoRABackbone + LinearHead (tiny_eva.npz)."""
+    g = np.load(GOLDEN / "tiny_eva.npz")
+    cfg = synthetic.tiny_eva_config()
+    _, bb, hd, oc = _eva_parts(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 80, 112, seed=1234), MEAN, STD, True)
+    with torch.no_grad():
+        feats = torch_ref.eva_forward(x[:, :, :64, :64], bb, depth=oc["depth"], num_heads=oc["num_heads"], out_indices=oc["out_indices"],
+                                      lora_scale=oc["lora_scale"])
+        logits = torch_ref.eva_slide_inference(x, bb, hd, oc, crop=(64, 64), stride=(43, 43))
+    np.testing.assert_allclose(torch.stack(feats).numpy(), g["feats"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(logits.numpy(), g["logits"].astype(np.float32), rtol=2e-3, atol=2e-3)

@@ -16,7 +16,7 @@ __global__ void k(uint32_t* out, int iters, uint32_t seed) {
       if (MODE == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(r[i]));
       if (MODE == 1) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r[i]));
       if (MODE == 2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r[i]));
-      if (MODE == 3) { asm volatile("{.reg .b64 t; mov.b64 t, {%0,%1}; fma.rn.f32x2 t, t, t, t; mov.b64 {%0,%1}, t;}" : "+r"(r[i]), "+r"(r[(i + 1) & 7])); }
+      if (MODE == 3) { if ((i & 1) == 0) asm volatile("{.reg .b64 t; mov.b64 t, {%0,%1}; fma.rn.f32x2 t, t, t, t; mov.b64 {%0,%1}, t;}" : "+r"(r[i]), "+r"(r[i + 1])); }
       if (MODE == 4) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+r"(r[i]));
       if (MODE == 5) asm volatile("{.reg .b16 lo, hi; mov.b32 {lo,hi}, %0; ex2.approx.ftz.bf16 lo, lo; mov.b32 %0, {lo,hi};}" : "+r"(r[i]));
       if (MODE == 6) asm volatile("tanh.approx.f32 %0, %0;" : "+r"(r[i]));
@@ -54,7 +54,7 @@ int main() {
     run<2>("ex2.approx.f16x2", w, 2);
     run<5>("ex2.approx.ftz.bf16", w, 1);
     run<6>("tanh.approx.f32", w, 1);
-    run<3>("fma.rn.f32x2", w, 2);
+    run<3>("fma.rn.f32x2 (4 per 8 slots)", w, 1);
     run<4>("fma.rn.f32", w, 1);
   }
   return 0;

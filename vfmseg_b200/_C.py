@@ -70,6 +70,8 @@ SIGNATURES = {
     "vfm_geglu": (_i, [_p, _p, _ll, _i, _p]),
     "vfm_cast_f32_bf16": (_i, [_p, _p, _ll, _p]),
     "vfm_ms_merge_argmax": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "vfm_rope_qk": (_i, [_p, _ll, _i, _i, _i, _p, _p, _p]),
+    "vfm_swiglu_layernorm": (_i, [_p, _p, _p, _p, _ll, _i, _i, _f, _p]),
     "vfm_patch_gather": (_i, [_p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i, _p, _p]),
     "vfm_cls_rows": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "vfm_layernorm": (_i, [_p, _p, _p, _p, _i, _i, _f, _p]),

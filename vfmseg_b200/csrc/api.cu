@@ -14,6 +14,7 @@
 
 #include "attention_sm100.cuh"
 #include "elementwise.cuh"
+#include "eva_ops.cuh"
 #include "gemm_sm100.cuh"
 #include "ms_refine.cuh"
 #include "slide_tail.cuh"
@@ -635,6 +636,30 @@ int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_
                                                                  nc, crop_h, crop_w, lh, lw, rh, rw, H, W, n_img, labels, logits_out);
   }
   VFM_LAUNCH_CHECK("ms_merge_argmax");
+  return VFM_OK;
+}
+
+// ------------------------------------------------------------------------------ EVA02 (config 4)
+int vfm_rope_qk(void* qkv, long long M, int C, int heads, int tokens_per_seq, const float* cos_t, const float* sin_t, void* stream) {
+  if (!qkv || !cos_t || !sin_t || M <= 0 || heads <= 0 || C != heads * 64 || tokens_per_seq < 2 || M > 0x7fffffffLL)
+    return fail(VFM_ERR_INVALID, "rope_qk: bad args (head_dim 64)");
+  {
+    LaunchScope scope("rope_qk", S(stream));
+    rope_qk_kernel<<<grid_for(M * 2 * heads * 8), 256, 0, S(stream)>>>(BF(qkv), M, C, heads, FastDiv(tokens_per_seq), cos_t, sin_t);
+  }
+  VFM_LAUNCH_CHECK("rope_qk");
+  return VFM_OK;
+}
+
+int vfm_swiglu_layernorm(const void* in, void* out, const float* gamma, const float* beta, long long M, int H, int Hp, float eps,
+                         void* stream) {
+  if (!in || !out || !gamma || !beta || M <= 0 || H <= 0 || Hp < H || (Hp % 8) || Hp > SWIGLU_MAX_ITERS * 256)
+    return fail(VFM_ERR_INVALID, "swiglu_layernorm: bad args (Hp %% 8 == 0, Hp <= %d)", SWIGLU_MAX_ITERS * 256);
+  {
+    LaunchScope scope("swiglu_layernorm", S(stream));
+    swiglu_layernorm_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, M, H, Hp, eps);
+  }
+  VFM_LAUNCH_CHECK("swiglu_layernorm");
   return VFM_OK;
 }
 

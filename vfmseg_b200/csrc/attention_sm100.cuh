@@ -324,7 +324,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int b = j & 1;
       const uint32_t ph = (j >> 1) & 1;
       const int st = j % ATT_V_STAGES;
+      const bool more = j + 2 < kv_tiles;
+      const int kst = (j + 2) % ATT_K_STAGES;
       ATT_TRACE(j, 0);
+      // one issue block per key tile: PV_j, the row-sum MMA and S_{j+2} behind a single fence / election (two separate
+      // blocks cost ~630 clk each on this warp, mostly fixed overhead, against ~370 clk of tensor-pipe work per tile)
+      if (more) mbar_wait(&k_full[kst], ((j + 2) / ATT_K_STAGES) & 1);
       mbar_wait(&v_full[st], (j / ATT_V_STAGES) & 1);
       mbar_wait(&p_full[b], ph);         // P_j stored (and O rescaled when the running max jumped); S_j is in registers
       tc_fence_after();
@@ -340,10 +345,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int k = 0; k < ksteps; ++k) umma_ts(tmem_l, tmem_p + 8 * k, d1 + 128 * k, idesc_l, (j | k) != 0);
         tc_commit(&v_empty[st]);
         tc_commit(&pv_done[b]);
+        if (more) {
+          const uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, kv_width(j + 2), 0, 0);
+          const uint64_t dk = dk0 + static_cast<uint64_t>(kst * (ATT_KV_BYTES >> 4));
+          const uint32_t tmem_s = tmem_base + ATT_COL_S + b * 64;
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+          tc_commit(&k_empty[kst]);
+          tc_commit(&s_full[b]);
+        }
       }
       __syncwarp();
-      ATT_TRACE(j, 2);
-      if (j + 2 < kv_tiles) issue_s(j + 2);
       ATT_TRACE(j, 3);
     }
   } else {
@@ -357,6 +369,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr float kRescaleThreshold = 24.0f;  // in log2 units: P stays <= 2^24 relative to the reference max (P is
                                                 // bf16 and O/l are fp32: range, not precision, is what a large P costs)
 
+#ifdef VFM_ATT_STAGGER
+    // de-phase the two co-resident CTAs of the first wave (they start together and otherwise stay in lockstep)
+    if ((blockIdx.x / 148) & 1) { const long long t0 = clock64(); while (clock64() - t0 < VFM_ATT_STAGGER) {} }
+#endif
     // m_ref: the max (times log2e) that P and the O accumulator in TMEM are currently relative to.
     float m_ref = -INFINITY, w_extra = 0.f;
     if (p.extra) {

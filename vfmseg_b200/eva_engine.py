@@ -1,0 +1,144 @@
+"""Engine side of the EVA02 backbone (BASELINE config 4; rein/models/backbones/eva_02.py:614-853): weight packing
+(LoRA merge of q/k/v/proj, q-scale fold, fused q|k|v and w1|w2 operands, hidden width padded 2730 -> 2736 so rows stay
+16-byte aligned for TMA) and the per-block launch sequence. Same kernels as the DINOv2 path plus RoPE and SwiGLU+LN.
+
+Block (eva_02.py:486-493, no LayerScale):  x += attn(norm1(x));  x += mlp(norm2(x))
+  attn (:331-381, subln=True, xattn=True): q = x Wq^T + q_bias, k = x Wk^T, v = x Wv^T + v_bias; RoPE on the patch tokens
+       of q and k; softmax(q k^T / sqrt d) v; proj
+  mlp  (:234-241): w3(LayerNorm(silu(w1 x) * w2 x))
+nn.LayerNorm eps is 1e-5 in the blocks: EVA2.__init__ does not forward the configured norm_layer to Block (:705-727).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _C, ops
+
+
+@dataclass
+class EvaSpec:
+    embed_dim: int
+    depth: int
+    num_heads: int
+    hidden: int            # int(embed_dim * mlp_ratio) = 2730 for ViT-L
+    patch_size: int
+    out_indices: Tuple[int, ...]
+    grid: int              # img_size // patch_size (pos_embed / RoPE are fixed to this grid, eva_02.py:690-697,825-826)
+    pt_hw_seq_len: int = 16
+    ln_eps: float = 1e-5
+
+
+def rope_tables(head_dim: int, pt_seq_len: int, ft_seq_len: int):
+    """VisionRotaryEmbeddingFast.__init__, eva_02.py:119-156 (freqs_for='lang', theta 10000): cos/sin [ft*ft, head_dim]."""
+    dim = head_dim // 2
+    freqs = 1.0 / (10000 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+    t = torch.arange(ft_seq_len) / ft_seq_len * pt_seq_len
+    f = torch.einsum("i,f->if", t, freqs).repeat_interleave(2, dim=-1)          # [ft, dim]
+    f2 = torch.cat((f[:, None, :].expand(ft_seq_len, ft_seq_len, dim), f[None, :, :].expand(ft_seq_len, ft_seq_len, dim)), dim=-1)
+    return f2.cos().reshape(-1, 2 * dim).contiguous(), f2.sin().reshape(-1, 2 * dim).contiguous()
+
+
+def _lora_merged(sd, key: str, scale: float) -> torch.Tensor:
+    """peft lora.Linear at inference: W + (alpha/r) B A when the module was wrapped, else the plain weight."""
+    if key + ".base_layer.weight" in sd:
+        w = sd[key + ".base_layer.weight"].float()
+        a, b = key + ".lora_A.default.weight", key + ".lora_B.default.weight"
+        if a in sd:
+            w = w + scale * (sd[b].float() @ sd[a].float())
+        return w
+    return sd[key + ".weight"].float()
+
+
+def _bias(sd, key: str):
+    for k in (key + ".base_layer.bias", key + ".bias"):
+        if k in sd:
+            return sd[k].float()
+    return None
+
+
+class PackedEva:
+    def __init__(self, sd: Dict[str, torch.Tensor], spec: EvaSpec, lora_scale: float, device):
+        self.spec, self.device = spec, device
+        sd = {k: v.detach().cpu() for k, v in sd.items()}      # fold on the host, upload once
+        C, H = spec.embed_dim, spec.hidden
+        if C // spec.num_heads != 64:
+            raise ValueError("vfmseg_b200 attention kernel needs head_dim 64")
+        if spec.patch_size != 16:
+            raise ValueError("vfmseg_b200 patch gather is built for patch_size 16")
+        self.Hp = Hp = (H + 7) // 8 * 8
+        keep: List[torch.Tensor] = []
+
+        def dev(t, dtype):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t
+
+        f32, bf = torch.float32, torch.bfloat16
+        scale = 64 ** -0.5
+        self.patch_w = dev(sd["patch_embed.proj.weight"].reshape(C, -1), bf)
+        self.patch_b = dev(sd["patch_embed.proj.bias"], f32)
+        self.cls_token = dev(sd["cls_token"].reshape(-1), f32)
+        self.pos = dev(sd["pos_embed"][0], f32)                                  # [1 + grid^2, C]
+        cos, sin = rope_tables(64, spec.pt_hw_seq_len, spec.grid)
+        self.rope_cos, self.rope_sin = dev(cos, f32), dev(sin, f32)
+        self.ones = dev(torch.ones(C), f32)
+        self.blocks = []
+        for i in range(spec.depth):
+            p = f"blocks.{i}."
+            # eva_02.py:337-339 calls F.linear(x, self.q_proj.weight, ...): with peft that attribute is the BASE weight,
+            # so the adapters on q_proj / k_proj / v_proj are inert in the reference's forward pass (scale 0 here);
+            # attn.proj is called as a module (:379) and is adapted.
+            wq = _lora_merged(sd, p + "attn.q_proj", 0.0) * scale
+            wk = _lora_merged(sd, p + "attn.k_proj", 0.0)
+            wv = _lora_merged(sd, p + "attn.v_proj", 0.0)
+            qb = sd[p + "attn.q_bias"].float() * scale if p + "attn.q_bias" in sd else torch.zeros(C)
+            vb = sd[p + "attn.v_bias"].float() if p + "attn.v_bias" in sd else torch.zeros(C)
+            w12 = torch.zeros(2 * Hp, C)
+            b12 = torch.zeros(2 * Hp)
+            w12[:H], w12[Hp:Hp + H] = _lora_merged(sd, p + "mlp.w1", lora_scale), _lora_merged(sd, p + "mlp.w2", lora_scale)
+            b12[:H], b12[Hp:Hp + H] = _bias(sd, p + "mlp.w1"), _bias(sd, p + "mlp.w2")
+            w3 = torch.zeros(C, Hp)
+            w3[:, :H] = _lora_merged(sd, p + "mlp.w3", lora_scale)
+            self.blocks.append(dict(
+                n1=(dev(sd[p + "norm1.weight"], f32), dev(sd[p + "norm1.bias"], f32)),
+                n2=(dev(sd[p + "norm2.weight"], f32), dev(sd[p + "norm2.bias"], f32)),
+                qkv_w=dev(torch.cat([wq, wk, wv], 0), bf), qkv_b=dev(torch.cat([qb, torch.zeros(C), vb]), f32),
+                proj_w=dev(_lora_merged(sd, p + "attn.proj", lora_scale), bf), proj_b=dev(_bias(sd, p + "attn.proj"), f32),
+                w12=dev(w12, bf), b12=dev(b12, f32),
+                ffn_ln=(dev(sd[p + "mlp.ffn_ln.weight"], f32), dev(sd[p + "mlp.ffn_ln.bias"], f32)),
+                w3=dev(w3, bf), b3=dev(_bias(sd, p + "mlp.w3"), f32)))
+        self._keep = keep
+
+    # SlideEngine.backbone_taps dispatches here
+    def forward_taps(self, img: torch.Tensor, crops: torch.Tensor, gh: int, gw: int, pixel_norm) -> torch.Tensor:
+        """EVA2.forward_features (eva_02.py:816-849) for the listed windows -> taps bf16 [n*gh*gw, n_taps*C] (token-major,
+        cls dropped): the un-normalised residual stream after the blocks in out_indices."""
+        s = self.spec
+        if gh != s.grid or gw != s.grid:
+            raise _C.VfmError(f"EVA02 adds a fixed {s.grid}x{s.grid} pos_embed / RoPE table without interpolation "
+                              f"(eva_02.py:690-697,825-826): windows must be {s.grid * 16}x{s.grid * 16}, got grid {gh}x{gw}")
+        n, P, C = crops.shape[0], gh * gw, s.embed_dim
+        T = P + 1
+        a = ops.patch_gather(img, crops, gh, gw, pixel_norm if img.dtype == torch.uint8 else None)
+        x = ops.gemm_patch_embed(a, self.patch_w, self.patch_b, self.pos, n, P)        # :818-826 (+ pos_embed[1:])
+        ops.cls_rows_(x, self.cls_token, self.pos, n, T)                              # cls_token + pos_embed[0]
+        outs = sorted(s.out_indices)
+        taps = torch.empty(n * P, len(outs) * C, dtype=torch.bfloat16, device=x.device)
+        for i, b in enumerate(self.blocks):
+            tap_i = outs.index(i - 1) if (i - 1) in outs else None                    # tap of the previous block's output
+            h = ops.layernorm_tap(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None,
+                                  (tap_i or 0) * C, T)
+            qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
+            ops.rope_qk_(qkv, s.num_heads, T, self.rope_cos, self.rope_sin)           # :362-369
+            att = ops.attention_fwd(qkv, n, T, s.num_heads)                           # xops.memory_efficient_attention :376
+            ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
+            h = ops.layernorm(x, *b["n2"], s.ln_eps)
+            u = ops.swiglu_layernorm(ops.gemm_bias_bf16(h, b["w12"], b["b12"]), *b["ffn_ln"], s.hidden, s.ln_eps)
+            ops.gemm_bias_ls_residual_(x, u, b["w3"], b["b3"], self.ones)
+        if (s.depth - 1) in outs:
+            ops.layernorm_tap(x, None, None, s.ln_eps, taps, outs.index(s.depth - 1) * C, T, want_out=False)
+        return taps

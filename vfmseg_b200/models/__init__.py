@@ -1,9 +1,10 @@
 from .dino_v2 import DinoVisionTransformer
+from .eva_02 import EVA2
 from .linear_head import LinearHead
 from .lora import LoRABackbone, LoraConfig, LoraLinear, PeftModel, get_peft_model
-from .segmentors import LoraBackboneEncoderDecoder, MsVFMEncoderDecoder, SegDataPreProcessor
+from .segmentors import EncoderDecoder, LoraBackboneEncoderDecoder, MsVFMEncoderDecoder, SegDataPreProcessor
 from .vfm_head import MaskTransformerDecoder, TransformerDecoder, VFMHead
 
 __all__ = ["DinoVisionTransformer", "LinearHead", "LoraBackboneEncoderDecoder", "SegDataPreProcessor", "MsVFMEncoderDecoder",
-           "VFMHead", "TransformerDecoder", "MaskTransformerDecoder", "LoRABackbone",
+           "VFMHead", "TransformerDecoder", "MaskTransformerDecoder", "LoRABackbone", "EVA2", "EncoderDecoder",
            "LoraConfig", "LoraLinear", "PeftModel", "get_peft_model"]

@@ -176,6 +176,19 @@ class LoraBackboneEncoderDecoder(nn.Module):
 
 
 @MODELS.register_module()
+class EncoderDecoder(LoraBackboneEncoderDecoder):
+    """mmseg's plain EncoderDecoder type name, as used by the LoRABackbone configs (configs/_base_/models/
+    lora_eva02_linear.py:4, lora_sam_*.py): the LoRA wrapping lives in the backbone entry, not in the segmentor."""
+
+    def __init__(self, backbone, decode_head, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None,
+                 data_preprocessor=None, pretrained=None, init_cfg=None, max_crops_per_pass: int = 36):
+        super().__init__(checkpoint=None, Lora_config=None, backbone=backbone, decode_head=decode_head, neck=neck,
+                         auxiliary_head=auxiliary_head, train_cfg=train_cfg, test_cfg=test_cfg,
+                         data_preprocessor=data_preprocessor, pretrained=pretrained, init_cfg=init_cfg,
+                         max_crops_per_pass=max_crops_per_pass)
+
+
+@MODELS.register_module()
 class MsVFMEncoderDecoder(LoraBackboneEncoderDecoder):
     """rein/models/segmentors/Ms_VFM_encoder_decoder.py:62-130 (constructor) and :278-332, :400-466 (inference):
     coarse whole-image pass + confidence-gated per-window refinement by the aux decoder (VFMHead).

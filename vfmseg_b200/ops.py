@@ -255,3 +255,29 @@ def ms_merge_argmax(low0, refined, ref_index, boxes, crop_hw, out_hw, want_logit
     _C.call("vfm_ms_merge_argmax", _f32(low0), _f32(refined), _ptr(ref_index), _ptr(boxes), n_crops, nc, crop_hw[0], crop_hw[1],
             lh, lw, rh, rw, H, W, n_img, _ptr(labels), _f32(logits), _stream())
     return labels, logits
+
+
+# ------------------------------------------------------------------ EVA02 (config 4)
+def rope_qk_(qkv, heads, tokens_per_seq, cos_t, sin_t):
+    """In-place RoPE on the q and k thirds of packed qkv [M, 3C] bf16; token 0 of each sequence is skipped."""
+    M, C3 = qkv.shape
+    _C.call("vfm_rope_qk", _bf16(qkv), M, C3 // 3, heads, tokens_per_seq, _f32(cos_t), _f32(sin_t), _stream())
+    return qkv
+
+
+def swiglu_layernorm(x12, gamma, beta, H, eps):
+    """x12 bf16 [M, 2*Hp] = (w1 x | w2 x) -> LayerNorm over H of silu(x1) * x2 -> bf16 [M, Hp] (padding columns zero)."""
+    M, Hp2 = x12.shape
+    out = torch.empty(M, Hp2 // 2, device=x12.device, dtype=torch.bfloat16)
+    _C.call("vfm_swiglu_layernorm", _bf16(x12), _bf16(out), _f32(gamma), _f32(beta), M, H, Hp2 // 2, float(eps), _stream())
+    return out
+
+
+def layernorm_tap(x, gamma, beta, eps, tap=None, tap_col0=0, tokens_per_crop=1, want_out=True):
+    """LayerNorm (fp32 [M,C] -> bf16) that can also snapshot the un-normalised rows, cls rows dropped, into columns
+    [tap_col0, tap_col0 + C) of `tap` (bf16 [n*(tokens-1), n_taps*C])."""
+    M, Cc = x.shape
+    out = torch.empty(M, Cc, device=x.device, dtype=torch.bfloat16) if want_out else None
+    _C.call("vfm_layernorm_tap", _f32(x), _f32(gamma), _f32(beta), _bf16(out) if out is not None else None, M, Cc, float(eps),
+            _bf16(tap) if tap is not None else None, tap.shape[1] if tap is not None else 0, tap_col0, tokens_per_crop, _stream())
+    return out

@@ -254,3 +254,95 @@ def ms_backbone_checkpoint_from(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.
         if k.startswith(p) and "lora_" not in k:
             out[k[len(p):].replace(".base_layer", "")] = v
     return out
+
+
+# ------------------------------------------------------------------ EVA02 configs (BASELINE config 4)
+def eva_model_config(embed_dim=1024, depth=24, num_heads=16, img_size=512, out_indices=(7, 11, 15, 23), num_classes=19,
+                     crop_size=(512, 512), stride=(320, 320), lora_r=32, lora_alpha=32, mode="slide") -> dict:
+    """A config dict shaped like configs/_base_/models/lora_eva02_linear.py:3-71 (same `type=` names)."""
+    n = len(out_indices)
+    return dict(
+        type="EncoderDecoder",
+        data_preprocessor=dict(type="SegDataPreProcessor", mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375],
+                               size=tuple(crop_size), bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
+        backbone=dict(type="LoRABackbone",
+                      Lora_config=dict(lora_alpha=lora_alpha, lora_dropout=0.1, r=lora_r,
+                                       target_modules=["q_proj", "k_proj", "v_proj", "attn.proj"]),
+                      checkpoint=None,
+                      backbone=dict(type="EVA2", depth=depth, drop_path_rate=0.1, embed_dim=embed_dim, img_size=img_size, in_chans=3,
+                                    init_values=None, intp_freq=True, mlp_ratio=2.6666666666666665, naiveswiglu=True,
+                                    norm_layer=dict(eps=1e-06, requires_grad=True, type="LN"), num_heads=num_heads,
+                                    out_indices=list(out_indices), patch_size=16, pt_hw_seq_len=16, qkv_bias=True, rope=True,
+                                    subln=True, use_abs_pos_emb=True, use_checkpoint=False, use_rel_pos_bias=False,
+                                    use_shared_rel_pos_bias=False, xattn=True)),
+        decode_head=dict(type="LinearHead", in_channels=[embed_dim] * n, in_index=list(range(n)), channels=embed_dim // 4,
+                         dropout_ratio=0.1, num_classes=num_classes, norm_cfg=dict(type="GN", num_groups=32), align_corners=False,
+                         loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0)),
+        train_cfg=dict(),
+        test_cfg=dict(mode=mode, stride=list(stride), crop_size=list(crop_size)),
+    )
+
+
+def tiny_eva_config(**kw) -> dict:
+    d = dict(embed_dim=256, depth=4, num_heads=4, img_size=64, out_indices=(0, 1, 2, 3), crop_size=(64, 64), stride=(43, 43),
+             lora_r=8, lora_alpha=16)
+    d.update(kw)
+    return eva_model_config(**d)
+
+
+def synthetic_eva_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """State dict of EncoderDecoder(LoRABackbone(EVA2), LinearHead) with the reference's key names
+    ('backbone.model.base_model.model.*' with peft's base_layer / lora_A / lora_B for q_proj, k_proj, v_proj, attn.proj)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    bb, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    C, depth, P = bb["embed_dim"], bb["depth"], bb["patch_size"]
+    hidden = int(C * bb["mlp_ratio"])
+    n_pos = (bb["img_size"] // P) ** 2
+    r = lc["r"]
+
+    def normal(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    def uniform(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+    sd: Dict[str, torch.Tensor] = {}
+    p = "backbone.model.base_model.model."
+    sd[p + "cls_token"] = normal(1, 1, C, std=0.1)
+    sd[p + "pos_embed"] = normal(1, 1 + n_pos, C, std=0.1)
+    sd[p + "patch_embed.proj.weight"] = normal(C, 3, P, P)
+    sd[p + "patch_embed.proj.bias"] = normal(C)
+    bound = 1.0 / math.sqrt(C)
+
+    def lora_linear(key, n_out, n_in, std, bias):
+        sd[key + ".base_layer.weight"] = normal(n_out, n_in, std=std)
+        if bias:
+            sd[key + ".base_layer.bias"] = normal(n_out)
+        sd[key + ".lora_A.default.weight"] = uniform(r, n_in, lo=-bound, hi=bound)
+        sd[key + ".lora_B.default.weight"] = normal(n_out, r)
+
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        for nm in ("norm1", "norm2"):
+            sd[b + nm + ".weight"] = uniform(C, lo=0.5, hi=1.5)
+            sd[b + nm + ".bias"] = normal(C, std=0.1)
+        lora_linear(b + "attn.q_proj", C, C, 0.04, False)     # hotter q/k: a non-uniform softmax
+        lora_linear(b + "attn.k_proj", C, C, 0.04, False)
+        lora_linear(b + "attn.v_proj", C, C, 0.02, False)
+        sd[b + "attn.q_bias"] = normal(C)
+        sd[b + "attn.v_bias"] = normal(C)
+        lora_linear(b + "attn.proj", C, C, 0.01, True)        # no LayerScale in EVA02: keep the residual branches moderate
+        sd[b + "mlp.w1.weight"] = normal(hidden, C, std=0.03)
+        sd[b + "mlp.w1.bias"] = normal(hidden)
+        sd[b + "mlp.w2.weight"] = normal(hidden, C, std=0.03)
+        sd[b + "mlp.w2.bias"] = normal(hidden)
+        sd[b + "mlp.ffn_ln.weight"] = uniform(hidden, lo=0.5, hi=1.5)
+        sd[b + "mlp.ffn_ln.bias"] = normal(hidden, std=0.1)
+        sd[b + "mlp.w3.weight"] = normal(C, hidden, std=0.005)
+        sd[b + "mlp.w3.bias"] = normal(C)
+    lin_cfg = dict(backbone=dict(embed_dim=C, depth=0, patch_size=P, mlp_ratio=4, img_size=bb["img_size"]),
+                   decode_head=cfg["decode_head"], Lora_config=dict(r=r))
+    for k, v in synthetic_state_dict(lin_cfg, seed=seed + 7).items():
+        if k.startswith("decode_head."):
+            sd[k] = v
+    return sd
