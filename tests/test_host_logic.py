@@ -1,6 +1,7 @@
 """CPU: host-side logic — registry/config drop-in surface, state-dict naming (peft layout), slide grid,
 weight folding, C-ABI symbol table, metric reduction. No GPU compute is issued."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -173,3 +174,48 @@ def test_weight_folding_matches_oracle_semantics():
     tok = f.permute(0, 2, 3, 1).reshape(-1, C) @ w1.t() + b1            # [n*h*w, 4*Cout], col = (dy*2+dx)*Cout + co
     got = tok.view(2, 4, 4, 2, 2, C // 2).permute(0, 5, 1, 3, 2, 4).reshape(2, C // 2, 8, 8)
     torch.testing.assert_close(got, y, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ checkpoint plumbing / PNG export
+def test_convert_dinov2_matches_reference_converter():
+    """vfmseg_b200.convert vs tools/convert_models/convert_dinov2.py (imported from the reference tree when present,
+    otherwise against the interpolation it is defined by)."""
+    import importlib.util
+    import torch
+    from vfmseg_b200 import convert
+    g = torch.Generator().manual_seed(0)
+    w = {"patch_embed.proj.weight": torch.randn(32, 3, 14, 14, generator=g), "pos_embed": torch.randn(1, 1 + 37 * 37, 32, generator=g),
+         "cls_token": torch.randn(1, 1, 32, generator=g)}
+    out = convert.convert_dinov2_state_dict(w, kernel=16, crop_size=(512, 512))
+    assert out["patch_embed.proj.weight"].shape == (32, 3, 16, 16) and out["pos_embed"].shape == (1, 1025, 32)
+    assert torch.equal(out["pos_embed"][:, :1], w["pos_embed"][:, :1]) and out["cls_token"] is w["cls_token"]
+    ref_path = "/root/reference/tools/convert_models/convert_dinov2.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_convert_dinov2", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = {k: v.clone() for k, v in w.items()}
+        mod.interpolate_patch_embed_(ref, kernel_conv=16)
+        mod.interpolate_pos_embed_(ref, crop_size=(512, 512), kernel_conv=16)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    ck = {"state_dict": {"decode_head.conv_seg.bias": torch.zeros(19)}}
+    convert.merge_backbone_checkpoint(ck, {"cls_token": w["cls_token"]})
+    assert set(ck["state_dict"]) == {"decode_head.conv_seg.bias", "backbone.cls_token"}
+
+
+def test_id2color_and_png_export(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from vfmseg_b200 import dg_metrics
+    lab = np.array([[0, 1, 18], [19, 255, 7]])
+    rgb = dg_metrics.id2color(lab)
+    assert rgb.dtype == np.uint8 and rgb.shape == (2, 3, 3)
+    assert tuple(rgb[0, 0]) == (128, 64, 128) and tuple(rgb[0, 2]) == (119, 11, 32) and tuple(rgb[1, 2]) == (220, 220, 0)
+    assert tuple(rgb[1, 0]) == (0, 0, 0) and tuple(rgb[1, 1]) == (0, 0, 0)      # outside the palette: black (dg_metrics.py:17-21)
+    import torch
+    m = dg_metrics.DGIoUMetric(dataset_keys=["citys"], output_dir=str(tmp_path), format_only=True)
+    m.dataset_meta = dict(classes=list(range(19)))
+    m.process({}, [dict(pred_sem_seg=dict(data=torch.from_numpy(lab)[None]), img_path="/x/y/frankfurt_000000.png", seg_map_path="a/citys/b.png")])
+    out = np.asarray(Image.open(tmp_path / "frankfurt_000000.png"))
+    assert np.array_equal(out, rgb) and m.results == []

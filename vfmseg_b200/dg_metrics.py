@@ -12,6 +12,8 @@ the whole path) instead of mmengine's pickled-object all-gather.
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict, defaultdict
 from typing import Dict, List, Optional, Sequence
 
@@ -42,6 +44,20 @@ def total_area_to_metrics(inter, union, pred, label) -> "OrderedDict[str, float]
     return out
 
 
+# mmseg CityscapesDataset.METAINFO['palette'] [3P], the 19 train-id colours
+CITYSCAPES_PALETTE = [[128, 64, 128], [244, 35, 232], [70, 70, 70], [102, 102, 156], [190, 153, 153], [153, 153, 153],
+                      [250, 170, 30], [220, 220, 0], [107, 142, 35], [152, 251, 152], [70, 130, 180], [220, 20, 60], [255, 0, 0],
+                      [0, 0, 142], [0, 0, 70], [0, 60, 100], [0, 80, 100], [0, 0, 230], [119, 11, 32]]
+
+
+def id2color(label_pred: np.ndarray) -> np.ndarray:
+    """rein/dg_metrics.py:14-22: label map [H,W] -> RGB uint8 [H,W,3]; ids outside the palette stay black."""
+    lut = np.zeros((int(max(label_pred.max(), 0)) + 2, 3), dtype=np.uint8)
+    n = min(len(CITYSCAPES_PALETTE), lut.shape[0])
+    lut[:n] = np.asarray(CITYSCAPES_PALETTE[:n], dtype=np.uint8)
+    return lut[np.clip(label_pred, 0, lut.shape[0] - 1)]
+
+
 @METRICS.register_module()
 class DGIoUMetric:
     default_prefix = None
@@ -51,8 +67,10 @@ class DGIoUMetric:
                  prefix: Optional[str] = None, **kwargs):
         if list(iou_metrics) != ["mIoU"]:
             raise NotImplementedError("only iou_metrics=['mIoU'] (what every reference config uses) is implemented")
-        if output_dir is not None or format_only:
-            raise NotImplementedError("colourised PNG export (dg_metrics.py:60-72) is outside the hot path")
+        self.output_dir = output_dir
+        self.format_only = format_only
+        if output_dir is not None:
+            os.makedirs(output_dir, exist_ok=True)
         self.dataset_keys = list(dataset_keys)
         self.mean_used_keys = list(mean_used_keys) if mean_used_keys else list(dataset_keys)
         self.ignore_index = ignore_index
@@ -74,6 +92,10 @@ class DGIoUMetric:
         num_classes = len(self.dataset_meta["classes"])
         for data_sample in data_samples:
             pred = data_sample["pred_sem_seg"]["data"].squeeze()
+            if self.output_dir is not None:      # dg_metrics.py:60-72: colourised PNG of the prediction
+                self._save_png(pred, data_sample)
+            if self.format_only:                 # test sets without ground truth (:46-47)
+                continue
             label = data_sample["gt_sem_seg"]["data"].squeeze().to(pred.device)
             if pred.dtype != torch.uint8:
                 pred = pred.to(torch.uint8)
@@ -88,6 +110,14 @@ class DGIoUMetric:
                     dataset_key = key
                     break
             self.results.append([dataset_key, cm])
+
+    def _save_png(self, pred: torch.Tensor, data_sample: dict) -> None:
+        from PIL import Image
+        basename = os.path.splitext(os.path.basename(data_sample["img_path"]))[0]
+        mask = pred.detach().cpu().numpy().astype(np.int64)
+        if data_sample.get("reduce_zero_label", False):
+            mask = mask + 1
+        Image.fromarray(id2color(mask)).save(os.path.abspath(os.path.join(self.output_dir, f"{basename}.png")))
 
     # ------------------------------------------------------------------ reduction
     @staticmethod
