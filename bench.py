@@ -286,8 +286,15 @@ def run_b200_arm(args):
         cnt, ms = prof[top]
         achieved = FLOP_PER_CROP[top] * crops_per_run / ms / 1e9
         peak = pk["bf16_sustained"]   # kernels are timed inside a long step -> sustained figure
+        traffic = None
+        try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (same launch shape only)
+            t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(top)
+            if t and t["crops_per_launch"] * cnt == crops_per_run:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            traffic = None
         roofline = {"bound": "tensor", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
                     "launch_ms": round(ms / cnt, 5), "flop_per_launch": FLOP_PER_CROP[top] * crops_per_run / cnt,
                     "families": fam,
                     "whole_step": {"tflops": round(FLOP_PER_IMAGE * B * K / ms_total / 1e9, 1),
