@@ -1,4 +1,4 @@
-"""Debug: event timeline of one attention CTA (needs the -DVFM_EPI_TIMING build in lib/libvfmseg_b200_dbg.so)."""
+"""Debug: event timelines of the two co-resident first-wave attention CTAs of SM 5 (needs a -DVFM_EPI_TIMING build)."""
 import ctypes, sys
 from pathlib import Path
 import torch
@@ -12,14 +12,20 @@ lib = _C.load()
 qkv = (torch.randn(18 * 1025, 3072, device="cuda") * 0.7).to(torch.bfloat16)
 for _ in range(2):
     ops.attention_fwd(qkv, 18, 1025, 16, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-tr = (ctypes.c_longlong * 384)()
+tr = (ctypes.c_longlong * 640)()
 lib.vfm_debug_att_trace(tr)
-t = [[tr[j * 24 + e] for e in range(24)] for j in range(16)]
-t0 = min(v for row in t for v in row if v > 0)
-names = ["mma:top", "mma:p_ok", "mma:pv_iss", "mma:s_iss", "-", "-", "-", "-",
-         "A:wait_s", "A:s_ok", "A:S_ld", "A:max", "A:jchk", "A:arrived", "A:pp_go", "A:exp_end",
-         "B:wait_s", "B:s_ok", "B:S_ld", "B:max", "B:jchk", "B:arrived", "B:pp_go", "B:exp_end"]
-print("event timeline of CTA 150 (cycles from first event)")
-print("tile " + " ".join(f"{n:>9s}" for n in names if n != "-"))
-for j in range(16):
-    print(f"{j:4d} " + " ".join(f"{(t[j][e]-t0) if t[j][e] > 0 else -1:9d}" for e in range(24) if names[e] != "-"))
+t = [[[tr[(s * 20 + j) * 16 + e] for e in range(16)] for j in range(20)] for s in range(2)]
+t0 = min(v for sl in t for row in sl for v in row if v > 0)
+names = ["mma:top", "mma:p_ok", "-", "mma:iss", "-", "-", "-", "-",
+         "wait_s", "s_ok", "S_ld", "max", "jchk", "arrived", "-", "exp_end"]
+print(build.LIB_PATH.name, "event timelines (cycles from first event), SM 5, slots = the two co-resident CTAs")
+for s in range(2):
+    print(f"slot {s}")
+    print("tile " + " ".join(f"{n:>9s}" for n in names if n != "-") + "   exp_len  period")
+    prev = None
+    for j in range(18):
+        r = t[s][j]
+        line = f"{j:4d} " + " ".join(f"{(r[e]-t0) if r[e] > 0 else -1:9d}" for e in range(16) if names[e] != "-")
+        line += f" {r[15]-r[12]:9d}" + (f" {r[8]-prev:7d}" if prev else "")
+        prev = r[8]
+        print(line)

@@ -14,6 +14,13 @@ out = ops.attention_fwd(qkv, 18, 1025, 16)
 q, k, v = qkv.float().view(18, 1025, 3, 16, 64).permute(2, 0, 3, 1, 4)
 ref = ((q[:2] @ k[:2].transpose(-1, -2)).softmax(-1) @ v[:2]).transpose(1, 2).reshape(2 * 1025, 1024)
 err = (out[:2050].float() - ref).abs().max().item()
+# wide score range: the running max jumps by more than 2^24 after the first tile (exercises the rescale / redo path)
+qkv2 = qkv.clone(); qkv2[:, :2048] *= 2.2
+out2 = ops.attention_fwd(qkv2, 18, 1025, 16)
+q, k, v = qkv2.float().view(18, 1025, 3, 16, 64).permute(2, 0, 3, 1, 4)
+ref2 = ((q[:2] @ k[:2].transpose(-1, -2)).softmax(-1) @ v[:2]).transpose(1, 2).reshape(2 * 1025, 1024)
+err2 = (out2[:2050].float() - ref2).abs().max().item()
+print("wide-range max abs err", err2, "finite", bool(torch.isfinite(out2.float()).all()))
 for _ in range(3): ops.attention_fwd(qkv, 18, 1025, 16)
 torch.cuda.synchronize()
 ts = []

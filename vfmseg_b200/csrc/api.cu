@@ -249,9 +249,9 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
 }
 
 #ifdef VFM_EPI_TIMING
-extern "C" int vfm_debug_att_trace(long long* out384) {
+extern "C" int vfm_debug_att_trace(long long* out640) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out384, vfm::g_att_trace, 16 * 24 * sizeof(long long));
+  cudaMemcpyFromSymbol(out640, vfm::g_att_trace, 2 * 20 * 16 * sizeof(long long));
   return 0;
 }
 // debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)

@@ -76,8 +76,12 @@ struct AttParams {
 };
 
 #ifdef VFM_EPI_TIMING
-__device__ long long g_att_trace[16][24];   // events 0..7 MMA warp, 8..15 softmax warp 2 (tile 0), 16..23 warp 6 (tile 1)
-#define ATT_TRACE(j, ev) do { if (blockIdx.x == 150 && lane == 0 && (j) < 16) g_att_trace[j][ev] = clock64(); } while (0)
+// [slot][tile][event]: the two co-resident first-wave CTAs of SM 5 (slot = parity of a per-SM ticket); events 0..7 MMA
+// warp, 8..15 softmax warp with quad == 2. Same SM -> same clock, so the two timelines can be laid side by side
+// (tools/att_trace.py).
+__device__ long long g_att_trace[2][20][16];
+__device__ unsigned int g_att_ticket[1024];
+#define ATT_TRACE(j, ev) do { if (trace_slot >= 0 && lane == 0 && (j) < 20) g_att_trace[trace_slot][j][ev] = clock64(); } while (0)
 __device__ unsigned long long g_att_dbg[8];
 #else
 #define ATT_TRACE(j, ev)
@@ -241,6 +245,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+#ifdef VFM_EPI_TIMING
+  if (threadIdx.x == 64) {   // debug build: pick the two first-wave CTAs of SM 5 for the timeline
+    uint32_t tr = 0xffffffffu, nsm, smid;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (blockIdx.x < 2 * nsm) {
+      const uint32_t t = atomicAdd(&g_att_ticket[smid & 1023], 1u) & 1u;
+      if (smid == 5) tr = t;
+    }
+    tmem_slot[1] = tr;
+  }
+#endif
   for (int i = threadIdx.x; i < ATT_ONES_BYTES / 16; i += ATT_THREADS)
     reinterpret_cast<uint4*>(smem_ones)[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
   fence_proxy_async_smem();   // the tensor core reads the ones tile through the async proxy
@@ -248,6 +264,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef VFM_EPI_TIMING
+  const int trace_slot = static_cast<int>(tmem_slot[1]);
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer (warp converged, one elected lane issues) =====================
@@ -369,10 +388,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     constexpr float kRescaleThreshold = 24.0f;  // in log2 units: P stays <= 2^24 relative to the reference max (P is
                                                 // bf16 and O/l are fp32: range, not precision, is what a large P costs)
 
-#ifdef VFM_ATT_STAGGER
-    // de-phase the two co-resident CTAs of the first wave (they start together and otherwise stay in lockstep)
-    if ((blockIdx.x / 148) & 1) { const long long t0 = clock64(); while (clock64() - t0 < VFM_ATT_STAGGER) {} }
-#endif
     // m_ref: the max (times log2e) that P and the O accumulator in TMEM are currently relative to.
     float m_ref = -INFINITY, w_extra = 0.f;
     if (p.extra) {
