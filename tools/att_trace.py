@@ -12,7 +12,7 @@ lib = _C.load()
 qkv = (torch.randn(18 * 1025, 3072, device="cuda") * 0.7).to(torch.bfloat16)
 for _ in range(2):
     ops.attention_fwd(qkv, 18, 1025, 16, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-tr = (ctypes.c_longlong * 640)()
+tr = (ctypes.c_longlong * 644)()
 lib.vfm_debug_att_trace(tr)
 t = [[[tr[(s * 20 + j) * 16 + e] for e in range(16)] for j in range(20)] for s in range(2)]
 t0 = min(v for sl in t for row in sl for v in row if v > 0)
@@ -29,3 +29,6 @@ for s in range(2):
         line += f" {r[15]-r[12]:9d}" + (f" {r[8]-prev:7d}" if prev else "")
         prev = r[8]
         print(line)
+clk, ns = tr[642] - tr[640], tr[643] - tr[641]
+if ns > 0:
+    print(f"slot-0 CTA life: {clk} clk in {ns} ns -> SM clock {clk / ns:.3f} GHz under this kernel")

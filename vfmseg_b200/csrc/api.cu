@@ -252,6 +252,7 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
 extern "C" int vfm_debug_att_trace(long long* out640) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out640, vfm::g_att_trace, 2 * 20 * 16 * sizeof(long long));
+  cudaMemcpyFromSymbol(out640 + 640, vfm::g_att_dbg, 4 * sizeof(long long));   // CTA life: clk0, ns0, clk1, ns1
   return 0;
 }
 // debug build only: read-and-clear the epilogue phase cycle counters (warp 4 of every CTA)
@@ -373,19 +374,32 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     VFM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES));
     attr_done = true;
   }
-  long long grid = static_cast<long long>(n_seq) * heads * p.q_tiles;
-  p.n_main = static_cast<int>(grid);
+  const long long units = static_cast<long long>(n_seq) * heads * p.q_tiles;
+  if (units > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention: too many units");
+  p.n_units = static_cast<int>(units);
   p.q_ptr = BF(q); p.q_ld = q_ld;
-  if (extra) {
-    // one appended CTA per (sequence, head) for the extra token's query row; its scratch lives in the same dynamic smem
-    const size_t need = (static_cast<size_t>((kv_total + 3) & ~3) + (ATT_THREADS / 32) * 65) * sizeof(float);
-    if (need > static_cast<size_t>(ATT_SMEM_BYTES)) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
-    grid += static_cast<long long>(n_seq) * heads;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    VFM_CUDA(cudaGetDevice(&dev));
+    VFM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  if (grid > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention: grid too large");
+  const unsigned grid = static_cast<unsigned>(units < 2LL * n_sm ? units : 2LL * n_sm);   // persistent: two CTAs per SM
   {
     LaunchScope scope("attention_fwd", st);
-    attention_fwd_kernel<<<static_cast<unsigned>(grid), ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+  }
+  if (extra) {
+    // one CTA per (sequence, head) for the extra token's query row (CUDA cores)
+    const size_t need = (static_cast<size_t>((kv_total + 3) & ~3) + (ATT_THREADS / 32) * 65) * sizeof(float);
+    if (need > 200 * 1024) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
+    static size_t attr_need = 0;
+    if (need > attr_need) {
+      VFM_CUDA(cudaFuncSetAttribute(attention_extra_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need)));
+      attr_need = need;
+    }
+    LaunchScope scope("attention_extra_query", st);
+    attention_extra_query_kernel<<<static_cast<unsigned>(n_seq * heads), ATT_THREADS, need, st>>>(p);
   }
   VFM_LAUNCH_CHECK("attention_fwd");
   return VFM_OK;
