@@ -13,7 +13,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
-LIB_PATH = LIB_DIR / "libvfmseg_b200.so"
+# VFMSEG_B200_LIB: experiment knob (tools/): load another build of the same sources, e.g. a macro sweep variant
+LIB_PATH = Path(os.environ["VFMSEG_B200_LIB"]) if os.environ.get("VFMSEG_B200_LIB") else LIB_DIR / "libvfmseg_b200.so"
 SOURCES = [CSRC / "api.cu"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "vfmseg_b200.h"]
 
