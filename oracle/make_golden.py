@@ -173,9 +173,31 @@ def tiny_eva():
     print("tiny_eva", logits.shape, logits.std())
 
 
+def tiny_sam():
+    """tiny_sam.npz: EncoderDecoder(LoRABackbone(SAMViT dim 160 / depth 4 / 2 heads x 80, 16x16 tokens, window 14, global
+    blocks 1 and 3), LinearHead), slide inference on one 256x384 image (crop 256 / stride 171): reference logits + the four
+    feature maps of window (0, 0)."""
+    cfg = synthetic.tiny_sam_config()
+    sd = synthetic.synthetic_sam_state_dict(cfg, seed=0)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_sam_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "num_batches_tracked" not in m], (missing, unexpected)
+    img = synthetic.synthetic_images(1, 256, 384, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    metas = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)]
+    with torch.no_grad():
+        logits = model.inference(x, metas)
+        feats = model.extract_feat(x[:, :, :256, :256])
+    np.savez_compressed(GOLDEN / "tiny_sam.npz", logits=logits.numpy().astype(np.float16), feats=torch.stack(list(feats)).numpy().astype(np.float16))
+    print("tiny_sam", logits.shape, logits.std(), [float(f.std()) for f in feats])
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva"]
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva", "tiny_sam"]
     for w in which:
         globals()[w]()

@@ -559,3 +559,18 @@ def build_reference_eva_segmentor(model_cfg: dict, backbone_ckpt_path: str):
     m = MODELS.build(cfg)
     m.eval()
     return m
+
+
+def build_reference_sam_segmentor(model_cfg: dict, backbone_ckpt_path: str):
+    """MODELS.build of the shim EncoderDecoder holding the reference's own LoRABackbone(SAMViT) and LinearHead, from a
+    config shaped like configs/_base_/models/lora_sam_linear.py."""
+    load("models.backbones.sam_vit", "models.backbones.lora_backbone", "models.heads.linear_head")
+    if "EncoderDecoder" not in MODELS.module_dict:
+        MODELS.register_module(name="EncoderDecoder", module=EncoderDecoder)
+    import copy
+    cfg = copy.deepcopy(model_cfg)
+    cfg["backbone"]["checkpoint"] = backbone_ckpt_path
+    cfg.pop("data_preprocessor", None)
+    m = MODELS.build(cfg)
+    m.eval()
+    return m

@@ -392,6 +392,91 @@ def eva_slide_inference(inputs: Tensor, bb, hd, cfg, *, crop, stride) -> Tensor:
     return preds / count
 
 
+# --------------------------------------------------------------------------- SAM ViT backbone (BASELINE config 5)
+def sam_rel_pos_table(q_size: int, k_size: int, rel_pos: Tensor) -> Tensor:
+    """get_rel_pos, rein/models/backbones/sam_vit.py:358-388: linear interpolation of the (L, C) table to
+    2 max(q, k) - 1 entries when L differs (global blocks are built with 4 * size - 1 entries, :248-254), then the
+    gather R[q, k] = table[q - k + (k_size - 1)] for equal sizes. Returns [q_size, k_size, C]."""
+    max_rel_dist = int(2 * max(q_size, k_size) - 1)
+    if rel_pos.shape[0] != max_rel_dist:
+        r = F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=max_rel_dist, mode="linear")
+        r = r.reshape(-1, max_rel_dist).permute(1, 0)
+    else:
+        r = rel_pos
+    q_coords = torch.arange(q_size)[:, None] * max(k_size / q_size, 1.0)
+    k_coords = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
+    rel = (q_coords - k_coords) + (k_size - 1) * max(q_size / k_size, 1.0)
+    return r[rel.long()]
+
+
+def sam_attention(x: Tensor, sd, pre: str, num_heads: int, lora_scale: float) -> Tensor:
+    """Attention.forward, sam_vit.py:263-289 on [B, H, W, C] with add_decomposed_rel_pos :391-428: the bias uses the
+    UNSCALED q (rel_h = q . Rh[qh, kh], rel_w = q . Rw[qw, kw]), added to (q * scale) k^T. qkv carries LoRA (peft [3P])."""
+    B, H, W, C = x.shape
+    d = C // num_heads
+    w = sd[pre + "qkv.base_layer.weight"] + lora_scale * (sd[pre + "qkv.lora_B.default.weight"] @ sd[pre + "qkv.lora_A.default.weight"])
+    qkv = F.linear(x, w, sd[pre + "qkv.base_layer.bias"]).reshape(B, H * W, 3, num_heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.reshape(3, B * num_heads, H * W, d).unbind(0)
+    attn = (q * d ** -0.5) @ k.transpose(-2, -1)
+    Rh = sam_rel_pos_table(H, H, sd[pre + "rel_pos_h"])
+    Rw = sam_rel_pos_table(W, W, sd[pre + "rel_pos_w"])
+    rq = q.reshape(B * num_heads, H, W, d)
+    rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
+    rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
+    attn = (attn.view(-1, H, W, H, W) + rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]).view(-1, H * W, H * W)
+    o = (attn.softmax(dim=-1) @ v).view(B, num_heads, H, W, d).permute(0, 2, 3, 1, 4).reshape(B, H, W, C)
+    return F.linear(o, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+
+
+def sam_forward(x: Tensor, sd: Dict[str, Tensor], *, depth: int, num_heads: int, window_size: int, global_attn_indexes,
+                out_indices, patch: int = 16, lora_scale: float = 1.0, ln_eps: float = 1e-6):
+    """SAMViT.forward, sam_vit.py:123-147 with Block.forward :201-217 (window_partition / window_unpartition :292-346:
+    zero padding AFTER norm1 to a multiple of the window, so padded tokens enter attention as q = k = v = bias) and
+    MLPBlock :17-29 (exact-erf GELU). pos_embed is added without interpolation (:131-132): the input must have the
+    size the model was built for. Returns the raw block outputs at out_indices as [B, C, h, w]."""
+    B = x.shape[0]
+    C = sd["pos_embed"].shape[-1]
+    t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch).permute(0, 2, 3, 1)
+    t = t + sd["pos_embed"]
+    H, W = t.shape[1], t.shape[2]
+    outs = []
+    for i in range(depth):
+        p = f"blocks.{i}."
+        h = F.layer_norm(t, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], ln_eps)
+        ws = 0 if i in global_attn_indexes else window_size
+        if ws > 0:
+            ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+            h = F.pad(h, (0, 0, 0, pw, 0, ph))
+            Hp, Wp = H + ph, W + pw
+            h = h.view(B, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, C)
+        h = sam_attention(h, sd, p + "attn.", num_heads, lora_scale)
+        if ws > 0:
+            h = h.view(B, Hp // ws, Wp // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp, Wp, C)[:, :H, :W, :]
+        t = t + h
+        h = F.layer_norm(t, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], ln_eps)
+        t = t + F.linear(F.gelu(F.linear(h, sd[p + "mlp.lin1.weight"], sd[p + "mlp.lin1.bias"])), sd[p + "mlp.lin2.weight"], sd[p + "mlp.lin2.bias"])
+        if i in out_indices:
+            outs.append(t.permute(0, 3, 1, 2).contiguous())
+    return outs
+
+
+def sam_slide_inference(inputs: Tensor, bb, hd, cfg, *, crop, stride) -> Tensor:
+    """slide_inference (same loop as above) with the SAM ViT backbone + LinearHead."""
+    B, _, H, W = inputs.shape
+    preds, count = None, inputs.new_zeros((B, 1, H, W))
+    for (y1, y2, x1, x2) in slide_boxes(H, W, crop, stride):
+        feats = sam_forward(inputs[:, :, y1:y2, x1:x2], bb, depth=cfg["depth"], num_heads=cfg["num_heads"],
+                            window_size=cfg["window_size"], global_attn_indexes=cfg["global_attn_indexes"],
+                            out_indices=cfg["out_indices"], lora_scale=cfg["lora_scale"])
+        logit = F.interpolate(linear_head_forward(feats, hd, groups=cfg.get("groups", 32)), size=(y2 - y1, x2 - x1), mode="bilinear",
+                              align_corners=False)
+        if preds is None:
+            preds = inputs.new_zeros((B, logit.shape[1], H, W))
+        preds += F.pad(logit, (int(x1), int(W - x2), int(y1), int(H - y2)))
+        count[:, :, y1:y2, x1:x2] += 1
+    return preds / count
+
+
 # --------------------------------------------------------------------------- metric (integer/np)
 def intersect_and_union(pred: Tensor, label: Tensor, num_classes: int, ignore_index: int):
     """mmseg IoUMetric.intersect_and_union [3P] as called from rein/dg_metrics.py:50-52:

@@ -182,3 +182,52 @@ def test_tiny_eva_against_reference_golden():
         logits = torch_ref.eva_slide_inference(x, bb, hd, oc, crop=(64, 64), stride=(43, 43))
     np.testing.assert_allclose(torch.stack(feats).numpy(), g["feats"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(logits.numpy(), g["logits"].astype(np.float32), rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------ SAM ViT backbone (BASELINE config 5)
+def _sam_parts(cfg, seed=0):
+    sd = synthetic.synthetic_sam_state_dict(cfg, seed=seed)
+    pre = "backbone.model.base_model.model."
+    bb = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    hd = {k[len("decode_head."):]: v for k, v in sd.items() if k.startswith("decode_head.")}
+    b, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    oc = dict(depth=b["depth"], num_heads=b["num_heads"], out_indices=tuple(b["out_indices"]), window_size=b["window_size"],
+              global_attn_indexes=tuple(b["global_attn_indexes"]), lora_scale=lc["lora_alpha"] / lc["r"], groups=32)
+    return sd, bb, hd, oc
+
+
+def test_tiny_sam_against_reference_golden():
+    """oracle sam_forward / slide loop vs the reference's own SAMViT + LoRABackbone + LinearHead (tiny_sam.npz): windowed
+    blocks with zero-padded windows, global blocks with interpolated rel-pos tables, decomposed rel-pos bias on unscaled q."""
+    g = np.load(GOLDEN / "tiny_sam.npz")
+    cfg = synthetic.tiny_sam_config()
+    _, bb, hd, oc = _sam_parts(cfg)
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 256, 384, seed=1234), MEAN, STD, True)
+    with torch.no_grad():
+        feats = torch_ref.sam_forward(x[:, :, :256, :256], bb, depth=oc["depth"], num_heads=oc["num_heads"], window_size=oc["window_size"],
+                                      global_attn_indexes=oc["global_attn_indexes"], out_indices=oc["out_indices"], lora_scale=oc["lora_scale"])
+        logits = torch_ref.sam_slide_inference(x, bb, hd, oc, crop=(256, 256), stride=(171, 171))
+    np.testing.assert_allclose(torch.stack(feats).numpy(), g["feats"].astype(np.float32), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(logits.numpy(), g["logits"].astype(np.float32), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+def test_sam_oracle_against_live_reference():
+    """Same restatement against the reference's sam_vit.py imported here, fp32 tolerance, on a second seed and a
+    non-square token grid is impossible (fixed pos_embed) — so a different window layout: 20x20 tokens (pad to 28)."""
+    import os, tempfile
+    cfg = synthetic.tiny_sam_config(img_size=320, crop_size=(320, 320), depth=2, global_attn_indexes=(1,), out_indices=(0, 1))
+    sd, bb, hd, oc = _sam_parts(cfg, seed=3)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = ref_shim.build_reference_sam_segmentor(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "num_batches_tracked" not in m]
+    x = torch_ref.preprocess(synthetic.synthetic_images(1, 320, 320, seed=9), MEAN, STD, True)
+    with torch.no_grad():
+        ref = model.extract_feat(x)
+        got = torch_ref.sam_forward(x, bb, depth=oc["depth"], num_heads=oc["num_heads"], window_size=oc["window_size"],
+                                    global_attn_indexes=oc["global_attn_indexes"], out_indices=oc["out_indices"], lora_scale=oc["lora_scale"])
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-4)

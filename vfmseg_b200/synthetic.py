@@ -346,3 +346,83 @@ def synthetic_eva_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor
         if k.startswith("decode_head."):
             sd[k] = v
     return sd
+
+
+# ------------------------------------------------------------------ SAM ViT configs (BASELINE config 5)
+def sam_model_config(embed_dim=1280, depth=32, num_heads=16, img_size=512, out_indices=(7, 15, 23, 31),
+                     global_attn_indexes=(7, 15, 23, 31), window_size=14, num_classes=19, crop_size=(512, 512), stride=(320, 320),
+                     lora_r=32, lora_alpha=32, mode="slide") -> dict:
+    """A config dict shaped like configs/_base_/models/lora_sam_linear.py:3-55 (same `type=` names)."""
+    n = len(out_indices)
+    return dict(
+        type="EncoderDecoder",
+        data_preprocessor=dict(type="SegDataPreProcessor", mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375],
+                               size=tuple(crop_size), bgr_to_rgb=True, pad_val=0, seg_pad_val=255),
+        backbone=dict(type="LoRABackbone",
+                      backbone=dict(type="SAMViT", img_size=img_size, embed_dim=embed_dim, depth=depth, num_heads=num_heads,
+                                    global_attn_indexes=list(global_attn_indexes), out_indices=list(out_indices),
+                                    window_size=window_size, use_rel_pos=True),
+                      checkpoint=None,
+                      Lora_config=dict(r=lora_r, lora_alpha=lora_alpha, target_modules=["qkv"], lora_dropout=0.1)),
+        decode_head=dict(type="LinearHead", in_channels=[embed_dim] * n, in_index=list(range(n)), channels=embed_dim // 4,
+                         dropout_ratio=0.1, num_classes=num_classes, norm_cfg=dict(type="GN", num_groups=32), align_corners=False,
+                         loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, loss_weight=1.0)),
+        train_cfg=dict(),
+        test_cfg=dict(mode=mode, stride=list(stride), crop_size=list(crop_size)),
+    )
+
+
+def tiny_sam_config(**kw) -> dict:
+    """2 heads x 80, 16x16 tokens: windowed blocks pad 16 -> 28 (four 14x14 windows, three of them with pad tokens),
+    global blocks interpolate their 63-entry rel-pos tables to 31."""
+    d = dict(embed_dim=160, depth=4, num_heads=2, img_size=256, out_indices=(0, 1, 2, 3), global_attn_indexes=(1, 3),
+             crop_size=(256, 256), stride=(171, 171), lora_r=8, lora_alpha=16)
+    d.update(kw)
+    return sam_model_config(**d)
+
+
+def synthetic_sam_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """State dict of EncoderDecoder(LoRABackbone(SAMViT), LinearHead) with the reference's key names
+    ('backbone.model.base_model.model.*', peft layout for attn.qkv; rein/models/backbones/sam_vit.py:97-121,229-254)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    bb, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    C, depth, P, heads = bb["embed_dim"], bb["depth"], 16, bb["num_heads"]
+    grid, ws, d = bb["img_size"] // P, bb["window_size"], bb["embed_dim"] // bb["num_heads"]
+    r = lc["r"]
+
+    def normal(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    def uniform(*shape, lo=0.0, hi=1.0):
+        return torch.rand(*shape, generator=g) * (hi - lo) + lo
+
+    sd: Dict[str, torch.Tensor] = {}
+    p = "backbone.model.base_model.model."
+    sd[p + "pos_embed"] = normal(1, grid, grid, C, std=0.1)
+    sd[p + "patch_embed.proj.weight"] = normal(C, 3, P, P)
+    sd[p + "patch_embed.proj.bias"] = normal(C)
+    bound = 1.0 / math.sqrt(C)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        for nm in ("norm1", "norm2"):
+            sd[b + nm + ".weight"] = uniform(C, lo=0.5, hi=1.5)
+            sd[b + nm + ".bias"] = normal(C, std=0.1)
+        sd[b + "attn.qkv.base_layer.weight"] = normal(3 * C, C, std=0.04)
+        sd[b + "attn.qkv.base_layer.bias"] = normal(3 * C, std=0.1)          # pad tokens enter attention as the bias
+        sd[b + "attn.qkv.lora_A.default.weight"] = uniform(r, C, lo=-bound, hi=bound)
+        sd[b + "attn.qkv.lora_B.default.weight"] = normal(3 * C, r)
+        n_rel = (4 * grid - 1) if i in bb["global_attn_indexes"] else (2 * ws - 1)
+        sd[b + "attn.rel_pos_h"] = normal(n_rel, d, std=0.1)
+        sd[b + "attn.rel_pos_w"] = normal(n_rel, d, std=0.1)
+        sd[b + "attn.proj.weight"] = normal(C, C, std=0.01)                   # no LayerScale: keep the branches moderate
+        sd[b + "attn.proj.bias"] = normal(C)
+        sd[b + "mlp.lin1.weight"] = normal(4 * C, C, std=0.03)
+        sd[b + "mlp.lin1.bias"] = normal(4 * C)
+        sd[b + "mlp.lin2.weight"] = normal(C, 4 * C, std=0.005)
+        sd[b + "mlp.lin2.bias"] = normal(C)
+    lin_cfg = dict(backbone=dict(embed_dim=C, depth=0, patch_size=P, mlp_ratio=4, img_size=bb["img_size"]),
+                   decode_head=cfg["decode_head"], Lora_config=dict(r=r))
+    for k, v in synthetic_state_dict(lin_cfg, seed=seed + 7).items():
+        if k.startswith("decode_head."):
+            sd[k] = v
+    return sd
