@@ -242,6 +242,29 @@ int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_
                         int crop_h, int crop_w, int lh, int lw, int rh, int rw, int H, int W, int n_img, uint8_t* labels,
                         float* logits_out, void* stream);
 
+/* ---- SAM ViT backbone (BASELINE config 5), rein/models/backbones/sam_vit.py ---------------------------------------- */
+/* Same as vfm_gemm_patch_embed / vfm_layernorm_tap with cls_rows = 0: no cls row in x / pos / the taps (SAMViT has no cls
+ * token, sam_vit.py:123-132). cls_rows = 1 is the behaviour of the plain entry points. */
+int vfm_gemm_patch_embed_ex(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
+                            int patches, int cls_rows, int M, int N, int K, void* stream);
+int vfm_layernorm_tap_ex(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                         void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, void* stream);
+
+/* rel[seq][head][token][0..k_h) = q . Rh[qh, kh, :], rel[..][k_h + kw] = q . Rw[qw, kw, :] with the UNSCALED q of the packed
+ * qkv buffer (bf16 [n_seq * q_h * q_w, 3 * heads * head_dim]); Rh fp32 [q_h][k_h][head_dim], Rw fp32 [q_w][k_w][head_dim] are
+ * get_rel_pos's gathers (sam_vit.py:358-388). Replaces the two einsums of add_decomposed_rel_pos, sam_vit.py:417-421. */
+int vfm_relpos_terms(const void* qkv, const float* Rh, const float* Rw, float* rel, int n_seq, int heads, int head_dim,
+                     int q_h, int q_w, int k_h, int k_w, void* stream);
+
+/* dst[i, :] = map[i] >= 0 ? src[map[i], :] : 0 for bf16 rows of C elements (C % 8 == 0): window_partition with its zero
+ * padding and window_unpartition, sam_vit.py:292-346. */
+int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows, int C, void* stream);
+
+/* softmax(scale * q k^T + rel[.., kh(k)] + rel[.., k_h + kw(k)]) v per (sequence, head), key k = kh * k_w + kw; head_dim 64
+ * or 80; rel may be NULL (no bias). Replaces Attention.forward's core, sam_vit.py:272-287. */
+int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,
+                         int k_h, int k_w, float scale, void* stream);
+
 /* ---------------------------------------------------------------- EVA02 backbone (rein/models/backbones/eva_02.py)
  * In-place 2-D rotary embedding of the q and k thirds of packed qkv activations [M, 3C] bf16 (VisionRotaryEmbeddingFast
  * :119-160 applied at :362-369); token 0 of every sequence (cls) is left untouched. cos/sin: fp32 [tokens_per_seq-1, 64]. */

@@ -174,7 +174,7 @@ def tiny_eva():
 
 
 def tiny_sam():
-    """tiny_sam.npz: EncoderDecoder(LoRABackbone(SAMViT dim 160 / depth 4 / 2 heads x 80, 16x16 tokens, window 14, global
+    """tiny_sam.npz: EncoderDecoder(LoRABackbone(SAMViT dim 640 / depth 4 / 8 heads x 80, 16x16 tokens, window 14, global
     blocks 1 and 3), LinearHead), slide inference on one 256x384 image (crop 256 / stride 171): reference logits + the four
     feature maps of window (0, 0)."""
     cfg = synthetic.tiny_sam_config()

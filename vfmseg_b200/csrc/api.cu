@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "attention_sm100.cuh"
+#include "sam_ops.cuh"
 #include "elementwise.cuh"
 #include "eva_ops.cuh"
 #include "gemm_sm100.cuh"
@@ -301,11 +302,16 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_tap");
 }
 
+int vfm_gemm_patch_embed_ex(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
+                            int patches, int cls_rows, int M, int N, int K, void* stream) {
+  if (!x || !bias || !pos || patches <= 0 || (M % patches) || (cls_rows & ~1)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
+  EpiPatchEmbed e{x, N, bias, pos, FastDiv(patches), cls_rows};
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
+}
+
 int vfm_gemm_patch_embed(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
                          int patches, int M, int N, int K, void* stream) {
-  if (!x || !bias || !pos || patches <= 0 || (M % patches)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
-  EpiPatchEmbed e{x, N, bias, pos, FastDiv(patches)};
-  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
+  return vfm_gemm_patch_embed_ex(A, lda, W, ldw, bias, pos, x, patches, 1, M, N, K, stream);
 }
 
 int vfm_gemm_convt2x2_gelu(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int c_out,
@@ -416,6 +422,74 @@ int vfm_attention_fwd_ex(const void* qkv, void* out, int n_seq, int seq_len, int
                           seq_len, heads, mode, S(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SAM ViT pieces (sam_ops.cuh)
+int vfm_relpos_terms(const void* qkv, const float* Rh, const float* Rw, float* rel, int n_seq, int heads, int head_dim,
+                     int q_h, int q_w, int k_h, int k_w, void* stream) {
+  if (!qkv || !Rh || !Rw || !rel || n_seq <= 0 || heads <= 0 || q_h <= 0 || q_w <= 0 || k_h <= 0 || k_w <= 0)
+    return fail(VFM_ERR_INVALID, "relpos_terms: bad args");
+  if (head_dim != 80 && head_dim != 64) return fail(VFM_ERR_INVALID, "relpos_terms: head_dim must be 64 or 80 (got %d)", head_dim);
+  const int kn = k_h > k_w ? k_h : k_w;
+  const size_t smem = (static_cast<size_t>(kn) * (head_dim + 1) + 8 * head_dim) * sizeof(float);
+  if (smem > 48 * 1024) return fail(VFM_ERR_INVALID, "relpos_terms: key grid too large (%d x %d)", k_h, k_w);
+  const dim3 grid(q_h + q_w, n_seq);
+  {
+    LaunchScope scope("relpos_terms", S(stream));
+    if (head_dim == 80)
+      relpos_terms_kernel<80><<<grid, 256, smem, S(stream)>>>(BF(qkv), 3 * heads * head_dim, Rh, Rw, rel, q_h * q_w, heads, q_h, q_w, k_h, k_w);
+    else
+      relpos_terms_kernel<64><<<grid, 256, smem, S(stream)>>>(BF(qkv), 3 * heads * head_dim, Rh, Rw, rel, q_h * q_w, heads, q_h, q_w, k_h, k_w);
+  }
+  VFM_LAUNCH_CHECK("relpos_terms");
+  return VFM_OK;
+}
+
+int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows, int C, void* stream) {
+  if (!src || !dst || !map || n_rows <= 0 || C <= 0 || (C % 8)) return fail(VFM_ERR_INVALID, "rows_gather: bad args (C %% 8 == 0)");
+  long long blocks = (n_rows * (C / 8) + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchScope scope("rows_gather", S(stream));
+    rows_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(BF(src), const_cast<__nv_bfloat16*>(BF(dst)), map, n_rows, C);
+  }
+  VFM_LAUNCH_CHECK("rows_gather");
+  return VFM_OK;
+}
+
+extern "C++" {
+template <int D>
+static int launch_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int k_h,
+                                   int k_w, float scale, cudaStream_t st) {
+  const int kk = rel ? k_h + k_w : 0;
+  const size_t smem = RelposAttSmem<D>::bytes(kk);
+  if (smem > 200 * 1024) return fail(VFM_ERR_INVALID, "attention_relpos: key grid too large (%d x %d)", k_h, k_w);
+  static size_t attr = 0;
+  if (smem > attr) {
+    VFM_CUDA(cudaFuncSetAttribute(attention_relpos_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  const dim3 grid((seq_len + RP_BLOCK_Q - 1) / RP_BLOCK_Q, heads, n_seq);
+  {
+    LaunchScope scope("attention_relpos", st);
+    attention_relpos_kernel<D><<<grid, RP_THREADS, smem, st>>>(BF(qkv), rel, const_cast<__nv_bfloat16*>(BF(out)), seq_len, heads, k_h, k_w, scale);
+  }
+  VFM_LAUNCH_CHECK("attention_relpos");
+  return VFM_OK;
+}
+}  // extern "C++"
+
+int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,
+                         int k_h, int k_w, float scale, void* stream) {
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_relpos: bad args");
+  if (rel && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len))
+    return fail(VFM_ERR_INVALID, "attention_relpos: k_h * k_w must equal seq_len when a bias is given (%d x %d vs %d)", k_h, k_w, seq_len);
+  if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_relpos: grid too large");
+  if (head_dim == 80) return launch_attention_relpos<80>(qkv, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
+  if (head_dim == 64) return launch_attention_relpos<64>(qkv, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
+  return fail(VFM_ERR_INVALID, "attention_relpos: head_dim must be 64 or 80 (got %d)", head_dim);
+}
+
 int vfm_attention_cross(const void* q, int q_ld, const void* kv, int kv_ld, void* out, int out_ld, int n_seq, int q_len,
                         int kv_len, int heads, void* stream) {
   const int C = heads * ATT_D;
@@ -463,10 +537,15 @@ int vfm_cls_rows(float* x, const float* cls_token, const float* pos, int n_crops
 
 int vfm_layernorm_tap(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
                       void* tap, int tap_ld, int tap_col0, int tokens_per_crop, void* stream) {
+  return vfm_layernorm_tap_ex(x, gamma, beta, out, M, C, eps, tap, tap_ld, tap_col0, tokens_per_crop, 1, stream);
+}
+
+int vfm_layernorm_tap_ex(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                         void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, void* stream) {
   if (!x || M <= 0) return fail(VFM_ERR_INVALID, "layernorm: bad args");
   if (!out && !tap) return fail(VFM_ERR_INVALID, "layernorm: neither an output nor a tap was given");
   if (out && (!gamma || !beta)) return fail(VFM_ERR_INVALID, "layernorm: null gamma/beta");
-  if (C % 128 || C < 128 || C > 1024) return fail(VFM_ERR_INVALID, "layernorm: C must be a multiple of 128 in [128,1024] (C=%d)", C);
+  if (C % 128 || C < 128 || C > 1536) return fail(VFM_ERR_INVALID, "layernorm: C must be a multiple of 128 in [128,1536] (C=%d)", C);
   if (tap && ((tap_ld % 8) || (tap_col0 % 8) || tokens_per_crop <= 0)) return fail(VFM_ERR_INVALID, "layernorm: bad tap layout");
   const int grid = (M + 7) / 8;
   cudaStream_t st = S(stream);
@@ -474,8 +553,9 @@ int vfm_layernorm_tap(const float* x, const float* gamma, const float* beta, voi
   {
     LaunchScope scope("layernorm", st);
     switch (C / 128) {
-#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps, BF(tap), tap_ld, tap_col0, fd); break;
+#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps, BF(tap), tap_ld, tap_col0, fd, cls_rows); break;
       VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
+      VFM_LN_CASE(9) VFM_LN_CASE(10) VFM_LN_CASE(11) VFM_LN_CASE(12)
 #undef VFM_LN_CASE
     }
   }
@@ -787,7 +867,11 @@ int vfm_linear_head_forward(const VfmLinearHeadParams* p, const void* taps, int 
   void* u2 = ws;
   int rc;
   if ((rc = vfm_gemm_bias_bf16(taps, p->in_channels, p->fusion_w, p->in_channels, nullptr, f0, mid, R, mid, p->in_channels, stream))) return rc;
-  if ((rc = vfm_groupnorm_relu(f0, f1, p->gn_w, p->gn_b, n_crops, P, mid, p->groups, p->gn_eps, 1, stream))) return rc;
+  if ((mid / p->groups) % 8 == 0) {
+    if ((rc = vfm_groupnorm_relu(f0, f1, p->gn_w, p->gn_b, n_crops, P, mid, p->groups, p->gn_eps, 1, stream))) return rc;
+  } else {   // any channels-per-group (e.g. 640 / 32 = 20)
+    if ((rc = vfm_groupnorm_act(f0, f1, 0, p->gn_w, p->gn_b, n_crops, P, mid, p->groups, p->gn_eps, 1, stream))) return rc;
+  }
   if ((rc = vfm_gemm_convt2x2_gelu(f1, mid, p->up1_w, mid, p->up1_b, u1, mid / 2, gh, gw, R, mid, stream))) return rc;
   if ((rc = vfm_gemm_convt2x2_gelu(u1, mid / 2, p->up2_w, mid / 2, p->up2_b, u2, mid / 4, 2 * gh, 2 * gw, 4 * R, mid / 2, stream))) return rc;
   if ((rc = vfm_gemm_cls_nchw(u2, mid / 4, p->cls_w, mid / 4, p->cls_b, lowres, p->num_classes, 16 * P, 16 * R, mid / 4, stream))) return rc;

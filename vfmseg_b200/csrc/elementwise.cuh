@@ -79,7 +79,7 @@ template <int ITERS>  // C = 128 * ITERS
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, int M, float eps, __nv_bfloat16* __restrict__ tap, int tap_ld,
-                 int tap_col0, FastDiv tokens_per_crop) {
+                 int tap_col0, FastDiv tokens_per_crop, int cls_rows) {
   constexpr int C = 128 * ITERS;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,10 +93,10 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   if (tap != nullptr) {
-    int crop, tok;
-    tokens_per_crop.divmod(row, crop, tok);
+    int crop = 0, tok = 1;
+    if (cls_rows) tokens_per_crop.divmod(row, crop, tok);   // cls_rows = 0 (SAM ViT: no cls token): every row is tapped
     if (tok != 0) {
-      uint2* trow = reinterpret_cast<uint2*>(tap + static_cast<size_t>(row - crop - 1) * tap_ld + tap_col0);
+      uint2* trow = reinterpret_cast<uint2*>(tap + static_cast<size_t>(row - (cls_rows ? crop + 1 : 0)) * tap_ld + tap_col0);
 #pragma unroll
       for (int i = 0; i < ITERS; ++i)
         trow[i * 32 + lane] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));

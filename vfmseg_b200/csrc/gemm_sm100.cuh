@@ -190,18 +190,19 @@ struct EpiResidual {
 struct EpiPatchEmbed {
   static constexpr int kMode = EPI_F32;
   float* x; int ldx; const float* bias; const float* pos; FastDiv patches;
+  int cls = 1;   // 1: a cls row precedes each crop's patch rows in x and in pos (DINOv2, EVA02); 0: none (SAM ViT)
   static constexpr bool kNeedsOld = true;   // "old" = the pos-embed value: all 32 are fetched before the first store
   struct Col { float b; };
   __device__ __forceinline__ Col col_setup(int col) const { return {__ldg(bias + col)}; }
   __device__ __forceinline__ float load_old(int row, int col) const {
     int crop, p;
     patches.divmod(row, crop, p);
-    return __ldg(pos + static_cast<size_t>(1 + p) * ldx + col);
+    return __ldg(pos + static_cast<size_t>(cls + p) * ldx + col);
   }
   __device__ __forceinline__ void elem(int row, int col, float v, float pe, const Col& c) const {
     int crop, p;
     patches.divmod(row, crop, p);
-    const size_t xrow = static_cast<size_t>(crop) * (patches.d + 1) + 1 + p;
+    const size_t xrow = static_cast<size_t>(crop) * (patches.d + cls) + cls + p;
     x[xrow * ldx + col] = v + c.b + pe;
   }
 };

@@ -99,7 +99,7 @@ class LoraBackboneEncoderDecoder(nn.Module):
     def engine(self) -> SlideEngine:
         if self._engine is None:
             bb = self.inner_backbone
-            dev = bb.cls_token.device
+            dev = next(bb.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("vfmseg_b200 runs on CUDA (sm_100a) only: call .cuda(); there is no CPU path")
             eng = SlideEngine(bb.packed(dev), self.decode_head.packed(), self.max_crops_per_pass)

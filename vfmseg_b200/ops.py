@@ -281,3 +281,49 @@ def layernorm_tap(x, gamma, beta, eps, tap=None, tap_col0=0, tokens_per_crop=1, 
     _C.call("vfm_layernorm_tap", _f32(x), _f32(gamma), _f32(beta), _bf16(out) if out is not None else None, M, Cc, float(eps),
             _bf16(tap) if tap is not None else None, tap.shape[1] if tap is not None else 0, tap_col0, tokens_per_crop, _stream())
     return out
+
+
+# ------------------------------------------------------------------ SAM ViT backbone (BASELINE config 5)
+def gemm_patch_embed_nocls(a, w, bias, pos, n_crops, patches):
+    """PatchEmbed + pos_embed add for a backbone without a cls token (sam_vit.py:126-132): x fp32 [n*patches, N]."""
+    M, K = a.shape
+    N = w.shape[0]
+    x = torch.empty(n_crops * patches, N, device=a.device, dtype=torch.float32)
+    _C.call("vfm_gemm_patch_embed_ex", _bf16(a), K, _bf16(w), K, _f32(bias), _f32(pos), _f32(x), patches, 0, M, N, K, _stream())
+    return x
+
+
+def layernorm_tap_nocls(x, gamma, beta, eps, tap=None, tap_col0=0, want_out=True):
+    """layernorm_tap for token streams without cls rows: tap row = x row."""
+    M, Cc = x.shape
+    out = torch.empty(M, Cc, device=x.device, dtype=torch.bfloat16) if want_out else None
+    _C.call("vfm_layernorm_tap_ex", _f32(x), _f32(gamma), _f32(beta), _bf16(out) if out is not None else None, M, Cc, float(eps),
+            _bf16(tap) if tap is not None else None, tap.shape[1] if tap is not None else 0, tap_col0, 1, 0, _stream())
+    return out
+
+
+def relpos_terms(qkv, Rh, Rw, n_seq, heads, head_dim):
+    """rel fp32 [n_seq, heads, q_h*q_w, k_h+k_w]: q . Rh[qh, kh] | q . Rw[qw, kw] on the unscaled q of the packed qkv buffer."""
+    q_h, k_h, _ = Rh.shape
+    q_w, k_w, _ = Rw.shape
+    assert qkv.shape == (n_seq * q_h * q_w, 3 * heads * head_dim)
+    rel = torch.empty(n_seq, heads, q_h * q_w, k_h + k_w, device=qkv.device, dtype=torch.float32)
+    _C.call("vfm_relpos_terms", _bf16(qkv), _f32(Rh), _f32(Rw), _f32(rel), n_seq, heads, head_dim, q_h, q_w, k_h, k_w, _stream())
+    return rel
+
+
+def rows_gather(src, row_map):
+    """dst[i] = src[row_map[i]] (zeros where row_map[i] < 0); src bf16 [*, C], row_map int32 [n]."""
+    assert row_map.dtype == torch.int32 and src.shape[1] % 8 == 0
+    dst = torch.empty(row_map.numel(), src.shape[1], device=src.device, dtype=torch.bfloat16)
+    _C.call("vfm_rows_gather", _bf16(src), _bf16(dst), _ptr(row_map), row_map.numel(), src.shape[1], _stream())
+    return dst
+
+
+def attention_relpos(qkv, rel, n_seq, seq_len, heads, head_dim, k_h, k_w, scale):
+    """softmax(scale q k^T + decomposed rel-pos bias) v on the packed qkv buffer; rel from relpos_terms or None."""
+    assert qkv.shape == (n_seq * seq_len, 3 * heads * head_dim)
+    out = torch.empty(n_seq * seq_len, heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_relpos", _bf16(qkv), _f32(rel) if rel is not None else None, _bf16(out), n_seq, seq_len, heads,
+            head_dim, k_h, k_w, float(scale), _stream())
+    return out

@@ -1,0 +1,161 @@
+"""Engine side of the SAM ViT backbone (BASELINE config 5; rein/models/backbones/sam_vit.py:55-147): weight packing (LoRA
+merge of qkv, rel-pos tables interpolated and gathered once per block) and the per-block launch sequence.
+
+Block (sam_vit.py:201-217):  x += attn(window_partition(norm1(x)));  x += mlp(norm2(x))
+  windowed blocks (window_size > 0): norm1(x) is zero-padded to a multiple of the window AFTER the norm (:306-310) and cut
+       into 14 x 14 windows, so padded tokens enter attention as q = k = v = qkv bias; attention per window with the
+       decomposed rel-pos bias of the 14 x 14 grid; windows are stitched back and the padding dropped (:335-346). proj is
+       per token, so it runs after the un-partition on the real tokens only.
+  global blocks: attention over the whole token grid; their rel-pos tables hold 4 * size - 1 entries (:248-254) and are
+       linearly interpolated to 2 * size - 1 by get_rel_pos (:372-379).
+  mlp (:17-29): lin2(GELU_erf(lin1(x))). No cls token, no LayerScale; pos_embed added without interpolation (:131-132).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _C, ops
+
+
+@dataclass
+class SamSpec:
+    embed_dim: int
+    depth: int
+    num_heads: int
+    hidden: int
+    patch_size: int
+    out_indices: Tuple[int, ...]
+    grid: int                          # img_size // patch_size: pos_embed is fixed to this grid
+    window_size: int
+    global_attn_indexes: Tuple[int, ...]
+    use_rel_pos: bool = True
+    ln_eps: float = 1e-6
+
+
+def rel_pos_table(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tensor:
+    """get_rel_pos, sam_vit.py:358-388 -> [q_size, k_size, head_dim] (the table indexed by q - k + k_size - 1)."""
+    max_rel_dist = int(2 * max(q_size, k_size) - 1)
+    r = rel_pos.float()
+    if r.shape[0] != max_rel_dist:
+        r = F.interpolate(r.reshape(1, r.shape[0], -1).permute(0, 2, 1), size=max_rel_dist, mode="linear")
+        r = r.reshape(-1, max_rel_dist).permute(1, 0)
+    q_coords = torch.arange(q_size)[:, None] * max(k_size / q_size, 1.0)
+    k_coords = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
+    rel = (q_coords - k_coords) + (k_size - 1) * max(q_size / k_size, 1.0)
+    return r[rel.long()].contiguous()
+
+
+def _lora_merged(sd, key: str, scale: float) -> torch.Tensor:
+    if key + ".base_layer.weight" in sd:
+        w = sd[key + ".base_layer.weight"].float()
+        a, b = key + ".lora_A.default.weight", key + ".lora_B.default.weight"
+        if a in sd:
+            w = w + scale * (sd[b].float() @ sd[a].float())
+        return w
+    return sd[key + ".weight"].float()
+
+
+def _bias(sd, key: str):
+    for k in (key + ".base_layer.bias", key + ".bias"):
+        if k in sd:
+            return sd[k].float()
+    return None
+
+
+class PackedSam:
+    def __init__(self, sd: Dict[str, torch.Tensor], spec: SamSpec, lora_scale: float, device):
+        self.spec, self.device = spec, device
+        sd = {k: v.detach().cpu() for k, v in sd.items()}      # fold on the host, upload once
+        C = spec.embed_dim
+        self.head_dim = d = C // spec.num_heads
+        if d not in (64, 80):
+            raise ValueError(f"vfmseg_b200 rel-pos attention kernel is built for head_dim 64 or 80, got {d}")
+        if spec.patch_size != 16:
+            raise ValueError("vfmseg_b200 patch gather is built for patch_size 16")
+        if C % 128 or spec.hidden % 32:
+            raise ValueError("embed_dim must be a multiple of 128 (LayerNorm kernel) and the MLP width of 32")
+        keep: List[torch.Tensor] = []
+
+        def dev(t, dtype):
+            t = t.detach().to(device=device, dtype=dtype).contiguous()
+            keep.append(t)
+            return t
+
+        f32, bf = torch.float32, torch.bfloat16
+        self.patch_w = dev(sd["patch_embed.proj.weight"].reshape(C, -1), bf)
+        self.patch_b = dev(sd["patch_embed.proj.bias"], f32)
+        self.pos = dev(sd["pos_embed"].reshape(-1, C), f32)                      # [grid^2, C]
+        self.ones = dev(torch.ones(C), f32)
+        g, ws = spec.grid, spec.window_size
+        self.blocks = []
+        for i in range(spec.depth):
+            p = f"blocks.{i}."
+            size = g if i in spec.global_attn_indexes or ws == 0 else ws
+            blk = dict(
+                window=0 if (i in spec.global_attn_indexes or ws == 0) else ws,
+                n1=(dev(sd[p + "norm1.weight"], f32), dev(sd[p + "norm1.bias"], f32)),
+                n2=(dev(sd[p + "norm2.weight"], f32), dev(sd[p + "norm2.bias"], f32)),
+                qkv_w=dev(_lora_merged(sd, p + "attn.qkv", lora_scale), bf), qkv_b=dev(_bias(sd, p + "attn.qkv"), f32),
+                proj_w=dev(_lora_merged(sd, p + "attn.proj", lora_scale), bf), proj_b=dev(_bias(sd, p + "attn.proj"), f32),
+                lin1_w=dev(_lora_merged(sd, p + "mlp.lin1", lora_scale), bf), lin1_b=dev(_bias(sd, p + "mlp.lin1"), f32),
+                lin2_w=dev(_lora_merged(sd, p + "mlp.lin2", lora_scale), bf), lin2_b=dev(_bias(sd, p + "mlp.lin2"), f32))
+            if spec.use_rel_pos:
+                blk["Rh"] = dev(rel_pos_table(size, size, sd[p + "attn.rel_pos_h"]), f32)
+                blk["Rw"] = dev(rel_pos_table(size, size, sd[p + "attn.rel_pos_w"]), f32)
+            self.blocks.append(blk)
+        self._keep = keep
+        self._maps: Dict[tuple, tuple] = {}
+
+    def _window_maps(self, n: int, gh: int, gw: int, ws: int):
+        """Row maps of window_partition / window_unpartition (sam_vit.py:292-346) for n crops of gh x gw tokens:
+        part[i] = token-order row feeding window-order row i (-1: zero padding), unpart[r] = window-order row of token r."""
+        key = (n, gh, gw, ws)
+        if key not in self._maps:
+            Hp, Wp = gh + (ws - gh % ws) % ws, gw + (ws - gw % ws) % ws
+            idx = torch.full((n, Hp, Wp), -1, dtype=torch.int64)
+            idx[:, :gh, :gw] = torch.arange(n * gh * gw).view(n, gh, gw)
+            part = idx.view(n, Hp // ws, ws, Wp // ws, ws).permute(0, 1, 3, 2, 4).reshape(-1)
+            unpart = torch.empty(n * gh * gw, dtype=torch.int64)
+            real = part >= 0
+            unpart[part[real]] = torch.arange(part.numel())[real]
+            n_win = n * (Hp // ws) * (Wp // ws)
+            self._maps[key] = (part.to(torch.int32).to(self.device), unpart.to(torch.int32).to(self.device), n_win)
+        return self._maps[key]
+
+    # SlideEngine.backbone_taps dispatches here
+    def forward_taps(self, img: torch.Tensor, crops: torch.Tensor, gh: int, gw: int, pixel_norm) -> torch.Tensor:
+        """SAMViT.forward (sam_vit.py:123-147) for the listed windows -> taps bf16 [n*gh*gw, n_taps*C] (token-major): the raw
+        block outputs at out_indices."""
+        s = self.spec
+        if gh != s.grid or gw != s.grid:
+            raise _C.VfmError(f"SAMViT adds a fixed {s.grid}x{s.grid} pos_embed without interpolation (sam_vit.py:131-132): "
+                              f"windows must be {s.grid * 16}x{s.grid * 16}, got grid {gh}x{gw}")
+        n, P, C, H, d = crops.shape[0], gh * gw, s.embed_dim, s.num_heads, self.head_dim
+        scale = d ** -0.5
+        a = ops.patch_gather(img, crops, gh, gw, pixel_norm if img.dtype == torch.uint8 else None)
+        x = ops.gemm_patch_embed_nocls(a, self.patch_w, self.patch_b, self.pos, n, P)
+        outs = sorted(s.out_indices)
+        taps = torch.empty(n * P, len(outs) * C, dtype=torch.bfloat16, device=x.device)
+        for i, b in enumerate(self.blocks):
+            tap_i = outs.index(i - 1) if (i - 1) in outs else None                    # tap of the previous block's output
+            h = ops.layernorm_tap_nocls(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None, (tap_i or 0) * C)
+            ws = b["window"]
+            if ws:
+                part, unpart, n_win = self._window_maps(n, gh, gw, ws)
+                qkv = ops.gemm_bias_bf16(ops.rows_gather(h, part), b["qkv_w"], b["qkv_b"])
+                rel = ops.relpos_terms(qkv, b["Rh"], b["Rw"], n_win, H, d) if s.use_rel_pos else None
+                att = ops.rows_gather(ops.attention_relpos(qkv, rel, n_win, ws * ws, H, d, ws, ws, scale), unpart)
+            else:
+                qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
+                rel = ops.relpos_terms(qkv, b["Rh"], b["Rw"], n, H, d) if s.use_rel_pos else None
+                att = ops.attention_relpos(qkv, rel, n, P, H, d, gh, gw, scale)
+            ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
+            h = ops.layernorm(x, *b["n2"], s.ln_eps)
+            ops.gemm_bias_ls_residual_(x, ops.gemm_bias_gelu_bf16(h, b["lin1_w"], b["lin1_b"]), b["lin2_w"], b["lin2_b"], self.ones)
+        if (s.depth - 1) in outs:
+            ops.layernorm_tap_nocls(x, None, None, s.ln_eps, taps, outs.index(s.depth - 1) * C, want_out=False)
+        return taps

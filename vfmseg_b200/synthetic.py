@@ -373,9 +373,10 @@ def sam_model_config(embed_dim=1280, depth=32, num_heads=16, img_size=512, out_i
 
 
 def tiny_sam_config(**kw) -> dict:
-    """2 heads x 80, 16x16 tokens: windowed blocks pad 16 -> 28 (four 14x14 windows, three of them with pad tokens),
-    global blocks interpolate their 63-entry rel-pos tables to 31."""
-    d = dict(embed_dim=160, depth=4, num_heads=2, img_size=256, out_indices=(0, 1, 2, 3), global_attn_indexes=(1, 3),
+    """8 heads x 80 (640 is the smallest width with head_dim 80 that the head's ConvT GEMMs accept: C/4 % 32 == 0), 16x16
+    tokens: windowed blocks pad 16 -> 28 (four 14x14 windows, three of them with pad tokens), global blocks interpolate
+    their 63-entry rel-pos tables to 31."""
+    d = dict(embed_dim=640, depth=4, num_heads=8, img_size=256, out_indices=(0, 1, 2, 3), global_attn_indexes=(1, 3),
              crop_size=(256, 256), stride=(171, 171), lora_r=8, lora_alpha=16)
     d.update(kw)
     return sam_model_config(**d)
