@@ -264,6 +264,12 @@ int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows
  * or 80; rel may be NULL (no bias). Replaces Attention.forward's core, sam_vit.py:272-287. */
 int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,
                          int k_h, int k_w, float scale, void* stream);
+/* Same with an explicit row pitch ld (elements) of the qkv buffer and, when g_col0 >= 0 (then rel must be NULL), the bias
+ * taken from table terms stored in the qkv rows: G_h[head][r] = q . T_h[r] (r in [0, 2 k_h - 1)) at column
+ * g_col0 + head * (2 k_h - 1) + r, all heads' G_w behind them; rel_h[q, kh] = G_h[qh - kh + k_h - 1] (get_rel_pos,
+ * sam_vit.py:382-388). G is linear in the block input: the engine emits it from the qkv GEMM (weights T . W_q). */
+int vfm_attention_relpos_ex(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len, int heads,
+                            int head_dim, int k_h, int k_w, float scale, void* stream);
 
 /* ---------------------------------------------------------------- EVA02 backbone (rein/models/backbones/eva_02.py)
  * In-place 2-D rotary embedding of the q and k thirds of packed qkv activations [M, 3C] bf16 (VisionRotaryEmbeddingFast

@@ -459,9 +459,9 @@ int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows
 
 extern "C++" {
 template <int D>
-static int launch_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int k_h,
-                                   int k_w, float scale, cudaStream_t st) {
-  const int kk = rel ? k_h + k_w : 0;
+static int launch_attention_relpos(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len,
+                                   int heads, int k_h, int k_w, float scale, cudaStream_t st) {
+  const int kk = (rel || g_col0 >= 0) ? k_h + k_w : 0;
   const size_t smem = RelposAttSmem<D>::bytes(kk);
   if (smem > 200 * 1024) return fail(VFM_ERR_INVALID, "attention_relpos: key grid too large (%d x %d)", k_h, k_w);
   static size_t attr = 0;
@@ -472,22 +472,33 @@ static int launch_attention_relpos(const void* qkv, const float* rel, void* out,
   const dim3 grid((seq_len + RP_BLOCK_Q - 1) / RP_BLOCK_Q, heads, n_seq);
   {
     LaunchScope scope("attention_relpos", st);
-    attention_relpos_kernel<D><<<grid, RP_THREADS, smem, st>>>(BF(qkv), rel, const_cast<__nv_bfloat16*>(BF(out)), seq_len, heads, k_h, k_w, scale);
+    attention_relpos_kernel<D><<<grid, RP_THREADS, smem, st>>>(BF(qkv), ld, g_col0, rel, const_cast<__nv_bfloat16*>(BF(out)), seq_len, heads,
+                                                               k_h, k_w, scale);
   }
   VFM_LAUNCH_CHECK("attention_relpos");
   return VFM_OK;
 }
 }  // extern "C++"
 
+int vfm_attention_relpos_ex(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len, int heads,
+                            int head_dim, int k_h, int k_w, float scale, void* stream) {
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_relpos: bad args");
+  const bool bias = rel != nullptr || g_col0 >= 0;
+  if (rel && g_col0 >= 0) return fail(VFM_ERR_INVALID, "attention_relpos: give either rel or g_col0, not both");
+  if (bias && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len || (k_h & 1) || (k_w & 1)))
+    return fail(VFM_ERR_INVALID, "attention_relpos: with a bias k_h * k_w must equal seq_len and both be even (%d x %d vs %d)", k_h, k_w, seq_len);
+  if (ld < 3 * heads * head_dim || (ld % 8)) return fail(VFM_ERR_INVALID, "attention_relpos: bad row pitch %d", ld);
+  if (g_col0 >= 0 && (g_col0 < 3 * heads * head_dim || g_col0 + heads * (2 * k_h - 1 + 2 * k_w - 1) > ld))
+    return fail(VFM_ERR_INVALID, "attention_relpos: table-term columns [%d, ...) do not fit the row pitch %d", g_col0, ld);
+  if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_relpos: grid too large");
+  if (head_dim == 80) return launch_attention_relpos<80>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
+  if (head_dim == 64) return launch_attention_relpos<64>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
+  return fail(VFM_ERR_INVALID, "attention_relpos: head_dim must be 64 or 80 (got %d)", head_dim);
+}
+
 int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,
                          int k_h, int k_w, float scale, void* stream) {
-  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_relpos: bad args");
-  if (rel && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len))
-    return fail(VFM_ERR_INVALID, "attention_relpos: k_h * k_w must equal seq_len when a bias is given (%d x %d vs %d)", k_h, k_w, seq_len);
-  if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_relpos: grid too large");
-  if (head_dim == 80) return launch_attention_relpos<80>(qkv, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
-  if (head_dim == 64) return launch_attention_relpos<64>(qkv, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
-  return fail(VFM_ERR_INVALID, "attention_relpos: head_dim must be 64 or 80 (got %d)", head_dim);
+  return vfm_attention_relpos_ex(qkv, 3 * heads * head_dim, -1, rel, out, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, stream);
 }
 
 int vfm_attention_cross(const void* q, int q_ld, const void* kv, int kv_ld, void* out, int out_ld, int n_seq, int q_len,

@@ -75,8 +75,13 @@ __global__ void rows_gather_kernel(const __nv_bfloat16* __restrict__ src, __nv_b
 
 // ---------------------------------------------------------------------------------------------------------------
 // softmax(scale * q k^T + rel_h[q, kh(k)] + rel_w[q, kw(k)]) v  per (sequence, head); Attention.forward sam_vit.py:263-289.
-// qkv bf16 [n_seq * seq_len, 3 * heads * D] as the qkv Linear emits it (:266-270); rel fp32 [n_seq][heads][seq_len][k_h+k_w]
-// from relpos_terms_kernel (nullptr: no bias); key index k = kh * k_w + kw. out bf16 [n_seq * seq_len, heads * D].
+// qkv bf16 [n_seq * seq_len, ld] with q | k | v in the first 3 * heads * D columns as the qkv Linear emits them (:266-270);
+// key index k = kh * k_w + kw. out bf16 [n_seq * seq_len, heads * D]. The bias comes from one of
+//   rel   fp32 [n_seq][heads][seq_len][k_h + k_w] (relpos_terms_kernel), or
+//   table terms in the qkv rows themselves (g_col0 >= 0): G_h[token][head][r] = q . T_h[r], r in [0, 2 k_h - 1), at column
+//         g_col0 + head * (2 k_h - 1) + r and G_w behind all heads' G_h; rel_h[q, kh] = G_h[qh - kh + k_h - 1] (the gather of
+//         get_rel_pos, :382-388). G is linear in the block input, so the engine gets it from the qkv GEMM as extra
+//         output columns (weights T . W_q folded on the host) instead of a separate pass over q.
 // CTA = 64 query rows of one (sequence, head); 4 warps x 16 rows; 64-key tiles double-buffered with cp.async.
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -106,13 +111,13 @@ template <int D>
 struct RelposAttSmem {
   static constexpr int kPitch = D + 8;                 // bf16 elements; (D + 8) * 2 B keeps ldmatrix rows conflict-free
   static constexpr int kTile = 64 * kPitch * 2;        // bytes of one 64-row tile
-  static size_t bytes(int kk) { return static_cast<size_t>(5) * kTile + static_cast<size_t>(RP_BLOCK_Q) * kk * 4 + 2 * 64 * 2 * 4; }
+  static size_t bytes(int kk) { return static_cast<size_t>(5) * kTile + static_cast<size_t>(RP_BLOCK_Q) * kk * 4 + 2 * 32 * 4; }
 };
 
 template <int D>
 __global__ void __launch_bounds__(RP_THREADS)
-attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ rel, __nv_bfloat16* __restrict__ out,
-                        int seq_len, int heads, int k_h, int k_w, float scale) {
+attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col0, const float* __restrict__ rel,
+                        __nv_bfloat16* __restrict__ out, int seq_len, int heads, int k_h, int k_w, float scale) {
   constexpr int P = RelposAttSmem<D>::kPitch;
   constexpr int KS = D / 16;                            // k-steps of Q K^T
   constexpr int NO = D / 8;                             // n-blocks of O
@@ -120,14 +125,14 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
   __nv_bfloat16* Ks = Qs + 64 * P;                      // [2][64][P]
   __nv_bfloat16* Vs = Ks + 2 * 64 * P;                  // [2][64][P]
-  const int kk = rel ? k_h + k_w : 0;
+  const bool has_bias = rel != nullptr || g_col0 >= 0;
+  const int kk = has_bias ? k_h + k_w : 0;                           // even: k_h, k_w are checked even by the launcher
   float* rel_s = reinterpret_cast<float*>(Vs + 2 * 64 * P);          // [64][kk]
-  int* col_h = reinterpret_cast<int*>(rel_s + RP_BLOCK_Q * kk);      // [2][64] kh of the tile's keys
-  int* col_w = col_h + 2 * 64;                                       // [2][64] kw
+  int* col_hw = reinterpret_cast<int*>(rel_s + RP_BLOCK_Q * kk);     // [2][32] per PAIR of keys: kh | (k_h + kw) << 16
 
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = heads * D, ld = 3 * C;
+  const int C = heads * D;
   const size_t row0 = static_cast<size_t>(seq) * seq_len;
   const int q0 = qt * RP_BLOCK_Q;
   const int kv_tiles = (seq_len + RP_BLOCK_KV - 1) / RP_BLOCK_KV;
@@ -141,12 +146,14 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
       else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);   // rows past the end: zeros (0 * garbage = NaN)
     }
   };
+  // k_w is even and tiles start at even keys, so the keys (2i, 2i + 1) of a pair share kh and have adjacent kw
   auto load_cols = [&](int buf, int j) {
-    if (tid < 64) {
-      const int c = j * RP_BLOCK_KV + tid;
-      const int h = k_w > 0 ? c / k_w : 0;
-      col_h[buf * 64 + tid] = h < k_h ? h : 0;
-      col_w[buf * 64 + tid] = k_h + (k_w > 0 ? c - h * k_w : 0);
+    if (tid < 32) {
+      const int c = j * RP_BLOCK_KV + 2 * tid;
+      int h = c / k_w;
+      const int w = c - h * k_w;
+      h = h < k_h ? h : 0;                     // keys past the end are masked anyway
+      col_hw[buf * 32 + tid] = h | ((k_h + w) << 16);
     }
   };
 
@@ -158,6 +165,21 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const float* rp = rel + ((static_cast<size_t>(seq) * heads + head) * seq_len + q0) * kk;
     for (int i = tid; i < RP_BLOCK_Q * kk; i += RP_THREADS) rel_s[i] = (q0 + i / kk) < seq_len ? rp[i] : 0.f;
     load_cols(0, 0);
+  } else if (g_col0 >= 0) {
+    const int Lh = 2 * k_h - 1, Lw = 2 * k_w - 1;
+    for (int i = tid; i < RP_BLOCK_Q * kk; i += RP_THREADS) {
+      const int r = i / kk, c = i - r * kk;
+      const int q = q0 + r;
+      float v = 0.f;
+      if (q < seq_len) {
+        const int qh = q / k_w, qw = q - qh * k_w;
+        const int col = c < k_h ? g_col0 + head * Lh + (qh - c + k_h - 1)
+                                : g_col0 + heads * Lh + head * Lw + (qw - (c - k_h) + k_w - 1);
+        v = __bfloat162float(qkv[(row0 + q) * ld + col]);
+      }
+      rel_s[i] = v;
+    }
+    load_cols(0, 0);
   }
 
   uint32_t qf[KS][4];
@@ -168,13 +190,14 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
   constexpr float kLog2e = 1.4426950408889634f;
   const int g = lane >> 2, t4 = lane & 3;
   const float sc = scale * kLog2e;
+  const bool warp_live = q0 + warp * 16 < seq_len;   // a warp whose 16 rows lie past the end only helps with the loads
 
   for (int j = 0; j < kv_tiles; ++j) {
     const int buf = j & 1;
     if (j + 1 < kv_tiles) {   // prefetch the next K / V tile into the other buffer (freed by the barrier at the loop end)
       load_tile(Ks + (buf ^ 1) * 64 * P, 1, (j + 1) * RP_BLOCK_KV);
       load_tile(Vs + (buf ^ 1) * 64 * P, 2, (j + 1) * RP_BLOCK_KV);
-      if (rel) load_cols(buf ^ 1, j + 1);
+      if (has_bias) load_cols(buf ^ 1, j + 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -188,14 +211,19 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     }
     const __nv_bfloat16* Kt = Ks + buf * 64 * P;
     const __nv_bfloat16* Vt = Vs + buf * 64 * P;
+    // ragged last tile: only the 16-key groups that hold real keys are multiplied (CTA-uniform bound)
+    const int keys_here = min(RP_BLOCK_KV, seq_len - j * RP_BLOCK_KV);
+    const int groups = (keys_here + 15) >> 4;
     // ---- S = Q K^T for 16 rows x 64 keys
     float s[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+    if (warp_live) {
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
 #pragma unroll
       for (int n2 = 0; n2 < 4; ++n2) {   // two 8-key blocks per ldmatrix.x4
+        if (n2 >= groups) break;
         uint32_t b[4];
         ldmatrix_x4(b, Kt + (n2 * 16 + (lane & 7) + (lane >> 4) * 8) * P + k * 16 + ((lane >> 3) & 1) * 8);
         mma_bf16_16816(s[2 * n2], qf[k], b[0], b[1]);
@@ -207,21 +235,23 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n * 8 + 2 * t4 + e;
-        float b_lo = 0.f, b_hi = 0.f;
-        if (rel) {
-          const int ch = col_h[buf * 64 + col], cw = col_w[buf * 64 + col];
-          b_lo = rel_s[r_lo * kk + ch] + rel_s[r_lo * kk + cw];
-          b_hi = rel_s[r_hi * kk + ch] + rel_s[r_hi * kk + cw];
-        }
-        const bool valid = j * RP_BLOCK_KV + col < seq_len;
-        s[n][e] = valid ? fmaf(s[n][e], sc, b_lo * kLog2e) : -INFINITY;
-        s[n][2 + e] = valid ? fmaf(s[n][2 + e], sc, b_hi * kLog2e) : -INFINITY;
-        mx0 = fmaxf(mx0, s[n][e]);
-        mx1 = fmaxf(mx1, s[n][2 + e]);
+      const int col = n * 8 + 2 * t4;        // this thread's key pair (col, col + 1) of block n
+      float2 w_lo = make_float2(0.f, 0.f), w_hi = w_lo;
+      float h_lo = 0.f, h_hi = 0.f;
+      if (has_bias) {
+        const int hw = col_hw[buf * 32 + (col >> 1)];
+        const int ch = hw & 0xffff, cw = hw >> 16;
+        h_lo = rel_s[r_lo * kk + ch]; h_hi = rel_s[r_hi * kk + ch];
+        w_lo = *reinterpret_cast<const float2*>(rel_s + r_lo * kk + cw);
+        w_hi = *reinterpret_cast<const float2*>(rel_s + r_hi * kk + cw);
       }
+      const int c_abs = j * RP_BLOCK_KV + col;
+      s[n][0] = c_abs < seq_len ? fmaf(s[n][0], sc, (h_lo + w_lo.x) * kLog2e) : -INFINITY;
+      s[n][1] = c_abs + 1 < seq_len ? fmaf(s[n][1], sc, (h_lo + w_lo.y) * kLog2e) : -INFINITY;
+      s[n][2] = c_abs < seq_len ? fmaf(s[n][2], sc, (h_hi + w_hi.x) * kLog2e) : -INFINITY;
+      s[n][3] = c_abs + 1 < seq_len ? fmaf(s[n][3], sc, (h_hi + w_hi.y) * kLog2e) : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
@@ -245,6 +275,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     // ---- O += P V
 #pragma unroll
     for (int k = 0; k < 4; ++k) {            // 16 keys per step
+      if (k >= groups) break;
 #pragma unroll
       for (int n2 = 0; n2 < NO / 2; ++n2) {  // two 8-wide blocks of head dims per ldmatrix.x4.trans
         uint32_t b[4];
@@ -253,6 +284,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         mma_bf16_16816(o[2 * n2 + 1], pa[k], b[2], b[3]);
       }
     }
+    }  // warp_live
     __syncthreads();   // everyone is done with this buffer before the next prefetch overwrites it
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

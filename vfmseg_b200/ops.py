@@ -327,3 +327,13 @@ def attention_relpos(qkv, rel, n_seq, seq_len, heads, head_dim, k_h, k_w, scale)
     _C.call("vfm_attention_relpos", _bf16(qkv), _f32(rel) if rel is not None else None, _bf16(out), n_seq, seq_len, heads,
             head_dim, k_h, k_w, float(scale), _stream())
     return out
+
+
+def attention_relpos_terms(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, g_col0):
+    """Same, with the bias read from the table terms G_h | G_w that the qkv GEMM wrote behind q | k | v (columns from g_col0
+    on: heads x (2 k_h - 1) then heads x (2 k_w - 1)); see vfm_attention_relpos_ex."""
+    assert qkv.shape[0] == n_seq * seq_len and qkv.stride(0) == qkv.shape[1]
+    out = torch.empty(n_seq * seq_len, heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_relpos_ex", _bf16(qkv), qkv.shape[1], g_col0, None, _bf16(out), n_seq, seq_len, heads, head_dim,
+            k_h, k_w, float(scale), _stream())
+    return out

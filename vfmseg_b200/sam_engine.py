@@ -49,6 +49,16 @@ def rel_pos_table(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tens
     return r[rel.long()].contiguous()
 
 
+def rel_pos_resized(size: int, rel_pos: torch.Tensor) -> torch.Tensor:
+    """The (2 size - 1, head_dim) table get_rel_pos indexes with q - k + size - 1 (sam_vit.py:372-388): linear
+    interpolation when the stored table has another length (global blocks store 4 size - 1 entries, :248-254)."""
+    L = 2 * size - 1
+    r = rel_pos.float()
+    if r.shape[0] != L:
+        r = F.interpolate(r.reshape(1, r.shape[0], -1).permute(0, 2, 1), size=L, mode="linear").reshape(-1, L).permute(1, 0)
+    return r.contiguous()
+
+
 def _lora_merged(sd, key: str, scale: float) -> torch.Tensor:
     if key + ".base_layer.weight" in sd:
         w = sd[key + ".base_layer.weight"].float()
@@ -95,17 +105,33 @@ class PackedSam:
         for i in range(spec.depth):
             p = f"blocks.{i}."
             size = g if i in spec.global_attn_indexes or ws == 0 else ws
+            wqkv, bqkv = _lora_merged(sd, p + "attn.qkv", lora_scale), _bias(sd, p + "attn.qkv")
+            if bqkv is None:
+                bqkv = torch.zeros(3 * C)
+            if spec.use_rel_pos:
+                # Table terms as extra output columns of the qkv GEMM. rel_h[q, kh] = q . T_h[qh - kh + size - 1]
+                # (add_decomposed_rel_pos :417-421 + get_rel_pos :382-388) and q = W_q x + b_q, so
+                # G_h[head][r] = q_head . T_h[r] = (T_h[r] W_q,head) x + T_h[r] . b_q,head is one more linear map of the
+                # block input: H * (2 size - 1) rows per axis, appended behind q | k | v; the attention kernel gathers
+                # rel_h / rel_w from them. Padded tokens of a window (x = 0) get G = T . b_q, exactly what q = b_q gives.
+                wq, bq = wqkv[:C].view(spec.num_heads, d, C), bqkv[:C].view(spec.num_heads, d)
+                ext_w, ext_b = [], []
+                for nm in ("attn.rel_pos_h", "attn.rel_pos_w"):
+                    T = rel_pos_resized(size, sd[p + nm])                             # [L, d]
+                    ext_w.append(torch.einsum("rd,hdc->hrc", T, wq).reshape(-1, C))  # [H * L, C]
+                    ext_b.append(torch.einsum("rd,hd->hr", T, bq).reshape(-1))
+                n_ext = sum(w.shape[0] for w in ext_w)
+                pad = (-(3 * C + n_ext)) % 32                                         # GEMM N must be a multiple of 32
+                wqkv = torch.cat([wqkv] + ext_w + [torch.zeros(pad, C)], 0)
+                bqkv = torch.cat([bqkv] + ext_b + [torch.zeros(pad)], 0)
             blk = dict(
                 window=0 if (i in spec.global_attn_indexes or ws == 0) else ws,
                 n1=(dev(sd[p + "norm1.weight"], f32), dev(sd[p + "norm1.bias"], f32)),
                 n2=(dev(sd[p + "norm2.weight"], f32), dev(sd[p + "norm2.bias"], f32)),
-                qkv_w=dev(_lora_merged(sd, p + "attn.qkv", lora_scale), bf), qkv_b=dev(_bias(sd, p + "attn.qkv"), f32),
+                qkv_w=dev(wqkv, bf), qkv_b=dev(bqkv, f32),
                 proj_w=dev(_lora_merged(sd, p + "attn.proj", lora_scale), bf), proj_b=dev(_bias(sd, p + "attn.proj"), f32),
                 lin1_w=dev(_lora_merged(sd, p + "mlp.lin1", lora_scale), bf), lin1_b=dev(_bias(sd, p + "mlp.lin1"), f32),
                 lin2_w=dev(_lora_merged(sd, p + "mlp.lin2", lora_scale), bf), lin2_b=dev(_bias(sd, p + "mlp.lin2"), f32))
-            if spec.use_rel_pos:
-                blk["Rh"] = dev(rel_pos_table(size, size, sd[p + "attn.rel_pos_h"]), f32)
-                blk["Rw"] = dev(rel_pos_table(size, size, sd[p + "attn.rel_pos_w"]), f32)
             self.blocks.append(blk)
         self._keep = keep
         self._maps: Dict[tuple, tuple] = {}
@@ -136,6 +162,7 @@ class PackedSam:
                               f"windows must be {s.grid * 16}x{s.grid * 16}, got grid {gh}x{gw}")
         n, P, C, H, d = crops.shape[0], gh * gw, s.embed_dim, s.num_heads, self.head_dim
         scale = d ** -0.5
+        g0 = 3 * C if s.use_rel_pos else -1          # first table-term column of the extended qkv rows
         a = ops.patch_gather(img, crops, gh, gw, pixel_norm if img.dtype == torch.uint8 else None)
         x = ops.gemm_patch_embed_nocls(a, self.patch_w, self.patch_b, self.pos, n, P)
         outs = sorted(s.out_indices)
@@ -146,13 +173,11 @@ class PackedSam:
             ws = b["window"]
             if ws:
                 part, unpart, n_win = self._window_maps(n, gh, gw, ws)
-                qkv = ops.gemm_bias_bf16(ops.rows_gather(h, part), b["qkv_w"], b["qkv_b"])
-                rel = ops.relpos_terms(qkv, b["Rh"], b["Rw"], n_win, H, d) if s.use_rel_pos else None
-                att = ops.rows_gather(ops.attention_relpos(qkv, rel, n_win, ws * ws, H, d, ws, ws, scale), unpart)
+                qkv = ops.gemm_bias_bf16(ops.rows_gather(h, part), b["qkv_w"], b["qkv_b"])          # q | k | v | G_h | G_w
+                att = ops.rows_gather(ops.attention_relpos_terms(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0), unpart)
             else:
                 qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
-                rel = ops.relpos_terms(qkv, b["Rh"], b["Rw"], n, H, d) if s.use_rel_pos else None
-                att = ops.attention_relpos(qkv, rel, n, P, H, d, gh, gw, scale)
+                att = ops.attention_relpos_terms(qkv, n, P, H, d, gh, gw, scale, g0)
             ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
             h = ops.layernorm(x, *b["n2"], s.ln_eps)
             ops.gemm_bias_ls_residual_(x, ops.gemm_bias_gelu_bf16(h, b["lin1_w"], b["lin1_b"]), b["lin2_w"], b["lin2_b"], self.ones)
