@@ -458,25 +458,33 @@ int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows
 }
 
 extern "C++" {
-template <int D>
-static int launch_attention_relpos(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len,
-                                   int heads, int k_h, int k_w, float scale, cudaStream_t st) {
+template <int D, int WARPS, int KV>
+static int launch_attention_relpos_cfg(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len,
+                                       int heads, int k_h, int k_w, float scale, cudaStream_t st) {
+  using Cfg = RelposCfg<D, WARPS, KV>;
   const int kk = (rel || g_col0 >= 0) ? k_h + k_w : 0;
-  const size_t smem = RelposAttSmem<D>::bytes(kk);
-  if (smem > 200 * 1024) return fail(VFM_ERR_INVALID, "attention_relpos: key grid too large (%d x %d)", k_h, k_w);
+  const size_t smem = Cfg::bytes(kk);
+  if (smem > 220 * 1024) return fail(VFM_ERR_INVALID, "attention_relpos: key grid too large (%d x %d)", k_h, k_w);
   static size_t attr = 0;
   if (smem > attr) {
-    VFM_CUDA(cudaFuncSetAttribute(attention_relpos_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    VFM_CUDA(cudaFuncSetAttribute(attention_relpos_kernel<D, WARPS, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr = smem;
   }
-  const dim3 grid((seq_len + RP_BLOCK_Q - 1) / RP_BLOCK_Q, heads, n_seq);
+  const dim3 grid((seq_len + Cfg::kBQ - 1) / Cfg::kBQ, heads, n_seq);
   {
     LaunchScope scope("attention_relpos", st);
-    attention_relpos_kernel<D><<<grid, RP_THREADS, smem, st>>>(BF(qkv), ld, g_col0, rel, const_cast<__nv_bfloat16*>(BF(out)), seq_len, heads,
-                                                               k_h, k_w, scale);
+    attention_relpos_kernel<D, WARPS, KV><<<grid, Cfg::kThreads, smem, st>>>(BF(qkv), ld, g_col0, rel, const_cast<__nv_bfloat16*>(BF(out)),
+                                                                           seq_len, heads, k_h, k_w, scale);
   }
   VFM_LAUNCH_CHECK("attention_relpos");
   return VFM_OK;
+}
+template <int D>
+static int launch_attention_relpos(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len,
+                                   int heads, int k_h, int k_w, float scale, cudaStream_t st) {
+  // short sequences (SAM's 14 x 14 windows): tiles cut to fit 196 tokens; long ones: 128 query rows share each K / V tile
+  if (seq_len <= 224) return launch_attention_relpos_cfg<D, 7, 112>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, st);
+  return launch_attention_relpos_cfg<D, 8, 64>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, st);
 }
 }  // extern "C++"
 

@@ -103,43 +103,51 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int RP_BLOCK_Q = 64;
-constexpr int RP_BLOCK_KV = 64;
-constexpr int RP_THREADS = 128;
-
-template <int D>
-struct RelposAttSmem {
+// Tile configuration: WARPS x 16 query rows per CTA, KV keys per tile. Windows of 196 tokens use <7, 112>: two query
+// tiles (112 + 84 rows: 13 of 14 warps carry rows) and two key tiles (112 + 84 keys: 26 eight-key blocks for 196 keys),
+// against four 64-row tiles x four 64-key tiles (a quarter of them padding) with the generic <4, 64> shape.
+template <int D, int WARPS, int KV>
+struct RelposCfg {
+  static constexpr int kBQ = 16 * WARPS;
+  static constexpr int kThreads = 32 * WARPS;
   static constexpr int kPitch = D + 8;                 // bf16 elements; (D + 8) * 2 B keeps ldmatrix rows conflict-free
-  static constexpr int kTile = 64 * kPitch * 2;        // bytes of one 64-row tile
-  static size_t bytes(int kk) { return static_cast<size_t>(5) * kTile + static_cast<size_t>(RP_BLOCK_Q) * kk * 4 + 2 * 32 * 4; }
+  static constexpr int kQBytes = kBQ * kPitch * 2;
+  static constexpr int kKVBytes = KV * kPitch * 2;     // one K or V tile
+  static size_t bytes(int kk) {
+    return static_cast<size_t>(kQBytes) + 4 * kKVBytes + static_cast<size_t>(kBQ) * kk * 4 + 2 * (KV / 2) * 4;
+  }
 };
 
-template <int D>
-__global__ void __launch_bounds__(RP_THREADS)
+template <int D, int WARPS, int KV>
+__global__ void __launch_bounds__(32 * WARPS, 2)
 attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col0, const float* __restrict__ rel,
                         __nv_bfloat16* __restrict__ out, int seq_len, int heads, int k_h, int k_w, float scale) {
-  constexpr int P = RelposAttSmem<D>::kPitch;
+  using Cfg = RelposCfg<D, WARPS, KV>;
+  constexpr int P = Cfg::kPitch, BQ = Cfg::kBQ, NT = Cfg::kThreads;
   constexpr int KS = D / 16;                            // k-steps of Q K^T
   constexpr int NO = D / 8;                             // n-blocks of O
+  constexpr int NB = KV / 8;                            // 8-key blocks per tile
+  constexpr int GRP = KV / 16;                          // 16-key groups per tile
+  static_assert(KV % 16 == 0 && D % 16 == 0, "tile shape");
   extern __shared__ __align__(16) uint8_t sm_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
-  __nv_bfloat16* Ks = Qs + 64 * P;                      // [2][64][P]
-  __nv_bfloat16* Vs = Ks + 2 * 64 * P;                  // [2][64][P]
+  __nv_bfloat16* Ks = Qs + BQ * P;                      // [2][KV][P]
+  __nv_bfloat16* Vs = Ks + 2 * KV * P;                  // [2][KV][P]
   const bool has_bias = rel != nullptr || g_col0 >= 0;
   const int kk = has_bias ? k_h + k_w : 0;                           // even: k_h, k_w are checked even by the launcher
-  float* rel_s = reinterpret_cast<float*>(Vs + 2 * 64 * P);          // [64][kk]
-  int* col_hw = reinterpret_cast<int*>(rel_s + RP_BLOCK_Q * kk);     // [2][32] per PAIR of keys: kh | (k_h + kw) << 16
+  float* rel_s = reinterpret_cast<float*>(Vs + 2 * KV * P);          // [BQ][kk]
+  int* col_hw = reinterpret_cast<int*>(rel_s + BQ * kk);             // [2][KV/2] per PAIR of keys: kh | (k_h + kw) << 16
 
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = heads * D;
   const size_t row0 = static_cast<size_t>(seq) * seq_len;
-  const int q0 = qt * RP_BLOCK_Q;
-  const int kv_tiles = (seq_len + RP_BLOCK_KV - 1) / RP_BLOCK_KV;
+  const int q0 = qt * BQ;
+  const int kv_tiles = (seq_len + KV - 1) / KV;
   constexpr int CH = D / 8;                             // 16-byte chunks per row
 
-  auto load_tile = [&](__nv_bfloat16* dst, int which, int r0) {   // 64 rows of Q / K / V (which = 0 / 1 / 2)
-    for (int i = tid; i < 64 * CH; i += RP_THREADS) {
+  auto load_tile = [&](__nv_bfloat16* dst, int which, int r0, int rows) {   // rows of Q / K / V (which = 0 / 1 / 2)
+    for (int i = tid; i < rows * CH; i += NT) {
       const int r = i / CH, c = i - r * CH;
       __nv_bfloat16* d = dst + r * P + c * 8;
       if (r0 + r < seq_len) cp_async16(d, qkv + (row0 + r0 + r) * ld + which * C + head * D + c * 8);
@@ -148,36 +156,50 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
   };
   // k_w is even and tiles start at even keys, so the keys (2i, 2i + 1) of a pair share kh and have adjacent kw
   auto load_cols = [&](int buf, int j) {
-    if (tid < 32) {
-      const int c = j * RP_BLOCK_KV + 2 * tid;
+    if (tid < KV / 2) {
+      const int c = j * KV + 2 * tid;
       int h = c / k_w;
       const int w = c - h * k_w;
       h = h < k_h ? h : 0;                     // keys past the end are masked anyway
-      col_hw[buf * 32 + tid] = h | ((k_h + w) << 16);
+      col_hw[buf * (KV / 2) + tid] = h | ((k_h + w) << 16);
     }
   };
 
-  load_tile(Qs, 0, q0);
-  load_tile(Ks, 1, 0);
-  load_tile(Vs, 2, 0);
+  load_tile(Qs, 0, q0, BQ);
+  load_tile(Ks, 1, 0, KV);
+  load_tile(Vs, 2, 0, KV);
   cp_async_commit();
   if (rel) {
     const float* rp = rel + ((static_cast<size_t>(seq) * heads + head) * seq_len + q0) * kk;
-    for (int i = tid; i < RP_BLOCK_Q * kk; i += RP_THREADS) rel_s[i] = (q0 + i / kk) < seq_len ? rp[i] : 0.f;
+    for (int i = tid; i < BQ * kk; i += NT) rel_s[i] = (q0 + i / kk) < seq_len ? rp[i] : 0.f;
     load_cols(0, 0);
   } else if (g_col0 >= 0) {
+    // row r of the tile: G_h is read backwards (qh - kh + k_h - 1 for kh = 0..k_h-1), G_w likewise — two contiguous runs.
+    // Four rows per warp step with all loads issued before the first store (one memory round trip per step, not four).
     const int Lh = 2 * k_h - 1, Lw = 2 * k_w - 1;
-    for (int i = tid; i < RP_BLOCK_Q * kk; i += RP_THREADS) {
-      const int r = i / kk, c = i - r * kk;
-      const int q = q0 + r;
-      float v = 0.f;
-      if (q < seq_len) {
-        const int qh = q / k_w, qw = q - qh * k_w;
-        const int col = c < k_h ? g_col0 + head * Lh + (qh - c + k_h - 1)
-                                : g_col0 + heads * Lh + head * Lw + (qw - (c - k_h) + k_w - 1);
-        v = __bfloat162float(qkv[(row0 + q) * ld + col]);
+    constexpr int RB = 4;
+    for (int r = warp; r < BQ; r += WARPS * RB) {
+      const __nv_bfloat16* gh[RB];
+      const __nv_bfloat16* gw[RB];
+      bool live[RB];
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int q = q0 + r + u * WARPS;
+        live[u] = r + u * WARPS < BQ && q < seq_len;
+        const int qq = live[u] ? q : 0;
+        const int qh = qq / k_w, qw = qq - qh * k_w;
+        const __nv_bfloat16* gp = qkv + (row0 + qq) * ld + g_col0;
+        gh[u] = gp + head * Lh + qh + k_h - 1;
+        gw[u] = gp + heads * Lh + head * Lw + qw + k_w - 1;
       }
-      rel_s[i] = v;
+      for (int c = lane; c < kk; c += 32) {
+        __nv_bfloat16 v[RB];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) v[u] = c < k_h ? gh[u][-c] : gw[u][-(c - k_h)];
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+          if (r + u * WARPS < BQ) rel_s[(r + u * WARPS) * kk + c] = live[u] ? __bfloat162float(v[u]) : 0.f;
+      }
     }
     load_cols(0, 0);
   }
@@ -195,8 +217,8 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
   for (int j = 0; j < kv_tiles; ++j) {
     const int buf = j & 1;
     if (j + 1 < kv_tiles) {   // prefetch the next K / V tile into the other buffer (freed by the barrier at the loop end)
-      load_tile(Ks + (buf ^ 1) * 64 * P, 1, (j + 1) * RP_BLOCK_KV);
-      load_tile(Vs + (buf ^ 1) * 64 * P, 2, (j + 1) * RP_BLOCK_KV);
+      load_tile(Ks + (buf ^ 1) * KV * P, 1, (j + 1) * KV, KV);
+      load_tile(Vs + (buf ^ 1) * KV * P, 2, (j + 1) * KV, KV);
       if (has_bias) load_cols(buf ^ 1, j + 1);
       cp_async_commit();
       cp_async_wait<1>();
@@ -204,89 +226,94 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (j == 0) {
-#pragma unroll
-      for (int k = 0; k < KS; ++k)
-        ldmatrix_x4(qf[k], Qs + (warp * 16 + (lane & 15)) * P + k * 16 + (lane >> 4) * 8);
-    }
-    const __nv_bfloat16* Kt = Ks + buf * 64 * P;
-    const __nv_bfloat16* Vt = Vs + buf * 64 * P;
-    // ragged last tile: only the 16-key groups that hold real keys are multiplied (CTA-uniform bound)
-    const int keys_here = min(RP_BLOCK_KV, seq_len - j * RP_BLOCK_KV);
-    const int groups = (keys_here + 15) >> 4;
-    // ---- S = Q K^T for 16 rows x 64 keys
-    float s[8][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
     if (warp_live) {
+      // wide key tiles (14 score blocks in registers) re-read the Q fragments from shared memory every tile instead of
+      // holding 20 registers across the loop: 158 -> <= 146 registers is the difference between one and two CTAs per SM
+      if (j == 0 || KV > 64) {
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
+        for (int k = 0; k < KS; ++k)
+          ldmatrix_x4(qf[k], Qs + (warp * 16 + (lane & 15)) * P + k * 16 + (lane >> 4) * 8);
+      }
+      const __nv_bfloat16* Kt = Ks + buf * KV * P;
+      const __nv_bfloat16* Vt = Vs + buf * KV * P;
+      // ragged last tile: only the 16-key groups that hold real keys are multiplied (CTA-uniform bound)
+      const int keys_here = min(KV, seq_len - j * KV);
+      const int groups = (keys_here + 15) >> 4;
+      // ---- S = Q K^T for 16 rows x KV keys
+      float s[NB][4];
 #pragma unroll
-      for (int n2 = 0; n2 < 4; ++n2) {   // two 8-key blocks per ldmatrix.x4
-        if (n2 >= groups) break;
-        uint32_t b[4];
-        ldmatrix_x4(b, Kt + (n2 * 16 + (lane & 7) + (lane >> 4) * 8) * P + k * 16 + ((lane >> 3) & 1) * 8);
-        mma_bf16_16816(s[2 * n2], qf[k], b[0], b[1]);
-        mma_bf16_16816(s[2 * n2 + 1], qf[k], b[2], b[3]);
+      for (int n = 0; n < NB; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+#pragma unroll
+      for (int n2 = 0; n2 < GRP; ++n2) {   // two 8-key blocks per ldmatrix.x4
+        if (n2 < groups) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            uint32_t b[4];
+            ldmatrix_x4(b, Kt + (n2 * 16 + (lane & 7) + (lane >> 4) * 8) * P + k * 16 + ((lane >> 3) & 1) * 8);
+            mma_bf16_16816(s[2 * n2], qf[k], b[0], b[1]);
+            mma_bf16_16816(s[2 * n2 + 1], qf[k], b[2], b[3]);
+          }
+        }
+      }
+      // ---- scale, bias, mask (everything in log2 units)
+      const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const int col = n * 8 + 2 * t4;        // this thread's key pair (col, col + 1) of block n
+        float2 w_lo = make_float2(0.f, 0.f), w_hi = w_lo;
+        float h_lo = 0.f, h_hi = 0.f;
+        if (has_bias) {
+          const int hw = col_hw[buf * (KV / 2) + (col >> 1)];
+          const int ch = hw & 0xffff, cw = hw >> 16;
+          h_lo = rel_s[r_lo * kk + ch]; h_hi = rel_s[r_hi * kk + ch];
+          w_lo = *reinterpret_cast<const float2*>(rel_s + r_lo * kk + cw);
+          w_hi = *reinterpret_cast<const float2*>(rel_s + r_hi * kk + cw);
+        }
+        const int c_abs = j * KV + col;
+        s[n][0] = c_abs < seq_len ? fmaf(s[n][0], sc, (h_lo + w_lo.x) * kLog2e) : -INFINITY;
+        s[n][1] = c_abs + 1 < seq_len ? fmaf(s[n][1], sc, (h_lo + w_lo.y) * kLog2e) : -INFINITY;
+        s[n][2] = c_abs < seq_len ? fmaf(s[n][2], sc, (h_hi + w_hi.x) * kLog2e) : -INFINITY;
+        s[n][3] = c_abs + 1 < seq_len ? fmaf(s[n][3], sc, (h_hi + w_hi.y) * kLog2e) : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);     // finite: every tile has at least one valid key
+      const float a0 = fast_exp2(m0 - mn0), a1 = fast_exp2(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int n = 0; n < NO; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
+      // ---- P = exp2(s - m) as bf16 A fragments; the row sums add up the rounded values the MMA consumes
+      uint32_t pa[GRP][4];
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(fast_exp2(s[n][0] - m0), fast_exp2(s[n][1] - m0));
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(fast_exp2(s[n][2] - m1), fast_exp2(s[n][3] - m1));
+        l0 += __low2float(lo) + __high2float(lo);
+        l1 += __low2float(hi) + __high2float(hi);
+        pa[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&lo);
+        pa[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+      // ---- O += P V
+#pragma unroll
+      for (int k = 0; k < GRP; ++k) {          // 16 keys per step
+        if (k < groups) {
+#pragma unroll
+          for (int n2 = 0; n2 < NO / 2; ++n2) {  // two 8-wide blocks of head dims per ldmatrix.x4.trans
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, Vt + (k * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + n2 * 16 + (lane >> 4) * 8);
+            mma_bf16_16816(o[2 * n2], pa[k], b[0], b[1]);
+            mma_bf16_16816(o[2 * n2 + 1], pa[k], b[2], b[3]);
+          }
+        }
       }
     }
-    // ---- scale, bias, mask (everything in log2 units)
-    const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int col = n * 8 + 2 * t4;        // this thread's key pair (col, col + 1) of block n
-      float2 w_lo = make_float2(0.f, 0.f), w_hi = w_lo;
-      float h_lo = 0.f, h_hi = 0.f;
-      if (has_bias) {
-        const int hw = col_hw[buf * 32 + (col >> 1)];
-        const int ch = hw & 0xffff, cw = hw >> 16;
-        h_lo = rel_s[r_lo * kk + ch]; h_hi = rel_s[r_hi * kk + ch];
-        w_lo = *reinterpret_cast<const float2*>(rel_s + r_lo * kk + cw);
-        w_hi = *reinterpret_cast<const float2*>(rel_s + r_hi * kk + cw);
-      }
-      const int c_abs = j * RP_BLOCK_KV + col;
-      s[n][0] = c_abs < seq_len ? fmaf(s[n][0], sc, (h_lo + w_lo.x) * kLog2e) : -INFINITY;
-      s[n][1] = c_abs + 1 < seq_len ? fmaf(s[n][1], sc, (h_lo + w_lo.y) * kLog2e) : -INFINITY;
-      s[n][2] = c_abs < seq_len ? fmaf(s[n][2], sc, (h_hi + w_hi.x) * kLog2e) : -INFINITY;
-      s[n][3] = c_abs + 1 < seq_len ? fmaf(s[n][3], sc, (h_hi + w_hi.y) * kLog2e) : -INFINITY;
-      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
-      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);     // finite: every tile has at least one valid key
-    const float a0 = fast_exp2(m0 - mn0), a1 = fast_exp2(m1 - mn1);
-    m0 = mn0; m1 = mn1;
-    l0 *= a0; l1 *= a1;
-#pragma unroll
-    for (int n = 0; n < NO; ++n) { o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1; }
-    // ---- P = exp2(s - m) as bf16 A fragments; the row sums add up the rounded values the MMA consumes
-    uint32_t pa[4][4];
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(fast_exp2(s[n][0] - m0), fast_exp2(s[n][1] - m0));
-      const __nv_bfloat162 hi = __floats2bfloat162_rn(fast_exp2(s[n][2] - m1), fast_exp2(s[n][3] - m1));
-      l0 += __low2float(lo) + __high2float(lo);
-      l1 += __low2float(hi) + __high2float(hi);
-      pa[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&lo);
-      pa[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&hi);
-    }
-    // ---- O += P V
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {            // 16 keys per step
-      if (k >= groups) break;
-#pragma unroll
-      for (int n2 = 0; n2 < NO / 2; ++n2) {  // two 8-wide blocks of head dims per ldmatrix.x4.trans
-        uint32_t b[4];
-        ldmatrix_x4_trans(b, Vt + (k * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + n2 * 16 + (lane >> 4) * 8);
-        mma_bf16_16816(o[2 * n2], pa[k], b[0], b[1]);
-        mma_bf16_16816(o[2 * n2 + 1], pa[k], b[2], b[3]);
-      }
-    }
-    }  // warp_live
     __syncthreads();   // everyone is done with this buffer before the next prefetch overwrites it
   }
+  if (!warp_live) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
