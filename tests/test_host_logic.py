@@ -219,3 +219,61 @@ def test_id2color_and_png_export(tmp_path):
     m.process({}, [dict(pred_sem_seg=dict(data=torch.from_numpy(lab)[None]), img_path="/x/y/frankfurt_000000.png", seg_map_path="a/citys/b.png")])
     out = np.asarray(Image.open(tmp_path / "frankfurt_000000.png"))
     assert np.array_equal(out, rgb) and m.results == []
+
+
+# ------------------------------------------------------------------ SAM ViT host logic (BASELINE config 5)
+def test_sam_window_maps_match_reference_partition():
+    """PackedSam._window_maps against the arithmetic of window_partition / window_unpartition (sam_vit.py:292-346)."""
+    import torch.nn.functional as F
+    from vfmseg_b200.sam_engine import PackedSam
+    n, gh, gw, ws, C = 2, 20, 16, 14, 8
+    holder = type("E", (), {"_maps": {}, "device": "cpu"})()
+    part, unpart, n_win = PackedSam._window_maps(holder, n, gh, gw, ws)
+    x = torch.arange(n * gh * gw * C, dtype=torch.float32).view(n, gh, gw, C) + 1.0
+    ph, pw = (ws - gh % ws) % ws, (ws - gw % ws) % ws
+    Hp, Wp = gh + ph, gw + pw
+    win = F.pad(x, (0, 0, 0, pw, 0, ph)).view(n, Hp // ws, ws, Wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, C)
+    flat = torch.cat([x.view(-1, C), torch.zeros(1, C)])            # index -1 -> the zero row
+    assert n_win == win.shape[0] // (ws * ws) == 8
+    assert torch.equal(flat[part.long()], win)
+    assert torch.equal(win[unpart.long()], x.view(-1, C))
+
+
+def test_sam_table_terms_folded_into_qkv_match_decomposed_rel_pos():
+    """The extra qkv output columns (T . W_q) reproduce add_decomposed_rel_pos (sam_vit.py:391-428): gathering
+    G_h[qh - kh + K - 1] / G_w[qw - kw + K - 1] equals the reference's two einsums on the unscaled q."""
+    from oracle import torch_ref
+    from vfmseg_b200 import synthetic
+    from vfmseg_b200.sam_engine import PackedSam, SamSpec
+    cfg = synthetic.tiny_sam_config(depth=2, global_attn_indexes=(1,), out_indices=(0, 1))
+    sd_full = synthetic.synthetic_sam_state_dict(cfg, seed=0)
+    pre = "backbone.model.base_model.model."
+    sd = {k[len(pre):]: v for k, v in sd_full.items() if k.startswith(pre)}
+    bb, lc = cfg["backbone"]["backbone"], cfg["backbone"]["Lora_config"]
+    C, H = bb["embed_dim"], bb["num_heads"]
+    d = C // H
+    spec = SamSpec(C, bb["depth"], H, 4 * C, 16, tuple(bb["out_indices"]), bb["img_size"] // 16, bb["window_size"],
+                   tuple(bb["global_attn_indexes"]))
+    scale = lc["lora_alpha"] / lc["r"]
+    pk = PackedSam(sd, spec, scale, "cpu")
+    g = torch.Generator().manual_seed(5)
+    for i, K in ((0, bb["window_size"]), (1, spec.grid)):            # windowed block, global block (interpolated table)
+        x = torch.randn(K * K, C, generator=g)
+        w, b = pk.blocks[i]["qkv_w"].float(), pk.blocks[i]["qkv_b"]
+        y = x @ w.t() + b
+        L = 2 * K - 1
+        assert w.shape[0] % 32 == 0 and w.shape[0] >= 3 * C + 2 * H * L
+        q = y[:, :C].view(K, K, H, d)
+        Gh = y[:, 3 * C:3 * C + H * L].view(K, K, H, L)
+        Gw = y[:, 3 * C + H * L:3 * C + 2 * H * L].view(K, K, H, L)
+        p = f"blocks.{i}.attn."
+        Rh = torch_ref.sam_rel_pos_table(K, K, sd[p + "rel_pos_h"])
+        Rw = torch_ref.sam_rel_pos_table(K, K, sd[p + "rel_pos_w"])
+        rel_h = torch.einsum("hwnc,hkc->hwnk", q, Rh)
+        rel_w = torch.einsum("hwnc,wkc->hwnk", q, Rw)
+        idx = torch.arange(K)[:, None] - torch.arange(K)[None, :] + K - 1                 # [q, k]
+        got_h = torch.gather(Gh, 3, idx[:, None, None, :].expand(K, K, H, K))
+        got_w = torch.gather(Gw, 3, idx[None, :, None, :].expand(K, K, H, K))
+        # bf16 weights on one side, fp32 on the other: compare at bf16 resolution of the accumulated products
+        assert torch.allclose(got_h, rel_h, rtol=2e-2, atol=2e-2), (got_h - rel_h).abs().max()
+        assert torch.allclose(got_w, rel_w, rtol=2e-2, atol=2e-2), (got_w - rel_w).abs().max()
