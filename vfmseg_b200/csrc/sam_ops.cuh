@@ -114,7 +114,7 @@ struct RelposCfg {
   static constexpr int kQBytes = kBQ * kPitch * 2;
   static constexpr int kKVBytes = KV * kPitch * 2;     // one K or V tile
   static size_t bytes(int kk) {
-    return static_cast<size_t>(kQBytes) + 4 * kKVBytes + static_cast<size_t>(kBQ) * kk * 4 + 2 * (KV / 2) * 4;
+    return static_cast<size_t>(kQBytes) + 4 * kKVBytes + static_cast<size_t>(kBQ) * kk * 2 + 2 * (KV / 2) * 4;
   }
 };
 
@@ -135,7 +135,9 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
   __nv_bfloat16* Vs = Ks + 2 * KV * P;                  // [2][KV][P]
   const bool has_bias = rel != nullptr || g_col0 >= 0;
   const int kk = has_bias ? k_h + k_w : 0;                           // even: k_h, k_w are checked even by the launcher
-  float* rel_s = reinterpret_cast<float*>(Vs + 2 * KV * P);          // [BQ][kk]
+  // bias terms of this CTA's query rows as bf16 (the table terms ARE bf16; 64 KB of fp32 for a 64 x 64 key grid would
+  // cost the second CTA per SM)
+  __nv_bfloat16* rel_s = Vs + 2 * KV * P;                            // [BQ][kk]
   int* col_hw = reinterpret_cast<int*>(rel_s + BQ * kk);             // [2][KV/2] per PAIR of keys: kh | (k_h + kw) << 16
 
   const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
@@ -171,7 +173,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
   cp_async_commit();
   if (rel) {
     const float* rp = rel + ((static_cast<size_t>(seq) * heads + head) * seq_len + q0) * kk;
-    for (int i = tid; i < BQ * kk; i += NT) rel_s[i] = (q0 + i / kk) < seq_len ? rp[i] : 0.f;
+    for (int i = tid; i < BQ * kk; i += NT) rel_s[i] = __float2bfloat16((q0 + i / kk) < seq_len ? rp[i] : 0.f);
     load_cols(0, 0);
   } else if (g_col0 >= 0) {
     // row r of the tile: G_h is read backwards (qh - kh + k_h - 1 for kh = 0..k_h-1), G_w likewise — two contiguous runs.
@@ -198,7 +200,7 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
         for (int u = 0; u < RB; ++u) v[u] = c < k_h ? gh[u][-c] : gw[u][-(c - k_h)];
 #pragma unroll
         for (int u = 0; u < RB; ++u)
-          if (r + u * WARPS < BQ) rel_s[(r + u * WARPS) * kk + c] = live[u] ? __bfloat162float(v[u]) : 0.f;
+          if (r + u * WARPS < BQ) rel_s[(r + u * WARPS) * kk + c] = live[u] ? v[u] : __float2bfloat16(0.f);
       }
     }
     load_cols(0, 0);
@@ -266,9 +268,9 @@ attention_relpos_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int g_col
         if (has_bias) {
           const int hw = col_hw[buf * (KV / 2) + (col >> 1)];
           const int ch = hw & 0xffff, cw = hw >> 16;
-          h_lo = rel_s[r_lo * kk + ch]; h_hi = rel_s[r_hi * kk + ch];
-          w_lo = *reinterpret_cast<const float2*>(rel_s + r_lo * kk + cw);
-          w_hi = *reinterpret_cast<const float2*>(rel_s + r_hi * kk + cw);
+          h_lo = __bfloat162float(rel_s[r_lo * kk + ch]); h_hi = __bfloat162float(rel_s[r_hi * kk + ch]);
+          w_lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rel_s + r_lo * kk + cw));
+          w_hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rel_s + r_hi * kk + cw));
         }
         const int c_abs = j * KV + col;
         s[n][0] = c_abs < seq_len ? fmaf(s[n][0], sc, (h_lo + w_lo.x) * kLog2e) : -INFINITY;
