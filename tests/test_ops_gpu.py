@@ -125,7 +125,10 @@ def _attn_ref(qkv, n_seq, S, heads):
 # mode 0 = automatic, 1 = tensor tiles over every token (ragged tail tiles), 2 = token 0 split off (cls token)
 @pytest.mark.parametrize("n_seq,S,heads,mode", [
     (1, 128, 1, 1), (2, 256, 2, 1), (1, 1025, 16, 0), (3, 1025, 4, 1), (3, 1025, 4, 2), (2, 197, 2, 1), (2, 197, 2, 2),
-    (1, 2049, 2, 0), (1, 2049, 2, 1), (2, 17, 2, 0), (2, 17, 2, 2), (2, 2, 1, 2), (1, 385, 3, 0), (2, 641, 2, 1)])
+    (1, 2049, 2, 0), (1, 2049, 2, 1), (2, 17, 2, 0), (2, 17, 2, 2), (2, 2, 1, 2), (1, 385, 3, 0), (2, 641, 2, 1),
+    # more units than persistent CTAs (2 x 148): every CTA streams several units back to back — odd and even key-tile
+    # counts per unit (buffer / phase parity across unit boundaries), one- and two-tile units, extra-token mode
+    (20, 257, 12, 0), (20, 257, 12, 2), (40, 65, 8, 1), (600, 17, 1, 0), (300, 129, 2, 2), (7, 1025, 16, 0)])
 def test_attention(ops, n_seq, S, heads, mode):
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=21, dtype=torch.bfloat16)
     out = ops.attention_fwd(qkv, n_seq, S, heads, mode)
