@@ -289,7 +289,7 @@ def run_b200_arm(args):
         traffic = None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (same launch shape only)
             t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(top)
-            if t and t["crops_per_launch"] * cnt == crops_per_run:
+            if t and t["crops_per_launch"] == min(args.crops_per_pass, B * CROPS_PER_IMAGE):
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         except Exception:
             traffic = None
