@@ -87,7 +87,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, smax, reasons = [], None, set()
+        sm, pw, smax, reasons = [], [], None, set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
@@ -99,13 +99,14 @@ class ClockSampler:
                         continue
                 sm.append(float(f[1]))
                 smax = float(f[2])
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": round(statistics.median(pw), 1) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
