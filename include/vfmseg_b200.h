@@ -264,6 +264,11 @@ int vfm_rows_gather(const void* src, void* dst, const int* map, long long n_rows
  * or 80; rel may be NULL (no bias). Replaces Attention.forward's core, sam_vit.py:272-287. */
 int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,
                          int k_h, int k_w, float scale, void* stream);
+/* The same attention for windows whose keys fit one score tile (seq_len <= 208, head_dim 80) on tcgen05: the bias is added by
+ * the tensor core ([rel_h | rel_w] x one-hot key columns as extra k-steps of the score MMA); arguments as
+ * vfm_attention_relpos_ex with rel == NULL (g_col0 < 0: no bias). sam_vit.py:272-287,391-428. */
+int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int n_seq, int seq_len, int heads, int head_dim,
+                            int k_h, int k_w, float scale, void* stream);
 /* Same with an explicit row pitch ld (elements) of the qkv buffer and, when g_col0 >= 0 (then rel must be NULL), the bias
  * taken from table terms stored in the qkv rows: G_h[head][r] = q . T_h[r] (r in [0, 2 k_h - 1)) at column
  * g_col0 + head * (2 k_h - 1) + r, all heads' G_w behind them; rel_h[q, kh] = G_h[qh - kh + k_h - 1] (get_rel_pos,

@@ -117,3 +117,31 @@ def test_full_size_sam_runs():
     assert torch.isfinite(logits).all() and labels.shape == (1, 1024, 2048)
     labels2, _ = model.predict_labels(img)
     assert torch.equal(labels2[0], labels[0])
+
+
+@pytest.mark.parametrize("n_seq,k,heads,bias", [(5, 14, 2, True), (162, 14, 16, True), (3, 14, 2, False), (4, 12, 3, True), (2, 8, 1, True)])
+def test_attention_window_tc(n_seq, k, heads, bias):
+    """tcgen05 window attention (bias added by the tensor core through one-hot key columns) against torch fp32 on the same
+    packed rows: q | k | v | G_h | G_w with random table terms, rel_h[q, kh] = G_h[qh - kh + k - 1]."""
+    from vfmseg_b200 import ops
+    d, S, L = 80, k * k, 2 * k - 1
+    C = heads * d
+    ld = 3 * C + 2 * heads * L
+    ld += (-ld) % 32
+    qkv = _rand(n_seq * S, ld, scale=0.7, seed=7, dtype=torch.bfloat16)
+    scale = d ** -0.5
+    got = ops.attention_window_tc(qkv, n_seq, S, heads, d, k, k, scale, 3 * C if bias else -1).float().cpu()
+    x = qkv.float().cpu()
+    q, kk_, v = x[:, :3 * C].view(n_seq, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    att = (q * scale) @ kk_.transpose(-1, -2)
+    if bias:
+        Gh = x[:, 3 * C:3 * C + heads * L].view(n_seq, k, k, heads, L)
+        Gw = x[:, 3 * C + heads * L:3 * C + 2 * heads * L].view(n_seq, k, k, heads, L)
+        idx = torch.arange(k)[:, None] - torch.arange(k)[None, :] + k - 1                      # [q, key]
+        rel_h = torch.gather(Gh, 4, idx[None, :, None, None, :].expand(n_seq, k, k, heads, k))  # [n, qh, qw, head, kh]
+        rel_w = torch.gather(Gw, 4, idx[None, None, :, None, :].expand(n_seq, k, k, heads, k))  # [n, qh, qw, head, kw]
+        b = rel_h[..., :, None] + rel_w[..., None, :]                                          # [n, qh, qw, head, kh, kw]
+        att = att + b.permute(0, 3, 1, 2, 4, 5).reshape(n_seq, heads, S, S)
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
+    err = (got - ref).abs()
+    assert (err <= 2e-2 + 2e-2 * ref.abs()).all(), err.max()

@@ -14,6 +14,7 @@
 
 #include "attention_sm100.cuh"
 #include "sam_ops.cuh"
+#include "attention_win_sm100.cuh"
 #include "elementwise.cuh"
 #include "eva_ops.cuh"
 #include "gemm_sm100.cuh"
@@ -502,6 +503,39 @@ int vfm_attention_relpos_ex(const void* qkv, int ld, int g_col0, const float* re
   if (head_dim == 80) return launch_attention_relpos<80>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
   if (head_dim == 64) return launch_attention_relpos<64>(qkv, ld, g_col0, rel, out, n_seq, seq_len, heads, k_h, k_w, scale, S(stream));
   return fail(VFM_ERR_INVALID, "attention_relpos: head_dim must be 64 or 80 (got %d)", head_dim);
+}
+
+int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int n_seq, int seq_len, int heads, int head_dim,
+                            int k_h, int k_w, float scale, void* stream) {
+  if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_window_tc: bad args");
+  if (head_dim != WIN_D) return fail(VFM_ERR_INVALID, "attention_window_tc: head_dim must be %d (got %d)", WIN_D, head_dim);
+  if (seq_len > WIN_KEYS) return fail(VFM_ERR_INVALID, "attention_window_tc: at most %d tokens per window (got %d)", WIN_KEYS, seq_len);
+  if (ld < 3 * heads * head_dim || (ld % 8)) return fail(VFM_ERR_INVALID, "attention_window_tc: bad row pitch %d", ld);
+  if (g_col0 >= 0 && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len || k_h + k_w > 64 || g_col0 < 3 * heads * head_dim ||
+                      g_col0 + heads * (2 * k_h - 1 + 2 * k_w - 1) > ld))
+    return fail(VFM_ERR_INVALID, "attention_window_tc: bad key grid %d x %d / table-term columns from %d (row pitch %d)", k_h, k_w, g_col0, ld);
+  if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_window_tc: grid too large");
+  if ((reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention_window_tc: out must be 16-byte aligned");
+  const uint64_t rows = static_cast<uint64_t>(n_seq) * seq_len;
+  CUtensorMap tq, tkv;
+  int rc;
+  if ((rc = make_tmap(&tq, qkv, rows, ld, ld, 64))) return rc;
+  if ((rc = make_tmap(&tkv, qkv, rows, ld, ld, WIN_KEYS / 2))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VFM_CUDA(cudaFuncSetAttribute(attention_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES));
+    attr_done = true;
+  }
+  WinParams p{};
+  p.seq_len = seq_len; p.heads = heads; p.k_h = k_h; p.k_w = k_w; p.ld = ld; p.g_col0 = g_col0; p.scale = scale;
+  p.qkv = BF(qkv); p.out = const_cast<__nv_bfloat16*>(BF(out));
+  const dim3 grid((seq_len + WIN_BLOCK_Q - 1) / WIN_BLOCK_Q, heads, n_seq);
+  {
+    LaunchScope scope("attention_window_tc", S(stream));
+    attention_win_kernel<<<grid, WIN_THREADS, WIN_SMEM_BYTES, S(stream)>>>(tq, tkv, p);
+  }
+  VFM_LAUNCH_CHECK("attention_window_tc");
+  return VFM_OK;
 }
 
 int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,

@@ -1,0 +1,246 @@
+// Window attention with the decomposed rel-pos bias on tcgen05 (SAM ViT windowed blocks: 196 tokens, head_dim 80).
+//
+// Replaces Attention.forward's core for one window, rein/models/backbones/sam_vit.py:272-287 with
+// add_decomposed_rel_pos :391-428, when the whole key set fits ONE score tile (seq_len <= 208):
+//   S[128 x 208] = [q(0:64) | q(64:80) | rel / scale] x [k(0:64) | k(64:80) | onehot(kh) onehot(kw)]^T
+//        seven tcgen05.mma (M 128, N 208, K 16) into TMEM: four over the first 64 head dims, one over the last 16, and
+//        ceil((k_h + k_w) / 16) over the bias columns — the bias is added BY the tensor core: rel_h[q, kh] + rel_w[q, kw]
+//        = [rel_h | rel_w] . [onehot(kh) | onehot(kw)], exact in fp32 (bf16 x 1.0). rel comes from the table terms the
+//        qkv GEMM wrote behind q | k | v (see vfm_attention_relpos_ex), pre-divided by the score scale that is applied to
+//        the whole sum afterwards.
+//   softmax: one query row per thread (TMEM lane), two passes over the 208 columns (max, then exp2 / sum / pack);
+//        P bf16 goes to its own TMEM columns.
+//   O[128 x 80] = P V: 13 k-steps x (N 64 over head dims 0:64, N 16 over 64:80), A = P from TMEM, B = V as MN-major
+//        SWIZZLE_128B tiles.
+// One CTA per (window, head, 128-query tile); operands arrive by TMA straight out of the packed qkv rows (the 64-wide
+// boxes of the 16-dim remainders also carry the neighbouring head's columns, which no k-step reads). 512 TMEM columns,
+// ~180 KB shared memory: one CTA per SM, no software pipeline inside the CTA — first tcgen05 version of this path; the
+// mma.sync kernel in sam_ops.cuh stays for the global blocks (1024 / 4096 keys).
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace vfm {
+
+constexpr int WIN_BLOCK_Q = 128;
+constexpr int WIN_KEYS = 208;                                  // 13 x 16: one score tile
+constexpr int WIN_D = 80;
+constexpr int WIN_THREADS = 192;                               // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2..5 softmax
+constexpr int WIN_Q_ATOM = WIN_BLOCK_Q * 128;                  // [128 rows x 64 bf16], 16 KB
+constexpr int WIN_K_ATOM = WIN_KEYS * 128;                     // [208 rows x 64 bf16], 26 KB
+constexpr int WIN_SMEM_BYTES = 3 * WIN_Q_ATOM + 5 * WIN_K_ATOM + 1024 + 128;
+constexpr uint32_t WIN_COL_S = 0, WIN_COL_P = 256, WIN_COL_O = 384;
+
+struct WinParams {
+  int seq_len, heads, k_h, k_w;
+  int ld, g_col0;               // row pitch of the qkv buffer (elements); first table-term column (-1: no bias)
+  float scale;
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* out;
+};
+
+// byte offset of element (r, c) in a K-major SWIZZLE_128B tile of [rows x 64 bf16] whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+}
+
+__global__ void __launch_bounds__(WIN_THREADS, 1)
+attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const WinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ0 = smem;
+  uint8_t* sQ1 = sQ0 + WIN_Q_ATOM;
+  uint8_t* sQB = sQ1 + WIN_Q_ATOM;          // bias terms of the query rows: [128][64], columns >= k_h + k_w are zero
+  uint8_t* sK0 = sQB + WIN_Q_ATOM;
+  uint8_t* sK1 = sK0 + WIN_K_ATOM;
+  uint8_t* sE = sK1 + WIN_K_ATOM;           // one-hot key tile: [208][64]
+  uint8_t* sV0 = sE + WIN_K_ATOM;
+  uint8_t* sV1 = sV0 + WIN_K_ATOM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV1 + WIN_K_ATOM);
+  uint64_t* load_full = bars;               // TMA -> MMA
+  uint64_t* s_full = bars + 1;              // MMA -> softmax
+  uint64_t* p_full = bars + 2;              // softmax -> MMA
+  uint64_t* o_full = bars + 3;              // MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, seq = blockIdx.z;
+  const int C = p.heads * WIN_D;
+  const int row0 = seq * p.seq_len;
+  const int q0 = qt * WIN_BLOCK_Q;
+  const int kk = p.g_col0 >= 0 ? p.k_h + p.k_w : 0;
+  const int bias_steps = (kk + 15) >> 4;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+    mbar_init(load_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // ---- bias operands, built by all threads while nothing else is running
+  if (kk > 0) {
+    for (int i = tid; i < (WIN_Q_ATOM + WIN_K_ATOM) / 16; i += WIN_THREADS) {
+      uint8_t* dst = i < WIN_Q_ATOM / 16 ? sQB + i * 16 : sE + (i - WIN_Q_ATOM / 16) * 16;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const float inv_scale = 1.f / p.scale;
+    const int Lh = 2 * p.k_h - 1, Lw = 2 * p.k_w - 1;
+    for (int i = tid; i < WIN_BLOCK_Q * kk; i += WIN_THREADS) {   // rel_h | rel_w of each live query row
+      const int r = i / kk, c = i - r * kk;
+      const int q = q0 + r;
+      if (q < p.seq_len) {
+        const int qh = q / p.k_w, qw = q - qh * p.k_w;
+        const int col = c < p.k_h ? p.g_col0 + head * Lh + (qh - c + p.k_h - 1)
+                                  : p.g_col0 + p.heads * Lh + head * Lw + (qw - (c - p.k_h) + p.k_w - 1);
+        const float v = __bfloat162float(p.qkv[static_cast<size_t>(row0 + q) * p.ld + col]) * inv_scale;
+        *reinterpret_cast<__nv_bfloat16*>(sQB + sw128_off(r, c)) = __float2bfloat16(v);
+      }
+    }
+    for (int key = tid; key < p.seq_len; key += WIN_THREADS) {    // 1.0 at column kh and at column k_h + kw
+      const int h = key / p.k_w, w = key - h * p.k_w;
+      *reinterpret_cast<__nv_bfloat16*>(sE + sw128_off(key, h)) = __float2bfloat16(1.f);
+      *reinterpret_cast<__nv_bfloat16*>(sE + sw128_off(key, p.k_h + w)) = __float2bfloat16(1.f);
+    }
+    fence_proxy_async_smem();   // the tensor core reads these tiles through the async proxy
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(load_full, 2 * WIN_Q_ATOM + 4 * WIN_K_ATOM);
+      const int qc = head * WIN_D, kc = C + head * WIN_D, vc = 2 * C + head * WIN_D;
+      for (int h = 0; h < 2; ++h) {   // 64-row boxes of the Q atoms, 104-row boxes of the K / V atoms
+        tma_load_2d(sQ0 + h * (WIN_Q_ATOM / 2), &tmap_q, load_full, qc, row0 + q0 + 64 * h);
+        tma_load_2d(sQ1 + h * (WIN_Q_ATOM / 2), &tmap_q, load_full, qc + 64, row0 + q0 + 64 * h);
+        tma_load_2d(sK0 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, kc, row0 + 104 * h);
+        tma_load_2d(sK1 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, kc + 64, row0 + 104 * h);
+        tma_load_2d(sV0 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, vc, row0 + 104 * h);
+        tma_load_2d(sV1 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, vc + 64, row0 + 104 * h);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = make_idesc_bf16(WIN_BLOCK_Q, WIN_KEYS, 0, 0);
+    constexpr uint32_t idesc_pv64 = make_idesc_bf16(WIN_BLOCK_Q, 64, 0, 1);   // B = V is MN-major
+    constexpr uint32_t idesc_pv16 = make_idesc_bf16(WIN_BLOCK_Q, 16, 0, 1);
+    const uint32_t tmem_s = tmem_base + WIN_COL_S, tmem_p = tmem_base + WIN_COL_P, tmem_o = tmem_base + WIN_COL_O;
+    mbar_wait(load_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint64_t dq0 = make_sw128_desc(smem_u32(sQ0)), dq1 = make_sw128_desc(smem_u32(sQ1)), dqb = make_sw128_desc(smem_u32(sQB));
+      const uint64_t dk0 = make_sw128_desc(smem_u32(sK0)), dk1 = make_sw128_desc(smem_u32(sK1)), de = make_sw128_desc(smem_u32(sE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_ss(tmem_s, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k != 0);   // head dims 0..63
+      umma_ss(tmem_s, dq1, dk1, idesc_s, true);                                                  // head dims 64..79
+      for (int k = 0; k < bias_steps; ++k) umma_ss(tmem_s, dqb + 2 * k, de + 2 * k, idesc_s, true);
+      tc_commit(s_full);
+    }
+    __syncwarp();
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+    if (elect_one_sync()) {
+      const uint64_t dv0 = make_sw128_desc(smem_u32(sV0)), dv1 = make_sw128_desc(smem_u32(sV1));
+#pragma unroll 1
+      for (int k = 0; k < WIN_KEYS / 16; ++k) {
+        // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
+        umma_ts(tmem_o, tmem_p + 8 * k, dv0 + 128 * k, idesc_pv64, k != 0);
+        umma_ts(tmem_o + 64, tmem_p + 8 * k, dv1 + 128 * k, idesc_pv16, k != 0);
+      }
+      tc_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax + output (warps 2..5): one query row per thread =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + WIN_COL_S;
+    const uint32_t tmem_p = tmem_base + lane_base + WIN_COL_P;
+    const uint32_t tmem_o = tmem_base + lane_base + WIN_COL_O;
+    const float sc = p.scale * 1.4426950408889634f;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    // pass 1: row max over the real keys
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < WIN_KEYS / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tmem_s + 16 * c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (16 * c + i < p.seq_len) m = fmaxf(m, __uint_as_float(r[i]));
+    }
+    const float ms = m * sc;
+    // pass 2: P = exp2(s * sc - ms) rounded to bf16; the row sum adds up the rounded values the PV MMA consumes
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < (WIN_KEYS + 31) / 32; ++c) {   // 32 keys = 16 packed columns per store; the last step holds 16 keys
+      uint32_t pk[16];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int key0 = 32 * c + 16 * hh;
+        if (key0 < WIN_KEYS) {
+          uint32_t r[16];
+          tmem_ld16(tmem_s + key0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int key = key0 + 2 * i;
+            const float e0 = key < p.seq_len ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), sc, -ms)) : 0.f;
+            const float e1 = key + 1 < p.seq_len ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), sc, -ms)) : 0.f;
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(e0, e1);
+            l += __low2float(bb) + __high2float(bb);
+            pk[8 * hh + i] = *reinterpret_cast<const uint32_t*>(&bb);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[8 * hh + i] = 0u;   // columns past the last k-step (inside the P region)
+        }
+      }
+      tmem_st16(tmem_p + 16 * c, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_full);
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int q = q0 + row;
+    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row0 + q) * C + head * WIN_D);
+#pragma unroll 1
+    for (int c = 0; c < WIN_D / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tmem_o + 16 * c, r);
+      tmem_ld_wait();
+      if (q < p.seq_len) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]) * inv;
+          dst[2 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace vfm

@@ -337,3 +337,13 @@ def attention_relpos_terms(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, scale
     _C.call("vfm_attention_relpos_ex", _bf16(qkv), qkv.shape[1], g_col0, None, _bf16(out), n_seq, seq_len, heads, head_dim,
             k_h, k_w, float(scale), _stream())
     return out
+
+
+def attention_window_tc(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, g_col0):
+    """tcgen05 window attention (seq_len <= 208, head_dim 80) with the rel-pos bias added by the tensor core; same
+    operands as attention_relpos_terms."""
+    assert qkv.shape[0] == n_seq * seq_len and qkv.stride(0) == qkv.shape[1]
+    out = torch.empty(n_seq * seq_len, heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_window_tc", _bf16(qkv), qkv.shape[1], g_col0, _bf16(out), n_seq, seq_len, heads, head_dim,
+            k_h, k_w, float(scale), _stream())
+    return out
