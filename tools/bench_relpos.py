@@ -27,4 +27,20 @@ def run(name, n_seq, k):
         flop = 4 * n_seq * H * S * S * d
         print(f"{name} bias={with_bias}: {ms*1e3:.1f} us, {flop/ms/1e9:.1f} TFLOP/s (algorithmic), qkv buffer {qkv.numel()*2/1e6:.0f} MB")
 run("windowed 162 x 196", 162, 14)
+def run_tc(n_seq, k):
+    S = k * k
+    ld = 3 * C + 2 * H * (2 * k - 1)
+    ld += (-ld) % 32
+    qkv = (torch.randn(n_seq * S, ld, device="cuda") * 0.7).to(torch.bfloat16)
+    for g0 in (3 * C, -1):
+        f = lambda: ops.attention_window_tc(qkv, n_seq, S, H, d, k, k, d ** -0.5, g0)
+        for _ in range(3): f()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_(); s.record(); f(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+        ms = sorted(ts)[5]
+        print(f"windowed tcgen05 bias={g0 >= 0}: {ms*1e3:.1f} us, {4 * n_seq * H * S * S * d/ms/1e9:.1f} TFLOP/s (algorithmic)")
+run_tc(162, 14)
 run("global 18 x 1024", 18, 32)

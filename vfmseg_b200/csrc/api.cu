@@ -98,6 +98,23 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
   return make_tmap_ex(m, ptr, rows, cols, ld, box_rows, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
 }
 
+// bf16 row-major [rows, cols], box = {box_cols, box_rows} with box_cols * 2 B == the swizzle span (32 / 64 / 128 B)
+int make_tmap_sw(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) % 16) != 0)
+    return fail(VFM_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte row pitch");
+  const CUtensorMapSwizzle sw = box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return VFM_OK;
+}
+
 // row-major [rows, cols] tensor of `esize`-byte elements; box rows x box_cols with box_cols * esize == 128 B.
 int make_tmap_ex(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                  uint32_t box_cols, CUtensorMapDataType dt, uint32_t esize) {
@@ -511,16 +528,18 @@ int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int 
   if (head_dim != WIN_D) return fail(VFM_ERR_INVALID, "attention_window_tc: head_dim must be %d (got %d)", WIN_D, head_dim);
   if (seq_len > WIN_KEYS) return fail(VFM_ERR_INVALID, "attention_window_tc: at most %d tokens per window (got %d)", WIN_KEYS, seq_len);
   if (ld < 3 * heads * head_dim || (ld % 8)) return fail(VFM_ERR_INVALID, "attention_window_tc: bad row pitch %d", ld);
-  if (g_col0 >= 0 && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len || k_h + k_w > 64 || g_col0 < 3 * heads * head_dim ||
+  if (g_col0 >= 0 && (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len || k_h > 16 || k_w > 16 || g_col0 < 3 * heads * head_dim ||
                       g_col0 + heads * (2 * k_h - 1 + 2 * k_w - 1) > ld))
     return fail(VFM_ERR_INVALID, "attention_window_tc: bad key grid %d x %d / table-term columns from %d (row pitch %d)", k_h, k_w, g_col0, ld);
   if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_window_tc: grid too large");
   if ((reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention_window_tc: out must be 16-byte aligned");
   const uint64_t rows = static_cast<uint64_t>(n_seq) * seq_len;
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tq16, tkv16;
   int rc;
   if ((rc = make_tmap(&tq, qkv, rows, ld, ld, 64))) return rc;
   if ((rc = make_tmap(&tkv, qkv, rows, ld, ld, WIN_KEYS / 2))) return rc;
+  if ((rc = make_tmap_sw(&tq16, qkv, rows, ld, ld, 64, 16))) return rc;
+  if ((rc = make_tmap_sw(&tkv16, qkv, rows, ld, ld, WIN_KEYS / 2, 16))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
     VFM_CUDA(cudaFuncSetAttribute(attention_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIN_SMEM_BYTES));
@@ -532,7 +551,7 @@ int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int 
   const dim3 grid((seq_len + WIN_BLOCK_Q - 1) / WIN_BLOCK_Q, heads, n_seq);
   {
     LaunchScope scope("attention_window_tc", S(stream));
-    attention_win_kernel<<<grid, WIN_THREADS, WIN_SMEM_BYTES, S(stream)>>>(tq, tkv, p);
+    attention_win_kernel<<<grid, WIN_THREADS, WIN_SMEM_BYTES, S(stream)>>>(tq, tkv, tq16, tkv16, p);
   }
   VFM_LAUNCH_CHECK("attention_window_tc");
   return VFM_OK;

@@ -12,10 +12,13 @@
 //        P bf16 goes to its own TMEM columns.
 //   O[128 x 80] = P V: 13 k-steps x (N 64 over head dims 0:64, N 16 over 64:80), A = P from TMEM, B = V as MN-major
 //        SWIZZLE_128B tiles.
-// One CTA per (window, head, 128-query tile); operands arrive by TMA straight out of the packed qkv rows (the 64-wide
-// boxes of the 16-dim remainders also carry the neighbouring head's columns, which no k-step reads). 512 TMEM columns,
-// ~180 KB shared memory: one CTA per SM, no software pipeline inside the CTA — first tcgen05 version of this path; the
-// mma.sync kernel in sam_ops.cuh stays for the global blocks (1024 / 4096 keys).
+// One CTA per (window, head, 128-query tile), two CTAs per SM; operands arrive by TMA straight out of the packed qkv
+// rows. Shared memory holds each operand at its real width: the 64-dim parts as SWIZZLE_128B tiles, the 16-dim
+// remainders as SWIZZLE_32B tiles (one k-step), the 32 bias columns as SWIZZLE_64B tiles — 106 KB per CTA. TMEM: the
+// probabilities overwrite the scores in place (pass 2 has consumed a 32-column chunk before it writes 16 packed columns
+// at half the offset) and O lands on score columns 112..191, so one CTA needs 208 of its 256 columns.
+// No software pipeline inside the CTA: the second CTA of the SM fills the gaps. The mma.sync kernel in sam_ops.cuh stays
+// for the global blocks (1024 / 4096 keys).
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -25,10 +28,12 @@ constexpr int WIN_BLOCK_Q = 128;
 constexpr int WIN_KEYS = 208;                                  // 13 x 16: one score tile
 constexpr int WIN_D = 80;
 constexpr int WIN_THREADS = 192;                               // warp 0 TMA, warp 1 MMA + TMEM allocator, warps 2..5 softmax
-constexpr int WIN_Q_ATOM = WIN_BLOCK_Q * 128;                  // [128 rows x 64 bf16], 16 KB
-constexpr int WIN_K_ATOM = WIN_KEYS * 128;                     // [208 rows x 64 bf16], 26 KB
-constexpr int WIN_SMEM_BYTES = 3 * WIN_Q_ATOM + 5 * WIN_K_ATOM + 1024 + 128;
-constexpr uint32_t WIN_COL_S = 0, WIN_COL_P = 256, WIN_COL_O = 384;
+constexpr int WIN_Q64 = WIN_BLOCK_Q * 128, WIN_K64 = WIN_KEYS * 128;   // [rows x 64 bf16] SWIZZLE_128B: 16 KB / 26 KB
+constexpr int WIN_Q32 = WIN_BLOCK_Q * 64, WIN_K32 = WIN_KEYS * 64;     // [rows x 32 bf16] SWIZZLE_64B (bias columns)
+constexpr int WIN_Q16 = WIN_BLOCK_Q * 32, WIN_K16 = WIN_KEYS * 32;     // [rows x 16 bf16] SWIZZLE_32B (head dims 64..79)
+constexpr int WIN_SMEM_BYTES = WIN_Q64 + 2 * WIN_K64 + WIN_Q32 + WIN_K32 + WIN_Q16 + 2 * WIN_K16 + 1024 + 128;
+constexpr uint32_t WIN_TMEM_COLS = 256;
+constexpr uint32_t WIN_COL_S = 0, WIN_COL_P = 0, WIN_COL_O = 112;      // P in place over S; O over consumed S columns
 
 struct WinParams {
   int seq_len, heads, k_h, k_w;
@@ -38,24 +43,33 @@ struct WinParams {
   __nv_bfloat16* out;
 };
 
-// byte offset of element (r, c) in a K-major SWIZZLE_128B tile of [rows x 64 bf16] whose base is 1024-byte aligned
-__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
-  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ (r & 7)) & 7) << 4) + (c & 7) * 2);
+// Shared-memory matrix descriptors for the narrower swizzle modes (cf. make_sw128_desc): rows of 64 B / 32 B, 8-row groups
+// 512 B / 256 B apart; layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B. K-major: advance K by 16 -> +32 B; MN-major (rows =
+// K): advance K by 16 rows.
+__device__ __forceinline__ uint64_t make_sw_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
 }
 
-__global__ void __launch_bounds__(WIN_THREADS, 1)
-attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const WinParams p) {
+__global__ void __launch_bounds__(WIN_THREADS, 2)
+attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                     const __grid_constant__ CUtensorMap tmap_q16, const __grid_constant__ CUtensorMap tmap_kv16, const WinParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ0 = smem;
-  uint8_t* sQ1 = sQ0 + WIN_Q_ATOM;
-  uint8_t* sQB = sQ1 + WIN_Q_ATOM;          // bias terms of the query rows: [128][64], columns >= k_h + k_w are zero
-  uint8_t* sK0 = sQB + WIN_Q_ATOM;
-  uint8_t* sK1 = sK0 + WIN_K_ATOM;
-  uint8_t* sE = sK1 + WIN_K_ATOM;           // one-hot key tile: [208][64]
-  uint8_t* sV0 = sE + WIN_K_ATOM;
-  uint8_t* sV1 = sV0 + WIN_K_ATOM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV1 + WIN_K_ATOM);
+  uint8_t* sQ0 = smem;                      // SWIZZLE_128B tiles first (1024-byte aligned)
+  uint8_t* sK0 = sQ0 + WIN_Q64;
+  uint8_t* sV0 = sK0 + WIN_K64;
+  uint8_t* sQB = sV0 + WIN_K64;             // SWIZZLE_64B: bias terms of the query rows [128][32] (rel_h | 0 | rel_w | 0)
+  uint8_t* sE = sQB + WIN_Q32;              //              one-hot key tile [208][32]
+  uint8_t* sQ1 = sE + WIN_K32;              // SWIZZLE_32B: head dims 64..79
+  uint8_t* sK1 = sQ1 + WIN_Q16;
+  uint8_t* sV1 = sK1 + WIN_K16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV1 + WIN_K16);
   uint64_t* load_full = bars;               // TMA -> MMA
   uint64_t* s_full = bars + 1;              // MMA -> softmax
   uint64_t* p_full = bars + 2;              // softmax -> MMA
@@ -68,42 +82,63 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int row0 = seq * p.seq_len;
   const int q0 = qt * WIN_BLOCK_Q;
   const int kk = p.g_col0 >= 0 ? p.k_h + p.k_w : 0;
-  const int bias_steps = (kk + 15) >> 4;
+  const int bias_steps = kk > 0 ? 2 : 0;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_kv);
+    tma_prefetch_desc(&tmap_q16);
+    tma_prefetch_desc(&tmap_kv16);
     mbar_init(load_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // ---- bias operands, built by all threads while nothing else is running
+  if (warp == 1) tmem_alloc<WIN_TMEM_COLS>(tmem_slot);
+  // ---- bias operands, built by all threads while nothing else is running. Fixed column layout (k_h, k_w <= 16):
+  // k-step 0 = rel_h | zeros, k-step 1 = rel_w | zeros; the one-hot tile has its ones at columns kh and 16 + kw.
   if (kk > 0) {
-    for (int i = tid; i < (WIN_Q_ATOM + WIN_K_ATOM) / 16; i += WIN_THREADS) {
-      uint8_t* dst = i < WIN_Q_ATOM / 16 ? sQB + i * 16 : sE + (i - WIN_Q_ATOM / 16) * 16;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    __syncthreads();
     const float inv_scale = 1.f / p.scale;
     const int Lh = 2 * p.k_h - 1, Lw = 2 * p.k_w - 1;
-    for (int i = tid; i < WIN_BLOCK_Q * kk; i += WIN_THREADS) {   // rel_h | rel_w of each live query row
-      const int r = i / kk, c = i - r * kk;
+    // one task = one (query row, axis): 16 contiguous table terms read backwards (all loads in flight together), scaled,
+    // written as two 16-byte chunks of the swizzled row
+    for (int t = tid; t < 2 * WIN_BLOCK_Q; t += WIN_THREADS) {
+      const int r = t >> 1, axis = t & 1;
       const int q = q0 + r;
+      const int kn = axis ? p.k_w : p.k_h;
+      __nv_bfloat16 v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = __float2bfloat16(0.f);
       if (q < p.seq_len) {
         const int qh = q / p.k_w, qw = q - qh * p.k_w;
-        const int col = c < p.k_h ? p.g_col0 + head * Lh + (qh - c + p.k_h - 1)
-                                  : p.g_col0 + p.heads * Lh + head * Lw + (qw - (c - p.k_h) + p.k_w - 1);
-        const float v = __bfloat162float(p.qkv[static_cast<size_t>(row0 + q) * p.ld + col]) * inv_scale;
-        *reinterpret_cast<__nv_bfloat16*>(sQB + sw128_off(r, c)) = __float2bfloat16(v);
+        const __nv_bfloat16* gp = p.qkv + static_cast<size_t>(row0 + q) * p.ld + p.g_col0 +
+                                  (axis ? p.heads * Lh + head * Lw + qw + p.k_w - 1 : head * Lh + qh + p.k_h - 1);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < kn) v[c] = gp[-c];
       }
+      uint32_t w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        w[c] = pack_bf16x2(__bfloat162float(v[2 * c]) * inv_scale, __bfloat162float(v[2 * c + 1]) * inv_scale);
+      uint8_t* rowp = sQB + r * 64;        // SWIZZLE_64B: 16-byte chunk index ^ ((row >> 1) & 3)
+      *reinterpret_cast<uint4*>(rowp + (((2 * axis) ^ ((r >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(rowp + (((2 * axis + 1) ^ ((r >> 1) & 3)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
     }
-    for (int key = tid; key < p.seq_len; key += WIN_THREADS) {    // 1.0 at column kh and at column k_h + kw
-      const int h = key / p.k_w, w = key - h * p.k_w;
-      *reinterpret_cast<__nv_bfloat16*>(sE + sw128_off(key, h)) = __float2bfloat16(1.f);
-      *reinterpret_cast<__nv_bfloat16*>(sE + sw128_off(key, p.k_h + w)) = __float2bfloat16(1.f);
+    for (int key = tid; key < WIN_KEYS; key += WIN_THREADS) {   // one-hot rows: columns 0..31 (four chunks), zeros elsewhere
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) w[c] = 0u;
+      if (key < p.seq_len) {
+        const int h = key / p.k_w, ww = key - h * p.k_w;
+        w[h >> 1] |= 0x3f80u << ((h & 1) * 16);                 // bf16 1.0
+        w[8 + (ww >> 1)] |= 0x3f80u << ((ww & 1) * 16);
+      }
+      uint8_t* rowp = sE + key * 64;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(rowp + ((ch ^ ((key >> 1) & 3)) << 4)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
     }
     fence_proxy_async_smem();   // the tensor core reads these tiles through the async proxy
   }
@@ -115,15 +150,15 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(load_full, 2 * WIN_Q_ATOM + 4 * WIN_K_ATOM);
+      mbar_arrive_expect_tx(load_full, WIN_Q64 + 2 * WIN_K64 + WIN_Q16 + 2 * WIN_K16);
       const int qc = head * WIN_D, kc = C + head * WIN_D, vc = 2 * C + head * WIN_D;
-      for (int h = 0; h < 2; ++h) {   // 64-row boxes of the Q atoms, 104-row boxes of the K / V atoms
-        tma_load_2d(sQ0 + h * (WIN_Q_ATOM / 2), &tmap_q, load_full, qc, row0 + q0 + 64 * h);
-        tma_load_2d(sQ1 + h * (WIN_Q_ATOM / 2), &tmap_q, load_full, qc + 64, row0 + q0 + 64 * h);
-        tma_load_2d(sK0 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, kc, row0 + 104 * h);
-        tma_load_2d(sK1 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, kc + 64, row0 + 104 * h);
-        tma_load_2d(sV0 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, vc, row0 + 104 * h);
-        tma_load_2d(sV1 + h * (WIN_K_ATOM / 2), &tmap_kv, load_full, vc + 64, row0 + 104 * h);
+      for (int h = 0; h < 2; ++h) {   // 64-row boxes of the Q tiles, 104-row boxes of the K / V tiles
+        tma_load_2d(sQ0 + h * (WIN_Q64 / 2), &tmap_q, load_full, qc, row0 + q0 + 64 * h);
+        tma_load_2d(sQ1 + h * (WIN_Q16 / 2), &tmap_q16, load_full, qc + 64, row0 + q0 + 64 * h);
+        tma_load_2d(sK0 + h * (WIN_K64 / 2), &tmap_kv, load_full, kc, row0 + 104 * h);
+        tma_load_2d(sK1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, kc + 64, row0 + 104 * h);
+        tma_load_2d(sV0 + h * (WIN_K64 / 2), &tmap_kv, load_full, vc, row0 + 104 * h);
+        tma_load_2d(sV1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, vc + 64, row0 + 104 * h);
       }
     }
     __syncwarp();
@@ -136,8 +171,9 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_wait(load_full, 0);
     tc_fence_after();
     if (elect_one_sync()) {
-      const uint64_t dq0 = make_sw128_desc(smem_u32(sQ0)), dq1 = make_sw128_desc(smem_u32(sQ1)), dqb = make_sw128_desc(smem_u32(sQB));
-      const uint64_t dk0 = make_sw128_desc(smem_u32(sK0)), dk1 = make_sw128_desc(smem_u32(sK1)), de = make_sw128_desc(smem_u32(sE));
+      const uint64_t dq0 = make_sw128_desc(smem_u32(sQ0)), dk0 = make_sw128_desc(smem_u32(sK0));
+      const uint64_t dq1 = make_sw_desc(smem_u32(sQ1), 256, 6), dk1 = make_sw_desc(smem_u32(sK1), 256, 6);
+      const uint64_t dqb = make_sw_desc(smem_u32(sQB), 512, 4), de = make_sw_desc(smem_u32(sE), 512, 4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss(tmem_s, dq0 + 2 * k, dk0 + 2 * k, idesc_s, k != 0);   // head dims 0..63
       umma_ss(tmem_s, dq1, dk1, idesc_s, true);                                                  // head dims 64..79
@@ -148,12 +184,12 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_wait(p_full, 0);
     tc_fence_after();
     if (elect_one_sync()) {
-      const uint64_t dv0 = make_sw128_desc(smem_u32(sV0)), dv1 = make_sw128_desc(smem_u32(sV1));
+      const uint64_t dv0 = make_sw128_desc(smem_u32(sV0)), dv1 = make_sw_desc(smem_u32(sV1), 256, 6);
 #pragma unroll 1
       for (int k = 0; k < WIN_KEYS / 16; ++k) {
         // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
         umma_ts(tmem_o, tmem_p + 8 * k, dv0 + 128 * k, idesc_pv64, k != 0);
-        umma_ts(tmem_o + 64, tmem_p + 8 * k, dv1 + 128 * k, idesc_pv16, k != 0);
+        umma_ts(tmem_o + 64, tmem_p + 8 * k, dv1 + 32 * k, idesc_pv16, k != 0);   // 16 key rows of 32 B
       }
       tc_commit(o_full);
     }
@@ -239,7 +275,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<WIN_TMEM_COLS>(tmem_base);
   }
 }
 

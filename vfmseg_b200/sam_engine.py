@@ -174,7 +174,11 @@ class PackedSam:
             if ws:
                 part, unpart, n_win = self._window_maps(n, gh, gw, ws)
                 qkv = ops.gemm_bias_bf16(ops.rows_gather(h, part), b["qkv_w"], b["qkv_b"])          # q | k | v | G_h | G_w
-                att = ops.rows_gather(ops.attention_relpos_terms(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0), unpart)
+                if d == 80 and ws * ws <= 208 and ws <= 16:      # whole window in one tcgen05 score tile
+                    aw = ops.attention_window_tc(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0)
+                else:
+                    aw = ops.attention_relpos_terms(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0)
+                att = ops.rows_gather(aw, unpart)
             else:
                 qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
                 att = ops.attention_relpos_terms(qkv, n, P, H, d, gh, gw, scale, g0)
