@@ -85,15 +85,22 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int bias_steps = kk > 0 ? 2 : 0;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_kv);
-    tma_prefetch_desc(&tmap_q16);
-    tma_prefetch_desc(&tmap_kv16);
     mbar_init(load_full, 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    // the loads go out at once: their latency runs under the bias-operand build below
+    mbar_arrive_expect_tx(load_full, WIN_Q64 + 2 * WIN_K64 + WIN_Q16 + 2 * WIN_K16);
+    const int qc = head * WIN_D, kc = C + head * WIN_D, vc = 2 * C + head * WIN_D;
+    for (int h = 0; h < 2; ++h) {   // 64-row boxes of the Q tiles, 104-row boxes of the K / V tiles
+      tma_load_2d(sQ0 + h * (WIN_Q64 / 2), &tmap_q, load_full, qc, row0 + q0 + 64 * h);
+      tma_load_2d(sQ1 + h * (WIN_Q16 / 2), &tmap_q16, load_full, qc + 64, row0 + q0 + 64 * h);
+      tma_load_2d(sK0 + h * (WIN_K64 / 2), &tmap_kv, load_full, kc, row0 + 104 * h);
+      tma_load_2d(sK1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, kc + 64, row0 + 104 * h);
+      tma_load_2d(sV0 + h * (WIN_K64 / 2), &tmap_kv, load_full, vc, row0 + 104 * h);
+      tma_load_2d(sV1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, vc + 64, row0 + 104 * h);
+    }
   }
   if (warp == 1) tmem_alloc<WIN_TMEM_COLS>(tmem_slot);
   // ---- bias operands, built by all threads while nothing else is running. Fixed column layout (k_h, k_w <= 16):
@@ -148,20 +155,7 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(load_full, WIN_Q64 + 2 * WIN_K64 + WIN_Q16 + 2 * WIN_K16);
-      const int qc = head * WIN_D, kc = C + head * WIN_D, vc = 2 * C + head * WIN_D;
-      for (int h = 0; h < 2; ++h) {   // 64-row boxes of the Q tiles, 104-row boxes of the K / V tiles
-        tma_load_2d(sQ0 + h * (WIN_Q64 / 2), &tmap_q, load_full, qc, row0 + q0 + 64 * h);
-        tma_load_2d(sQ1 + h * (WIN_Q16 / 2), &tmap_q16, load_full, qc + 64, row0 + q0 + 64 * h);
-        tma_load_2d(sK0 + h * (WIN_K64 / 2), &tmap_kv, load_full, kc, row0 + 104 * h);
-        tma_load_2d(sK1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, kc + 64, row0 + 104 * h);
-        tma_load_2d(sV0 + h * (WIN_K64 / 2), &tmap_kv, load_full, vc, row0 + 104 * h);
-        tma_load_2d(sV1 + h * (WIN_K16 / 2), &tmap_kv16, load_full, vc + 64, row0 + 104 * h);
-      }
-    }
-    __syncwarp();
+    // (loads were issued in the prologue)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = make_idesc_bf16(WIN_BLOCK_Q, WIN_KEYS, 0, 0);
@@ -208,13 +202,21 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // pass 1: row max over the real keys
     float m = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < WIN_KEYS / 16; ++c) {
+    for (int c = 0; c < WIN_KEYS / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_s + 32 * c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (32 * c + i < p.seq_len) m = fmaxf(m, __uint_as_float(r[i]));
+    }
+    {
       uint32_t r[16];
-      tmem_ld16(tmem_s + 16 * c, r);
+      tmem_ld16(tmem_s + (WIN_KEYS / 32) * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (16 * c + i < p.seq_len) m = fmaxf(m, __uint_as_float(r[i]));
+        if ((WIN_KEYS / 32) * 32 + i < p.seq_len) m = fmaxf(m, __uint_as_float(r[i]));
     }
     const float ms = m * sc;
     // pass 2: P = exp2(s * sc - ms) rounded to bf16; the row sum adds up the rounded values the PV MMA consumes
@@ -222,13 +224,15 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll 1
     for (int c = 0; c < (WIN_KEYS + 31) / 32; ++c) {   // 32 keys = 16 packed columns per store; the last step holds 16 keys
       uint32_t pk[16];
+      uint32_t r2[2][16];
+      tmem_ld16(tmem_s + 32 * c, r2[0]);
+      if (32 * c + 16 < WIN_KEYS) tmem_ld16(tmem_s + 32 * c + 16, r2[1]);
+      tmem_ld_wait();
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int key0 = 32 * c + 16 * hh;
         if (key0 < WIN_KEYS) {
-          uint32_t r[16];
-          tmem_ld16(tmem_s + key0, r);
-          tmem_ld_wait();
+          const uint32_t (&r)[16] = r2[hh];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int key = key0 + 2 * i;
