@@ -269,6 +269,12 @@ int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq
  * vfm_attention_relpos_ex with rel == NULL (g_col0 < 0: no bias). sam_vit.py:272-287,391-428. */
 int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int n_seq, int seq_len, int heads, int head_dim,
                             int k_h, int k_w, float scale, void* stream);
+/* The same attention over a whole token grid (key-tile loop, online softmax) on tcgen05, head_dim 80, k_h and k_w rounded up
+ * to 16 summing to at most 128 bias columns (grids up to 64 x 64). onehot: bf16 [onehot_rows >= seq_len, 64 * ceil((bh + bw) / 64)],
+ * row k = 1.0 at column kh(k) and at column bh + kw(k) (bh = k_h rounded up to 16) — a constant of the grid the caller builds
+ * once. sam_vit.py:272-287,391-428. */
+int vfm_attention_global_tc(const void* qkv, int ld, int g_col0, const void* onehot, int onehot_rows, void* out, int n_seq,
+                            int seq_len, int heads, int head_dim, int k_h, int k_w, float scale, void* stream);
 /* Same with an explicit row pitch ld (elements) of the qkv buffer and, when g_col0 >= 0 (then rel must be NULL), the bias
  * taken from table terms stored in the qkv rows: G_h[head][r] = q . T_h[r] (r in [0, 2 k_h - 1)) at column
  * g_col0 + head * (2 k_h - 1) + r, all heads' G_w behind them; rel_h[q, kh] = G_h[qh - kh + k_h - 1] (get_rel_pos,

@@ -145,3 +145,43 @@ def test_attention_window_tc(n_seq, k, heads, bias):
     ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
     err = (got - ref).abs()
     assert (err <= 2e-2 + 2e-2 * ref.abs()).all(), err.max()
+
+
+def _relpos_ref(qkv, n_seq, k_h, k_w, heads, d, scale):
+    """torch fp32 attention on packed rows q | k | v | G_h | G_w with rel_h[q, kh] = G_h[qh - kh + k_h - 1] (and likewise w)."""
+    S, Lh, Lw = k_h * k_w, 2 * k_h - 1, 2 * k_w - 1
+    C = heads * d
+    x = qkv.float().cpu()
+    q, kk_, v = x[:, :3 * C].view(n_seq, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    att = (q * scale) @ kk_.transpose(-1, -2)
+    Gh = x[:, 3 * C:3 * C + heads * Lh].view(n_seq, k_h, k_w, heads, Lh)
+    Gw = x[:, 3 * C + heads * Lh:3 * C + heads * (Lh + Lw)].view(n_seq, k_h, k_w, heads, Lw)
+    ih = torch.arange(k_h)[:, None] - torch.arange(k_h)[None, :] + k_h - 1
+    iw = torch.arange(k_w)[:, None] - torch.arange(k_w)[None, :] + k_w - 1
+    rel_h = torch.gather(Gh, 4, ih[None, :, None, None, :].expand(n_seq, k_h, k_w, heads, k_h))
+    rel_w = torch.gather(Gw, 4, iw[None, None, :, None, :].expand(n_seq, k_h, k_w, heads, k_w))
+    b = rel_h[..., :, None] + rel_w[..., None, :]
+    att = att + b.permute(0, 3, 1, 2, 4, 5).reshape(n_seq, heads, S, S)
+    return (att.softmax(-1) @ v).transpose(1, 2).reshape(n_seq * S, C)
+
+
+@pytest.mark.parametrize("n_seq,k_h,k_w,heads", [(2, 32, 32, 2), (1, 64, 64, 1), (3, 20, 20, 2), (2, 16, 16, 3), (1, 24, 40, 1)])
+def test_attention_global_tc(n_seq, k_h, k_w, heads):
+    """tcgen05 grid attention (key-tile loop, online softmax, bias through one-hot key columns by TMA) against torch fp32:
+    full tiles, a ragged last tile (400, 960 keys), one and two bias atoms, non-square grid."""
+    from vfmseg_b200 import ops
+    d, S = 80, k_h * k_w
+    C = heads * d
+    ld = 3 * C + heads * (2 * k_h - 1 + 2 * k_w - 1)
+    ld += (-ld) % 32
+    qkv = _rand(n_seq * S, ld, scale=0.7, seed=8, dtype=torch.bfloat16)
+    scale = d ** -0.5
+    e = ops.relpos_onehot(k_h, k_w, "cuda")
+    got = ops.attention_global_tc(qkv, e, n_seq, S, heads, d, k_h, k_w, scale, 3 * C).float().cpu()
+    ref = _relpos_ref(qkv, n_seq, k_h, k_w, heads, d, scale)
+    err = (got - ref).abs()
+    assert (err <= 2e-2 + 2e-2 * ref.abs()).all(), err.max()
+    # and against the mma.sync kernel on the same rows
+    if k_h % 2 == 0 and k_w % 2 == 0:
+        other = ops.attention_relpos_terms(qkv, n_seq, S, heads, d, k_h, k_w, scale, 3 * C).float().cpu()
+        assert ((got - other).abs() <= 2e-2 + 2e-2 * other.abs()).all()

@@ -44,3 +44,22 @@ def run_tc(n_seq, k):
         print(f"windowed tcgen05 bias={g0 >= 0}: {ms*1e3:.1f} us, {4 * n_seq * H * S * S * d/ms/1e9:.1f} TFLOP/s (algorithmic)")
 run_tc(162, 14)
 run("global 18 x 1024", 18, 32)
+
+def run_glob(n_seq, k):
+    S = k * k
+    ld = 3 * C + 2 * H * (2 * k - 1)
+    ld += (-ld) % 32
+    qkv = (torch.randn(n_seq * S, ld, device="cuda") * 0.7).to(torch.bfloat16)
+    e = ops.relpos_onehot(k, k, "cuda")
+    f = lambda: ops.attention_global_tc(qkv, e, n_seq, S, H, d, k, k, d ** -0.5, 3 * C)
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        s, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_(); s.record(); f(); e2.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e2))
+    ms = sorted(ts)[5]
+    print(f"global tcgen05 {n_seq} x {S}: {ms*1e3:.1f} us, {4 * n_seq * H * S * S * d/ms/1e9:.1f} TFLOP/s (algorithmic)")
+run_glob(18, 32)
+run_glob(6, 64)
+run("global 6 x 4096", 6, 64)

@@ -15,6 +15,7 @@
 #include "attention_sm100.cuh"
 #include "sam_ops.cuh"
 #include "attention_win_sm100.cuh"
+#include "attention_glob_sm100.cuh"
 #include "elementwise.cuh"
 #include "eva_ops.cuh"
 #include "gemm_sm100.cuh"
@@ -555,6 +556,51 @@ int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int 
   }
   VFM_LAUNCH_CHECK("attention_window_tc");
   return VFM_OK;
+}
+
+extern "C++" {
+template <int NA>
+static int launch_attention_glob(const CUtensorMap& t64, const CUtensorMap& t16, const CUtensorMap& te, const GlobParams& p,
+                                 int n_seq, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    VFM_CUDA(cudaFuncSetAttribute(attention_glob_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, glb_smem_bytes<NA>()));
+    attr_done = true;
+  }
+  const dim3 grid((p.seq_len + GLB_BLOCK_Q - 1) / GLB_BLOCK_Q, p.heads, n_seq);
+  {
+    LaunchScope scope("attention_global_tc", st);
+    attention_glob_kernel<NA><<<grid, GLB_THREADS, glb_smem_bytes<NA>(), st>>>(t64, t16, te, p);
+  }
+  VFM_LAUNCH_CHECK("attention_global_tc");
+  return VFM_OK;
+}
+}  // extern "C++"
+
+int vfm_attention_global_tc(const void* qkv, int ld, int g_col0, const void* onehot, int onehot_rows, void* out, int n_seq,
+                            int seq_len, int heads, int head_dim, int k_h, int k_w, float scale, void* stream) {
+  if (!qkv || !out || !onehot || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_global_tc: bad args");
+  if (head_dim != GLB_D) return fail(VFM_ERR_INVALID, "attention_global_tc: head_dim must be %d (got %d)", GLB_D, head_dim);
+  if (ld < 3 * heads * head_dim || (ld % 8)) return fail(VFM_ERR_INVALID, "attention_global_tc: bad row pitch %d", ld);
+  const int bh = (k_h + 15) & ~15, bw = (k_w + 15) & ~15;
+  const int na = (bh + bw + 63) / 64;
+  if (k_h <= 0 || k_w <= 0 || k_h * k_w != seq_len || na > 2 || g_col0 < 3 * heads * head_dim ||
+      g_col0 + heads * (2 * k_h - 1 + 2 * k_w - 1) > ld)
+    return fail(VFM_ERR_INVALID, "attention_global_tc: bad key grid %d x %d (at most 128 bias columns) / table-term columns from %d (row pitch %d)",
+                k_h, k_w, g_col0, ld);
+  if (onehot_rows < seq_len) return fail(VFM_ERR_INVALID, "attention_global_tc: one-hot matrix has %d rows, needs %d", onehot_rows, seq_len);
+  if (n_seq > 65535 || heads > 65535) return fail(VFM_ERR_INVALID, "attention_global_tc: grid too large");
+  if ((reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention_global_tc: out must be 16-byte aligned");
+  const uint64_t rows = static_cast<uint64_t>(n_seq) * seq_len;
+  CUtensorMap t64, t16, te;
+  int rc;
+  if ((rc = make_tmap(&t64, qkv, rows, ld, ld, 64))) return rc;
+  if ((rc = make_tmap_sw(&t16, qkv, rows, ld, ld, 64, 16))) return rc;
+  if ((rc = make_tmap(&te, onehot, onehot_rows, 64 * na, 64 * na, 64))) return rc;
+  GlobParams p{};
+  p.seq_len = seq_len; p.heads = heads; p.k_h = k_h; p.k_w = k_w; p.bh = bh; p.bw = bw; p.ld = ld; p.g_col0 = g_col0; p.scale = scale;
+  p.qkv = BF(qkv); p.out = const_cast<__nv_bfloat16*>(BF(out));
+  return na == 1 ? launch_attention_glob<1>(t64, t16, te, p, n_seq, S(stream)) : launch_attention_glob<2>(t64, t16, te, p, n_seq, S(stream));
 }
 
 int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq, int seq_len, int heads, int head_dim,

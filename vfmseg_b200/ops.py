@@ -347,3 +347,24 @@ def attention_window_tc(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, g
     _C.call("vfm_attention_window_tc", _bf16(qkv), qkv.shape[1], g_col0, _bf16(out), n_seq, seq_len, heads, head_dim,
             k_h, k_w, float(scale), _stream())
     return out
+
+
+def relpos_onehot(k_h, k_w, device):
+    """The one-hot key matrix of vfm_attention_global_tc for a k_h x k_w grid: bf16 [k_h*k_w rounded up to 64, 64*NA]."""
+    bh, bw = (k_h + 15) // 16 * 16, (k_w + 15) // 16 * 16
+    cols = (bh + bw + 63) // 64 * 64
+    n = k_h * k_w
+    e = torch.zeros((n + 63) // 64 * 64, cols, dtype=torch.bfloat16)
+    idx = torch.arange(n)
+    e[idx, idx // k_w] = 1
+    e[idx, bh + idx % k_w] = 1
+    return e.to(device)
+
+
+def attention_global_tc(qkv, onehot, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, g_col0):
+    """tcgen05 attention over a whole token grid with the rel-pos bias added by the tensor core (head_dim 80)."""
+    assert qkv.shape[0] == n_seq * seq_len and qkv.stride(0) == qkv.shape[1] and onehot.is_contiguous()
+    out = torch.empty(n_seq * seq_len, heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_global_tc", _bf16(qkv), qkv.shape[1], g_col0, _bf16(onehot), onehot.shape[0], _bf16(out), n_seq, seq_len,
+            heads, head_dim, k_h, k_w, float(scale), _stream())
+    return out
