@@ -181,7 +181,14 @@ class PackedSam:
                 att = ops.rows_gather(aw, unpart)
             else:
                 qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
-                att = ops.attention_relpos_terms(qkv, n, P, H, d, gh, gw, scale, g0)
+                bias_cols = (gh + 15) // 16 * 16 + (gw + 15) // 16 * 16
+                if d == 80 and g0 >= 0 and bias_cols <= 128:           # key-tile loop on tcgen05
+                    key = ("onehot", gh, gw)
+                    if key not in self._maps:
+                        self._maps[key] = ops.relpos_onehot(gh, gw, self.device)
+                    att = ops.attention_global_tc(qkv, self._maps[key], n, P, H, d, gh, gw, scale, g0)
+                else:
+                    att = ops.attention_relpos_terms(qkv, n, P, H, d, gh, gw, scale, g0)
             ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
             h = ops.layernorm(x, *b["n2"], s.ln_eps)
             ops.gemm_bias_ls_residual_(x, ops.gemm_bias_gelu_bf16(h, b["lin1_w"], b["lin1_b"]), b["lin2_w"], b["lin2_b"], self.ones)
