@@ -128,7 +128,9 @@ def _attn_ref(qkv, n_seq, S, heads):
     (1, 2049, 2, 0), (1, 2049, 2, 1), (2, 17, 2, 0), (2, 17, 2, 2), (2, 2, 1, 2), (1, 385, 3, 0), (2, 641, 2, 1),
     # more units than persistent CTAs (2 x 148): every CTA streams several units back to back — odd and even key-tile
     # counts per unit (buffer / phase parity across unit boundaries), one- and two-tile units, extra-token mode
-    (20, 257, 12, 0), (20, 257, 12, 2), (40, 65, 8, 1), (600, 17, 1, 0), (300, 129, 2, 2), (7, 1025, 16, 0)])
+    (20, 257, 12, 0), (20, 257, 12, 2), (40, 65, 8, 1), (600, 17, 1, 0), (300, 129, 2, 2), (7, 1025, 16, 0),
+    # mode 3: the serial four-CTAs-per-SM kernel
+    (1, 128, 1, 3), (3, 1025, 4, 3), (2, 197, 2, 3), (1, 2049, 2, 3), (2, 17, 2, 3), (20, 257, 12, 3)])
 def test_attention(ops, n_seq, S, heads, mode):
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=21, dtype=torch.bfloat16)
     out = ops.attention_fwd(qkv, n_seq, S, heads, mode)

@@ -38,7 +38,7 @@ buf = ctypes.create_string_buffer(1 << 16)
 lib_.vfm_prof_report(buf, len(buf))
 lib_.vfm_prof_enable(0)
 print(buf.value.decode().strip().replace("\n", " | "))
-for mode in (1, 2):
+for mode in (1, 2, 3):
     ts = []
     for _ in range(10):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

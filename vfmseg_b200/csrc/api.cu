@@ -370,7 +370,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
                      int kv_total, int heads, int mode, cudaStream_t st) {
   if (!q || !k || !v || !out || n_seq <= 0 || q_total <= 0 || kv_total <= 0 || heads <= 0)
     return fail(VFM_ERR_INVALID, "attention: bad args");
-  if (mode < 0 || mode > 2) return fail(VFM_ERR_INVALID, "attention: mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 3) return fail(VFM_ERR_INVALID, "attention: mode must be 0, 1, 2 or 3");
   if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
   bool extra = mode == 2;
   // mode 0: plain tiles. The split saves a ninth query tile and a seventeenth key tile at 1025 tokens, but measured
@@ -408,6 +408,19 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     int dev = 0;
     VFM_CUDA(cudaGetDevice(&dev));
     VFM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (mode == 3) {   // experimental: serial kernel, four CTAs per SM (attention_serial_kernel)
+    static bool attr3 = false;
+    if (!attr3) {
+      VFM_CUDA(cudaFuncSetAttribute(attention_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATS_SMEM_BYTES));
+      attr3 = true;
+    }
+    {
+      LaunchScope scope("attention_fwd_serial", st);
+      attention_serial_kernel<<<static_cast<unsigned>(units), ATS_THREADS, ATS_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    }
+    VFM_LAUNCH_CHECK("attention_fwd_serial");
+    return VFM_OK;
   }
   const unsigned grid = static_cast<unsigned>(units < 2LL * n_sm ? units : 2LL * n_sm);   // persistent: two CTAs per SM
   {

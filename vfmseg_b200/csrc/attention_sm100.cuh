@@ -613,4 +613,193 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Experimental alternative (mode 3 of vfm_attention_fwd_ex): the SERIAL kernel shape of attention_glob_sm100.cuh at
+// head_dim 64 — one CTA per (sequence, head, 128-query tile), single score buffer with P in place, O in TMEM, row sum
+// in a register, K and V single-buffered but released in different phases — slimmed to 128 TMEM columns, 33 KB of shared
+// memory and <= 84 registers (two passes over the score columns, 32 at a time) so that FOUR CTAs share an SM: four
+// independent serial chains instead of two pipelined ones.
+constexpr int ATS_THREADS = 192;
+constexpr int ATS_SMEM_BYTES = ATT_Q_BYTES + 2 * ATT_KV_BYTES + 1024 + 128;
+constexpr uint32_t ATS_TMEM_COLS = 128;
+
+__global__ void __launch_bounds__(ATS_THREADS, 4)
+attention_serial_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_Q_BYTES;
+  uint8_t* sV = sK + ATT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;   // S_t executed
+  uint64_t* v_full = bars + 3;
+  uint64_t* v_empty = bars + 4;   // PV_t executed
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x;
+  const int qt = unit % p.q_tiles;
+  const int head = (unit / p.q_tiles) % p.heads;
+  const int seq = unit / (p.q_tiles * p.heads);
+  const int q_row0 = seq * p.q_seq_rows + p.q_row_off + qt * ATT_BLOCK_Q;
+  const int kv_row0 = seq * p.kv_seq_rows + p.kv_row_off;
+  const int n_tiles = (p.kv_len + ATT_BLOCK_KV - 1) / ATT_BLOCK_KV;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], i == 6 ? 4 : 1);
+    fence_barrier_init();
+    mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
+    tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0);
+    tma_load_2d(sQ + ATT_KV_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row0 + 64);
+    mbar_arrive_expect_tx(k_full, ATT_KV_BYTES);
+    tma_load_2d(sK, &tmap_k, k_full, p.k_col0 + head * ATT_D, kv_row0);
+    mbar_arrive_expect_tx(v_full, ATT_KV_BYTES);
+    tma_load_2d(sV, &tmap_v, v_full, p.v_col0 + head * ATT_D, kv_row0);
+  }
+  if (warp == 1) tmem_alloc<ATS_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    for (int t = 1; t < n_tiles; ++t) {
+      mbar_wait(k_empty, (t - 1) & 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(k_full, ATT_KV_BYTES);
+        tma_load_2d(sK, &tmap_k, k_full, p.k_col0 + head * ATT_D, kv_row0 + t * ATT_BLOCK_KV);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, (t - 1) & 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(v_full, ATT_KV_BYTES);
+        tma_load_2d(sV, &tmap_v, v_full, p.v_col0 + head * ATT_D, kv_row0 + t * ATT_BLOCK_KV);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BLOCK_Q, ATT_BLOCK_KV, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BLOCK_Q, ATT_D, 0, 1);
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+    const uint64_t dq = make_sw128_desc(smem_u32(sQ)), dk = make_sw128_desc(smem_u32(sK)), dv = make_sw128_desc(smem_u32(sV));
+    mbar_wait(q_full, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(k_full, t & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        tc_commit(k_empty);
+        tc_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(v_full, t & 1);
+      mbar_wait(p_full, t & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const int ksteps = (min(ATT_BLOCK_KV, p.kv_len - t * ATT_BLOCK_KV) + 15) >> 4;
+        for (int k = 0; k < ksteps; ++k) umma_ts(tmem_o, tmem_s + 8 * k, dv + 128 * k, idesc_pv, (t | k) != 0);
+        tc_commit(v_empty);
+        if (t == n_tiles - 1) tc_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base, tmem_o = tmem_base + lane_base + 64;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kRescaleThreshold = 8.0f;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      mbar_wait(s_full, t & 1);
+      tc_fence_after();
+      const int valid = p.kv_len - t * ATT_BLOCK_KV;
+      // pass 1: row max, 32 columns at a time
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + 32 * c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (32 * c + i < valid) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      const float m_tile = m * kLog2e;
+      const bool jump = m_tile > m_ref + (t == 0 ? 0.f : kRescaleThreshold);
+      if (__any_sync(0xffffffffu, jump)) {
+        const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;
+        if (jump) { m_ref = m_tile; l *= alpha; }
+        if (t > 0) {
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(tmem_o + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(tmem_o + c * 16, r);
+          }
+        }
+      }
+      // pass 2: P over the scores, in place (a 32-column chunk is in registers before 16 packed columns are written)
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + 32 * c, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = 32 * c + 2 * i;
+          const float e0 = key < valid ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), kLog2e, -m_ref)) : 0.f;
+          const float e1 = key + 1 < valid ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), kLog2e, -m_ref)) : 0.f;
+          const __nv_bfloat162 b = __floats2bfloat162_rn(e0, e1);
+          l += __low2float(b) + __high2float(b);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&b);
+        }
+        tmem_st16(tmem_s + 16 * c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int q_idx = qt * ATT_BLOCK_Q + row;
+    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + head * ATT_D);
+#pragma unroll 1
+    for (int c = 0; c < ATT_D / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld16(tmem_o + 16 * c, r);
+      tmem_ld_wait();
+      if (q_idx < p.q_len) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]) * inv;
+          dst[2 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<ATS_TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace vfm
