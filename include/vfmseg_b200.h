@@ -249,6 +249,10 @@ int vfm_gemm_patch_embed_ex(const void* A, int lda, const void* W, int ldw, cons
                             int patches, int cls_rows, int M, int N, int K, void* stream);
 int vfm_layernorm_tap_ex(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
                          void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, void* stream);
+/* Same, with window_partition (sam_vit.py:292-316) folded into the store: out_map[input row] = output row (NULL: identity).
+ * The padding rows of the destination are never written: the caller zero-fills the buffer once and reuses it. */
+int vfm_layernorm_tap_map(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                          void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, const int* out_map, void* stream);
 
 /* rel[seq][head][token][0..k_h) = q . Rh[qh, kh, :], rel[..][k_h + kw] = q . Rw[qw, kw, :] with the UNSCALED q of the packed
  * qkv buffer (bf16 [n_seq * q_h * q_w, 3 * heads * head_dim]); Rh fp32 [q_h][k_h][head_dim], Rw fp32 [q_w][k_w][head_dim] are
@@ -269,6 +273,10 @@ int vfm_attention_relpos(const void* qkv, const float* rel, void* out, int n_seq
  * vfm_attention_relpos_ex with rel == NULL (g_col0 < 0: no bias). sam_vit.py:272-287,391-428. */
 int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int n_seq, int seq_len, int heads, int head_dim,
                             int k_h, int k_w, float scale, void* stream);
+/* Same, with window_unpartition (sam_vit.py:335-346) folded into the store: out_map[window-order row] = output row, < 0 for the
+ * padding rows, which are not written (NULL: identity). */
+int vfm_attention_window_tc_map(const void* qkv, int ld, int g_col0, void* out, const int* out_map, int n_seq, int seq_len, int heads,
+                                int head_dim, int k_h, int k_w, float scale, void* stream);
 /* The same attention over a whole token grid (key-tile loop, online softmax) on tcgen05, head_dim 80, k_h and k_w rounded up
  * to 16 summing to at most 128 bias columns (grids up to 64 x 64). onehot: bf16 [onehot_rows >= seq_len, 64 * ceil((bh + bw) / 64)],
  * row k = 1.0 at column kh(k) and at column bh + kw(k) (bh = k_h rounded up to 16) — a constant of the grid the caller builds

@@ -82,6 +82,8 @@ SIGNATURES = {
     "vfm_rows_gather": (_i, [_p, _p, _p, _ll, _i, _p]),
     "vfm_attention_relpos": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     "vfm_attention_global_tc": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "vfm_attention_window_tc_map": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "vfm_layernorm_tap_map": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _i, _i, _i, _i, _p, _p]),
     "vfm_attention_window_tc": (_i, [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     "vfm_attention_relpos_ex": (_i, [_p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p]),
     "vfm_groupnorm_relu": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

@@ -538,6 +538,11 @@ int vfm_attention_relpos_ex(const void* qkv, int ld, int g_col0, const float* re
 
 int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int n_seq, int seq_len, int heads, int head_dim,
                             int k_h, int k_w, float scale, void* stream) {
+  return vfm_attention_window_tc_map(qkv, ld, g_col0, out, nullptr, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, stream);
+}
+
+int vfm_attention_window_tc_map(const void* qkv, int ld, int g_col0, void* out, const int* out_map, int n_seq, int seq_len, int heads,
+                                int head_dim, int k_h, int k_w, float scale, void* stream) {
   if (!qkv || !out || n_seq <= 0 || seq_len <= 0 || heads <= 0) return fail(VFM_ERR_INVALID, "attention_window_tc: bad args");
   if (head_dim != WIN_D) return fail(VFM_ERR_INVALID, "attention_window_tc: head_dim must be %d (got %d)", WIN_D, head_dim);
   if (seq_len > WIN_KEYS) return fail(VFM_ERR_INVALID, "attention_window_tc: at most %d tokens per window (got %d)", WIN_KEYS, seq_len);
@@ -561,7 +566,7 @@ int vfm_attention_window_tc(const void* qkv, int ld, int g_col0, void* out, int 
   }
   WinParams p{};
   p.seq_len = seq_len; p.heads = heads; p.k_h = k_h; p.k_w = k_w; p.ld = ld; p.g_col0 = g_col0; p.scale = scale;
-  p.qkv = BF(qkv); p.out = const_cast<__nv_bfloat16*>(BF(out));
+  p.qkv = BF(qkv); p.out = const_cast<__nv_bfloat16*>(BF(out)); p.out_map = out_map;
   const dim3 grid((seq_len + WIN_BLOCK_Q - 1) / WIN_BLOCK_Q, heads, n_seq);
   {
     LaunchScope scope("attention_window_tc", S(stream));
@@ -673,6 +678,11 @@ int vfm_layernorm_tap(const float* x, const float* gamma, const float* beta, voi
 
 int vfm_layernorm_tap_ex(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
                          void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, void* stream) {
+  return vfm_layernorm_tap_map(x, gamma, beta, out, M, C, eps, tap, tap_ld, tap_col0, tokens_per_crop, cls_rows, nullptr, stream);
+}
+
+int vfm_layernorm_tap_map(const float* x, const float* gamma, const float* beta, void* out, int M, int C, float eps,
+                          void* tap, int tap_ld, int tap_col0, int tokens_per_crop, int cls_rows, const int* out_map, void* stream) {
   if (!x || M <= 0) return fail(VFM_ERR_INVALID, "layernorm: bad args");
   if (!out && !tap) return fail(VFM_ERR_INVALID, "layernorm: neither an output nor a tap was given");
   if (out && (!gamma || !beta)) return fail(VFM_ERR_INVALID, "layernorm: null gamma/beta");
@@ -684,7 +694,7 @@ int vfm_layernorm_tap_ex(const float* x, const float* gamma, const float* beta, 
   {
     LaunchScope scope("layernorm", st);
     switch (C / 128) {
-#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps, BF(tap), tap_ld, tap_col0, fd, cls_rows); break;
+#define VFM_LN_CASE(I) case I: layernorm_kernel<I><<<grid, 256, 0, st>>>(x, gamma, beta, BF(out), M, eps, BF(tap), tap_ld, tap_col0, fd, cls_rows, out_map); break;
       VFM_LN_CASE(1) VFM_LN_CASE(2) VFM_LN_CASE(3) VFM_LN_CASE(4) VFM_LN_CASE(5) VFM_LN_CASE(6) VFM_LN_CASE(7) VFM_LN_CASE(8)
       VFM_LN_CASE(9) VFM_LN_CASE(10) VFM_LN_CASE(11) VFM_LN_CASE(12)
 #undef VFM_LN_CASE

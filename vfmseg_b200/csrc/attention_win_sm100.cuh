@@ -41,6 +41,8 @@ struct WinParams {
   float scale;
   const __nv_bfloat16* qkv;
   __nv_bfloat16* out;
+  const int* out_map;           // optional: output row of each (window-order) query row, < 0 = padding row, not written —
+                                // window_unpartition (sam_vit.py:335-346) folded into the store
 };
 
 // Shared-memory matrix descriptors for the narrower swizzle modes (cf. make_sw128_desc): rows of 64 B / 32 B, 8-row groups
@@ -263,13 +265,15 @@ attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const float inv = 1.f / l;
     const int q = q0 + row;
-    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row0 + q) * C + head * WIN_D);
+    int orow = row0 + q;
+    if (p.out_map != nullptr) orow = q < p.seq_len ? __ldg(p.out_map + row0 + q) : -1;
+    uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(orow < 0 ? 0 : orow) * C + head * WIN_D);
 #pragma unroll 1
     for (int c = 0; c < WIN_D / 16; ++c) {
       uint32_t r[16];
       tmem_ld16(tmem_o + 16 * c, r);
       tmem_ld_wait();
-      if (q < p.seq_len) {
+      if (q < p.seq_len && orow >= 0) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float v[8];

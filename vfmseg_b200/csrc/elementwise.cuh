@@ -79,7 +79,7 @@ template <int ITERS>  // C = 128 * ITERS
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, int M, float eps, __nv_bfloat16* __restrict__ tap, int tap_ld,
-                 int tap_col0, FastDiv tokens_per_crop, int cls_rows) {
+                 int tap_col0, FastDiv tokens_per_crop, int cls_rows, const int* __restrict__ out_map) {
   constexpr int C = 128 * ITERS;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -115,7 +115,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.f / C) + eps);
-  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * C);
+  // out_map (optional): destination row of each input row — SAM's window partition writes the normalised tokens straight
+  // into window order (the zero rows of the padding are never written: the caller keeps them zero)
+  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(out_map ? __ldg(out_map + row) : row) * C);
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);

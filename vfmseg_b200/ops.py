@@ -368,3 +368,21 @@ def attention_global_tc(qkv, onehot, n_seq, seq_len, heads, head_dim, k_h, k_w, 
     _C.call("vfm_attention_global_tc", _bf16(qkv), qkv.shape[1], g_col0, _bf16(onehot), onehot.shape[0], _bf16(out), n_seq, seq_len,
             heads, head_dim, k_h, k_w, float(scale), _stream())
     return out
+
+
+def layernorm_tap_nocls_into(x, gamma, beta, eps, out, out_map, tap=None, tap_col0=0):
+    """layernorm_tap_nocls writing row i of the result to row out_map[i] of `out` (window order; padding rows untouched)."""
+    M, Cc = x.shape
+    assert out_map.dtype == torch.int32 and out_map.numel() == M and out.shape[1] == Cc
+    _C.call("vfm_layernorm_tap_map", _f32(x), _f32(gamma), _f32(beta), _bf16(out), M, Cc, float(eps),
+            _bf16(tap) if tap is not None else None, tap.shape[1] if tap is not None else 0, tap_col0, 1, 0, _ptr(out_map), _stream())
+    return out
+
+
+def attention_window_tc_into(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, scale, g_col0, out_map, n_out_rows):
+    """attention_window_tc storing window-order row i at output row out_map[i] (< 0: padding, dropped): token order."""
+    assert qkv.shape[0] == n_seq * seq_len and qkv.stride(0) == qkv.shape[1] and out_map.numel() == n_seq * seq_len
+    out = torch.empty(n_out_rows, heads * head_dim, device=qkv.device, dtype=torch.bfloat16)
+    _C.call("vfm_attention_window_tc_map", _bf16(qkv), qkv.shape[1], g_col0, _bf16(out), _ptr(out_map), n_seq, seq_len, heads,
+            head_dim, k_h, k_w, float(scale), _stream())
+    return out

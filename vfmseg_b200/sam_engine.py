@@ -152,6 +152,13 @@ class PackedSam:
             self._maps[key] = (part.to(torch.int32).to(self.device), unpart.to(torch.int32).to(self.device), n_win)
         return self._maps[key]
 
+    def _window_buffer(self, rows: int, C: int) -> torch.Tensor:
+        """Persistent window-order activation buffer, zero-filled once: the padding rows are never written afterwards."""
+        key = ("winbuf", rows, C)
+        if key not in self._maps:
+            self._maps[key] = torch.zeros(rows, C, dtype=torch.bfloat16, device=self.device)
+        return self._maps[key]
+
     # SlideEngine.backbone_taps dispatches here
     def forward_taps(self, img: torch.Tensor, crops: torch.Tensor, gh: int, gw: int, pixel_norm) -> torch.Tensor:
         """SAMViT.forward (sam_vit.py:123-147) for the listed windows -> taps bf16 [n*gh*gw, n_taps*C] (token-major): the raw
@@ -169,17 +176,21 @@ class PackedSam:
         taps = torch.empty(n * P, len(outs) * C, dtype=torch.bfloat16, device=x.device)
         for i, b in enumerate(self.blocks):
             tap_i = outs.index(i - 1) if (i - 1) in outs else None                    # tap of the previous block's output
-            h = ops.layernorm_tap_nocls(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None, (tap_i or 0) * C)
             ws = b["window"]
+            tap_args = (taps if tap_i is not None else None, (tap_i or 0) * C)
             if ws:
+                # window_partition folded into the LayerNorm store (rows go straight to window order; the padding rows of
+                # the persistent buffer stay zero) and window_unpartition into the attention kernel's store
                 part, unpart, n_win = self._window_maps(n, gh, gw, ws)
-                qkv = ops.gemm_bias_bf16(ops.rows_gather(h, part), b["qkv_w"], b["qkv_b"])          # q | k | v | G_h | G_w
+                hw = self._window_buffer(n_win * ws * ws, C)
+                ops.layernorm_tap_nocls_into(x, *b["n1"], s.ln_eps, hw, unpart, *tap_args)
+                qkv = ops.gemm_bias_bf16(hw, b["qkv_w"], b["qkv_b"])                               # q | k | v | G_h | G_w
                 if d == 80 and ws * ws <= 208 and ws <= 16:      # whole window in one tcgen05 score tile
-                    aw = ops.attention_window_tc(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0)
+                    att = ops.attention_window_tc_into(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0, part, n * P)
                 else:
-                    aw = ops.attention_relpos_terms(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0)
-                att = ops.rows_gather(aw, unpart)
+                    att = ops.rows_gather(ops.attention_relpos_terms(qkv, n_win, ws * ws, H, d, ws, ws, scale, g0), unpart)
             else:
+                h = ops.layernorm_tap_nocls(x, *b["n1"], s.ln_eps, *tap_args)
                 qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
                 bias_cols = (gh + 15) // 16 * 16 + (gw + 15) // 16 * 16
                 if d == 80 and g0 >= 0 and bias_cols <= 128:           # key-tile loop on tcgen05
