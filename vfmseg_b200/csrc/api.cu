@@ -888,11 +888,11 @@ int vfm_rope_qk(void* qkv, long long M, int C, int heads, int tokens_per_seq, co
 
 int vfm_swiglu_layernorm(const void* in, void* out, const float* gamma, const float* beta, long long M, int H, int Hp, float eps,
                          void* stream) {
-  if (!in || !out || !gamma || !beta || M <= 0 || H <= 0 || Hp < H || (Hp % 8) || Hp > SWIGLU_MAX_ITERS * 256)
-    return fail(VFM_ERR_INVALID, "swiglu_layernorm: bad args (Hp %% 8 == 0, Hp <= %d)", SWIGLU_MAX_ITERS * 256);
+  if (!in || !out || !gamma || !beta || M <= 0 || H <= 0 || Hp < H || (Hp % 8) || Hp > SWIGLU_MAX_ITERS * SWIGLU_TPR * 8)
+    return fail(VFM_ERR_INVALID, "swiglu_layernorm: bad args (Hp %% 8 == 0, Hp <= %d)", SWIGLU_MAX_ITERS * SWIGLU_TPR * 8);
   {
     LaunchScope scope("swiglu_layernorm", S(stream));
-    swiglu_layernorm_kernel<<<static_cast<unsigned>((M + 7) / 8), 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, M, H, Hp, eps);
+    swiglu_layernorm_kernel<<<static_cast<unsigned>((M + 1) / 2), 256, 0, S(stream)>>>(BF(in), BF(out), gamma, beta, M, H, Hp, eps);
   }
   VFM_LAUNCH_CHECK("swiglu_layernorm");
   return VFM_OK;
