@@ -34,8 +34,8 @@ __device__ __forceinline__ Bilerp bilerp_setup(int oy, int ox, float scale_h, fl
   return b;
 }
 __device__ __forceinline__ float bilerp_eval(const float* __restrict__ p, const Bilerp& b) {
-  return b.h0 * (b.w0 * __ldg(p + b.o00) + b.w1 * __ldg(p + b.o00 + b.dx)) +
-         b.h1 * (b.w0 * __ldg(p + b.o00 + b.dy) + b.w1 * __ldg(p + b.o00 + b.dy + b.dx));
+  return bilerp_rn(b.h0, b.h1, b.w0, b.w1, __ldg(p + b.o00), __ldg(p + b.o00 + b.dx), __ldg(p + b.o00 + b.dy),
+                   __ldg(p + b.o00 + b.dy + b.dx));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -63,7 +63,7 @@ image_resize_norm_kernel(const T* __restrict__ img, int B, int H, int W, PixelNo
       const float a00 = (static_cast<float>(__ldg(p + bl.o00)) - mu) * is, a01 = (static_cast<float>(__ldg(p + bl.o00 + bl.dx)) - mu) * is;
       const float a10 = (static_cast<float>(__ldg(p + bl.o00 + bl.dy)) - mu) * is;
       const float a11 = (static_cast<float>(__ldg(p + bl.o00 + bl.dy + bl.dx)) - mu) * is;
-      v = bl.h0 * (bl.w0 * a00 + bl.w1 * a01) + bl.h1 * (bl.w0 * a10 + bl.w1 * a11);
+      v = bilerp_rn(bl.h0, bl.h1, bl.w0, bl.w1, a00, a01, a10, a11);
     }
     out[idx] = v;
   }
@@ -154,7 +154,7 @@ ms_context_im2col_kernel(const float* __restrict__ low0, const int4* __restrict_
         const float u01 = bilerp_eval(p, bilerp_setup(cb.y + y0, cb.z + x1, up_h, up_w, lh, lw));
         const float u10 = bilerp_eval(p, bilerp_setup(cb.y + y1, cb.z + x0, up_h, up_w, lh, lw));
         const float u11 = bilerp_eval(p, bilerp_setup(cb.y + y1, cb.z + x1, up_h, up_w, lh, lw));
-        v[d] = h0 * (w0 * u00 + w1 * u01) + h1 * (w0 * u10 + w1 * u11);
+        v[d] = bilerp_rn(h0, h1, w0, w1, u00, u01, u10, u11);
       }
     }
     const size_t row = (static_cast<size_t>(r) * oh + oy) * ow + ox;
@@ -292,7 +292,7 @@ ms_merge_argmax_kernel(const float* __restrict__ low0, const float* __restrict__
         const float* p = refined + static_cast<size_t>(ri) * nc * plane_r;
 #pragma unroll
         for (int c = 0; c < NC_MAX; ++c)
-          if (c < nc) acc[c] += bilerp_eval(p + c * plane_r, bl);
+          if (c < nc) acc[c] = __fadd_rn(acc[c], bilerp_eval(p + c * plane_r, bl));
       } else {
         if (!have_ctx) {
           const Bilerp bl = bilerp_setup(y, x, up_h, up_w, lh, lw);
@@ -304,7 +304,7 @@ ms_merge_argmax_kernel(const float* __restrict__ low0, const float* __restrict__
         }
 #pragma unroll
         for (int c = 0; c < NC_MAX; ++c)
-          if (c < nc) acc[c] += ctx[c];
+          if (c < nc) acc[c] = __fadd_rn(acc[c], ctx[c]);
       }
     }
     const float cnt = static_cast<float>(count);

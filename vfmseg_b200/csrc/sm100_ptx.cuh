@@ -352,6 +352,14 @@ __device__ __forceinline__ float fast_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Bilinear blend with a FIXED operation order and explicit roundings (no fused-multiply-add contraction left to the compiler),
+// so every kernel that resamples logits — the three slide-merge kernels and the coarse-to-fine ones — produces the same bits
+// for the same taps and weights; the tests rely on that (merge of refined windows == plain slide merge, bit-exact).
+__device__ __forceinline__ float bilerp_rn(float h0, float h1, float w0, float w1, float tl, float tr, float bl, float br) {
+  const float top = __fmaf_rn(w1, tr, __fmul_rn(w0, tl));
+  const float bot = __fmaf_rn(w1, br, __fmul_rn(w0, bl));
+  return __fmaf_rn(h1, bot, __fmul_rn(h0, top));
+}
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
