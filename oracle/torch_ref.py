@@ -394,19 +394,17 @@ def eva_slide_inference(inputs: Tensor, bb, hd, cfg, *, crop, stride) -> Tensor:
 
 # --------------------------------------------------------------------------- SAM ViT backbone (BASELINE config 5)
 def sam_rel_pos_table(q_size: int, k_size: int, rel_pos: Tensor) -> Tensor:
-    """get_rel_pos, rein/models/backbones/sam_vit.py:358-388: linear interpolation of the (L, C) table to
-    2 max(q, k) - 1 entries when L differs (global blocks are built with 4 * size - 1 entries, :248-254), then the
-    gather R[q, k] = table[q - k + (k_size - 1)] for equal sizes. Returns [q_size, k_size, C]."""
-    max_rel_dist = int(2 * max(q_size, k_size) - 1)
-    if rel_pos.shape[0] != max_rel_dist:
-        r = F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=max_rel_dist, mode="linear")
-        r = r.reshape(-1, max_rel_dist).permute(1, 0)
-    else:
-        r = rel_pos
-    q_coords = torch.arange(q_size)[:, None] * max(k_size / q_size, 1.0)
-    k_coords = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
-    rel = (q_coords - k_coords) + (k_size - 1) * max(q_size / k_size, 1.0)
-    return r[rel.long()]
+    """get_rel_pos, rein/models/backbones/sam_vit.py:358-388, for self-attention on one grid (q_size == k_size = n, the only
+    way Attention.forward calls it, :278-280): the stored (L, C) table is brought to 2n - 1 entries by linear interpolation
+    when L differs (global blocks are built with 4n - 1 entries, :248-254) and entry [q, k] is row q - k + n - 1.
+    Returns [n, n, C]."""
+    assert q_size == k_size, "the reference only ever passes equal sizes"
+    n = q_size
+    table = rel_pos
+    if table.shape[0] != 2 * n - 1:
+        table = F.interpolate(table.t()[None], size=2 * n - 1, mode="linear")[0].t()
+    offset = torch.arange(n)[:, None] - torch.arange(n)[None, :] + (n - 1)
+    return table[offset]
 
 
 def sam_attention(x: Tensor, sd, pre: str, num_heads: int, lora_scale: float) -> Tensor:

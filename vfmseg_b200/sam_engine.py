@@ -36,19 +36,6 @@ class SamSpec:
     ln_eps: float = 1e-6
 
 
-def rel_pos_table(q_size: int, k_size: int, rel_pos: torch.Tensor) -> torch.Tensor:
-    """get_rel_pos, sam_vit.py:358-388 -> [q_size, k_size, head_dim] (the table indexed by q - k + k_size - 1)."""
-    max_rel_dist = int(2 * max(q_size, k_size) - 1)
-    r = rel_pos.float()
-    if r.shape[0] != max_rel_dist:
-        r = F.interpolate(r.reshape(1, r.shape[0], -1).permute(0, 2, 1), size=max_rel_dist, mode="linear")
-        r = r.reshape(-1, max_rel_dist).permute(1, 0)
-    q_coords = torch.arange(q_size)[:, None] * max(k_size / q_size, 1.0)
-    k_coords = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
-    rel = (q_coords - k_coords) + (k_size - 1) * max(q_size / k_size, 1.0)
-    return r[rel.long()].contiguous()
-
-
 def rel_pos_resized(size: int, rel_pos: torch.Tensor) -> torch.Tensor:
     """The (2 size - 1, head_dim) table get_rel_pos indexes with q - k + size - 1 (sam_vit.py:372-388): linear
     interpolation when the stored table has another length (global blocks store 4 size - 1 entries, :248-254)."""
