@@ -277,3 +277,19 @@ def test_sam_table_terms_folded_into_qkv_match_decomposed_rel_pos():
         # bf16 weights on one side, fp32 on the other: compare at bf16 resolution of the accumulated products
         assert torch.allclose(got_h, rel_h, rtol=2e-2, atol=2e-2), (got_h - rel_h).abs().max()
         assert torch.allclose(got_w, rel_w, rtol=2e-2, atol=2e-2), (got_w - rel_w).abs().max()
+
+
+def test_relpos_onehot_matrix():
+    """The constant one-hot key matrix of vfm_attention_global_tc: row k has 1.0 at column kh(k) and at column bh + kw(k)
+    (bh = k_h rounded up to 16), zero rows pad the key count to a multiple of 64, columns pad to 64-wide atoms."""
+    from vfmseg_b200 import ops
+    for k_h, k_w in ((32, 32), (64, 64), (20, 20), (24, 40)):
+        e = ops.relpos_onehot(k_h, k_w, "cpu").float()
+        bh, bw = (k_h + 15) // 16 * 16, (k_w + 15) // 16 * 16
+        n = k_h * k_w
+        assert e.shape == ((n + 63) // 64 * 64, (bh + bw + 63) // 64 * 64)
+        assert torch.all(e[:n].sum(1) == 2) and torch.all(e[n:] == 0)
+        rel = torch.randn(bh + bw)
+        got = e[:n] @ torch.cat([rel, torch.zeros(e.shape[1] - bh - bw)])
+        ref = (rel[:k_h, None] + rel[None, bh:bh + k_w]).reshape(-1)      # rel_h[kh] + rel_w[kw], key = kh * k_w + kw
+        assert torch.allclose(got, ref)
