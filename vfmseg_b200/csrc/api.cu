@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -372,6 +373,10 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     return fail(VFM_ERR_INVALID, "attention: bad args");
   if (mode < 0 || mode > 3) return fail(VFM_ERR_INVALID, "attention: mode must be 0, 1, 2 or 3");
   if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
+  if (mode == 0) {   // experiment knob (tools/): VFM_ATT_MODE=1|2|3 overrides the automatic choice
+    static const int forced = [] { const char* e = std::getenv("VFM_ATT_MODE"); return e ? std::atoi(e) : 0; }();
+    if (forced >= 1 && forced <= 3 && !(forced == 2 && (q_total != kv_total || kv_total < 2))) mode = forced;
+  }
   bool extra = mode == 2;
   // mode 0: plain tiles. The split saves a ninth query tile and a seventeenth key tile at 1025 tokens, but measured
   // 0.189 vs 0.167 ms on B200: its per-CTA prologue/epilogue loads and the appended query CTAs cost more than the tiles.
