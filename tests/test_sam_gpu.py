@@ -185,3 +185,31 @@ def test_attention_global_tc(n_seq, k_h, k_w, heads):
     if k_h % 2 == 0 and k_w % 2 == 0:
         other = ops.attention_relpos_terms(qkv, n_seq, S, heads, d, k_h, k_w, scale, 3 * C).float().cpu()
         assert ((got - other).abs() <= 2e-2 + 2e-2 * other.abs()).all()
+
+
+def test_sam_1024_crop_two_blocks_vs_oracle():
+    """BASELINE config 5's crop (1024^2 -> 64 x 64 tokens) at ViT-H width with two blocks (one windowed: 25 windows, 64 -> 70
+    zero padding; one global: 4096 tokens, two 64-column bias atoms, rel-pos tables interpolated 255 -> 127) against the oracle
+    restatement on the CPU."""
+    import vfmseg_b200
+    from oracle import torch_ref
+    from vfmseg_b200 import synthetic
+    cfg = synthetic.sam_model_config(img_size=1024, depth=2, global_attn_indexes=(1,), out_indices=(0, 1), crop_size=(1024, 1024),
+                                     stride=(682, 682))
+    sd = synthetic.synthetic_sam_state_dict(cfg, seed=2)
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "num_batches_tracked" not in m]
+    model = model.cuda().eval()
+    img = synthetic.synthetic_images(1, 1024, 1024, seed=5)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    feats = model.extract_feat(x.cuda())
+    pre = "backbone.model.base_model.model."
+    bb = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+    lc = cfg["backbone"]["Lora_config"]
+    with torch.no_grad():
+        ref = torch_ref.sam_forward(x, bb, depth=2, num_heads=16, window_size=14, global_attn_indexes=(1,), out_indices=(0, 1),
+                                    lora_scale=lc["lora_alpha"] / lc["r"])
+    for i, (f, r) in enumerate(zip(feats, ref)):
+        assert f.shape == (1, 1280, 64, 64)
+        _check_logits(f, r, f"SAM ViT-H 1024 crop, block {i} output vs oracle")
