@@ -291,6 +291,10 @@ int vfm_attention_global_tc(const void* qkv, int ld, int g_col0, const void* one
 int vfm_attention_relpos_ex(const void* qkv, int ld, int g_col0, const float* rel, void* out, int n_seq, int seq_len, int heads,
                             int head_dim, int k_h, int k_w, float scale, void* stream);
 
+/* qkv Linear + bias with the 2-D rotary embedding of vfm_rope_qk applied in the GEMM epilogue to columns [0, rope_cols) (the q
+ * and k thirds) of every non-cls row, on the fp32 accumulator. eva_02.py:337-369. */
+int vfm_gemm_bias_rope_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                            int N, int K, const float* cos_t, const float* sin_t, int rope_cols, int tokens_per_seq, void* stream);
 /* ---------------------------------------------------------------- EVA02 backbone (rein/models/backbones/eva_02.py)
  * In-place 2-D rotary embedding of the q and k thirds of packed qkv activations [M, 3C] bf16 (VisionRotaryEmbeddingFast
  * :119-160 applied at :362-369); token 0 of every sequence (cls) is left untouched. cos/sin: fp32 [tokens_per_seq-1, 64]. */

@@ -96,3 +96,27 @@ def test_full_size_eva_runs():
     assert torch.isfinite(logits).all() and labels.shape == (1, 1024, 2048)
     labels2, _ = model.predict_labels(img)
     assert torch.equal(labels2[0], labels[0])
+
+
+def test_gemm_bias_rope_matches_gemm_then_rope():
+    """RoPE in the qkv GEMM epilogue (fp32 accumulator, one rounding) against the GEMM followed by the in-place RoPE kernel
+    (two roundings) and against torch fp32."""
+    from oracle import torch_ref
+    from vfmseg_b200 import ops
+    n, grid, heads = 3, 4, 4
+    T, C = grid * grid + 1, heads * 64
+    a = _rand(n * T, C, seed=11, dtype=torch.bfloat16)
+    w = _rand(3 * C, C, scale=0.05, seed=12, dtype=torch.bfloat16)
+    b = _rand(3 * C, scale=0.1, seed=13)
+    cos, sin = torch_ref.eva_rope_tables(64, 16, grid)
+    cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    got = ops.gemm_bias_rope_bf16(a, w, b, cos, sin, 2 * C, T).float().cpu()
+    two = ops.rope_qk_(ops.gemm_bias_bf16(a, w, b), heads, T, cos, sin).float().cpu()
+    y = (a.float().cpu() @ w.float().cpu().t() + b.cpu()).view(n, T, 3, heads, 64)
+    ref = y.clone()
+    for which in (0, 1):
+        t = y[:, 1:, which]
+        ref[:, 1:, which] = t * cos.cpu()[None, :, None, :] + torch_ref._rotate_half(t) * sin.cpu()[None, :, None, :]
+    ref = ref.view(n * T, 3 * C)
+    assert ((got - ref).abs() <= 1e-2 + 1e-2 * ref.abs()).all()
+    assert ((got - two).abs() <= 2e-2 + 2e-2 * two.abs()).all()

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vfm_prof_enable": (_i, [_i]),
     "vfm_prof_report": (_i, [C.c_char_p, _sz]),
     "vfm_gemm_bias_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "vfm_gemm_bias_rope_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "vfm_gemm_bias_gelu_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_bias_ls_residual": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "vfm_gemm_patch_embed": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p]),

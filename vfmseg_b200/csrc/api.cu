@@ -301,6 +301,15 @@ int vfm_gemm_bias_bf16(const void* A, int lda, const void* W, int ldw, const flo
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_bf16", OutDesc{out, ldo});
 }
 
+int vfm_gemm_bias_rope_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo, int M,
+                            int N, int K, const float* cos_t, const float* sin_t, int rope_cols, int tokens_per_seq, void* stream) {
+  if (!out || (ldo % 8) || !cos_t || !sin_t || tokens_per_seq < 2 || rope_cols < 0 || (rope_cols % 64) || rope_cols > N ||
+      ((reinterpret_cast<uintptr_t>(cos_t) | reinterpret_cast<uintptr_t>(sin_t)) & 15))
+    return fail(VFM_ERR_INVALID, "gemm_bias_rope_bf16: bad args (rope_cols %% 64 == 0, 16-byte aligned tables)");
+  EpiTmaBf16Rope e{bias, cos_t, sin_t, rope_cols, FastDiv(tokens_per_seq)};
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_rope_bf16", OutDesc{out, ldo});
+}
+
 int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* out, int ldo,
                             int M, int N, int K, void* stream) {
   if (!out || !bias || (ldo % 8)) return fail(VFM_ERR_INVALID, "gemm_bias_gelu_bf16: bad out/bias/ldo");

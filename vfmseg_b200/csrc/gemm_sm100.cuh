@@ -103,6 +103,10 @@ struct EpiBiasGeluBf16 {        // out = bf16(gelu_erf(acc + bias))  (fc1; mlp.p
 // TMA-store epilogues: math stays row-per-thread in registers, the 32-row fragment is written to a
 // SWIZZLE_128B shared-memory box with conflict-free 16-byte stores and one elected lane hands it to the TMA
 // engine, which clips the M / N tails. No per-element global instructions at all.
+// epilogues whose apply needs the output row (not just the column) declare kNeedsRow and implement apply_row
+template <class E, class = void> struct epi_needs_row : std::false_type {};
+template <class E> struct epi_needs_row<E, std::enable_if_t<E::kNeedsRow>> : std::true_type {};
+
 template <bool kGelu>
 struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf GELU (fc1) or identity (qkv, fusion conv)
   static constexpr int kMode = EPI_TMA_BF16;
@@ -117,6 +121,37 @@ struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf 
         v[4 * i] = gelu_erf(v[4 * i]); v[4 * i + 1] = gelu_erf(v[4 * i + 1]);
         v[4 * i + 2] = gelu_erf(v[4 * i + 2]); v[4 * i + 3] = gelu_erf(v[4 * i + 3]);
       }
+    }
+  }
+};
+
+// qkv Linear + bias + 2-D rotary position embedding on the q and k thirds (EVA02, eva_02.py:337-369): columns below
+// rope_cols of every patch token (token 0 of a sequence, the cls token, is skipped) get t * cos + rotate_half(t) * sin with
+// rotate_half(x)[2i] = -x[2i+1], rotate_half(x)[2i+1] = x[2i] (:54-58), on the fp32 accumulator (one rounding to bf16 instead
+// of two). cos / sin: fp32 [tokens_per_seq - 1, 64]; head_dim 64, so a 32-column fragment is half a head.
+struct EpiTmaBf16Rope {
+  static constexpr int kMode = EPI_TMA_BF16;
+  static constexpr bool kStore4D = false;
+  static constexpr bool kNeedsRow = true;
+  const float* bias; const float* cos_t; const float* sin_t; int rope_cols; FastDiv tokens_per_seq;
+  __device__ __forceinline__ void apply_row(int row, int col0, float (&v)[32]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+    }
+    if (col0 >= rope_cols) return;   // warp-uniform: the v third
+    int seq, tok;
+    tokens_per_seq.divmod(row, seq, tok);
+    if (tok == 0) return;
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + static_cast<size_t>(tok - 1) * 64 + (col0 & 63));
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + static_cast<size_t>(tok - 1) * 64 + (col0 & 63));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 c = __ldg(cp + i), sn = __ldg(sp + i);
+      const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+      v[4 * i] = x0 * c.x - x1 * sn.x; v[4 * i + 1] = x1 * c.y + x0 * sn.y;
+      v[4 * i + 2] = x2 * c.z - x3 * sn.z; v[4 * i + 3] = x3 * c.w + x2 * sn.w;
     }
   }
 };
@@ -404,7 +439,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-              epi.apply(col0, v);
+              if constexpr (epi_needs_row<Epi>::value) epi.apply_row(row_base + lane, col0, v);
+              else epi.apply(col0, v);
               uint8_t* box = reinterpret_cast<uint8_t*>(stg);
               uint8_t* rowp = box + lane * 128;
               const int sw = lane & 7;   // SWIZZLE_128B: 16-byte chunk index ^= row % 8

@@ -132,8 +132,7 @@ class PackedEva:
             tap_i = outs.index(i - 1) if (i - 1) in outs else None                    # tap of the previous block's output
             h = ops.layernorm_tap(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None,
                                   (tap_i or 0) * C, T)
-            qkv = ops.gemm_bias_bf16(h, b["qkv_w"], b["qkv_b"])
-            ops.rope_qk_(qkv, s.num_heads, T, self.rope_cos, self.rope_sin)           # :362-369
+            qkv = ops.gemm_bias_rope_bf16(h, b["qkv_w"], b["qkv_b"], self.rope_cos, self.rope_sin, 2 * C, T)   # :337-369
             att = ops.attention_fwd(qkv, n, T, s.num_heads)                           # xops.memory_efficient_attention :376
             ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
             h = ops.layernorm(x, *b["n2"], s.ln_eps)

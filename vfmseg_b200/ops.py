@@ -386,3 +386,13 @@ def attention_window_tc_into(qkv, n_seq, seq_len, heads, head_dim, k_h, k_w, sca
     _C.call("vfm_attention_window_tc_map", _bf16(qkv), qkv.shape[1], g_col0, _bf16(out), _ptr(out_map), n_seq, seq_len, heads,
             head_dim, k_h, k_w, float(scale), _stream())
     return out
+
+
+def gemm_bias_rope_bf16(a, w, bias, cos_t, sin_t, rope_cols, tokens_per_seq):
+    """qkv GEMM with RoPE on columns [0, rope_cols) of the non-cls rows applied in the epilogue (EVA02)."""
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_bias_rope_bf16", _bf16(a), a.stride(0), _bf16(w), K, _f32(bias), _bf16(out), N, M, N, K,
+            _f32(cos_t), _f32(sin_t), rope_cols, tokens_per_seq, _stream())
+    return out
