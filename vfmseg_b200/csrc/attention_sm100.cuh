@@ -463,6 +463,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the Q tile from shared memory
       }
 
+      // A warp whose 32 query rows all lie past the end of the sequence (three of the four warps in the one-row ninth
+      // query tile of a 1025-token ViT window) only keeps the barrier phases moving: it leaves the MUFU pipe to the
+      // co-resident CTA. Its TMEM lanes hold garbage P / O / L rows that are never stored (MMA rows are independent).
+      const bool warp_live = qt * ATT_BLOCK_Q + quad * 32 < p.q_len;
+      if (!warp_live) {
+        for (int j = 0; j < kv_tiles; ++j, ++t) {
+          const int b = t & 1;
+          mbar_wait(&s_full[b], (t >> 1) & 1);   // keeps this warp in step with the others: S_{t+2} follows p_full_t
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[b]);
+        }
+        mbar_wait(&pv_done[(t - 1) & 1], ((t - 1) >> 1) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
+        continue;
+      }
+
       for (int j = 0; j < kv_tiles; ++j, ++t) {
         const int b = t & 1;
         const uint32_t ph = (t >> 1) & 1;
@@ -527,6 +544,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         // always 0), which ptxas cannot hoist over.
         constexpr int kExpDist = 4;
         constexpr int kPolyEvery = VFM_ATT_POLY;   // 0: all exponentials on the MUFU pipe; n: one in 2n on the FMA pipe
+        if (valid <= 2) {
+          // tail tile of one or two keys (the 1025th token of a ViT window): two exponentials instead of 32; the masked
+          // columns of the 32-key MMA step are exact zeros
+          uint32_t pk[16];
+          const float e0 = fast_exp2(fmaf(__uint_as_float(s[0]), kLog2e, -m_ref));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(s[1]), kLog2e, -m_ref));   // s[1] = -inf when masked
+          pk[0] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632u);
+#pragma unroll
+          for (int i = 1; i < 16; ++i) pk[i] = 0u;
+          tmem_st16(tmem_s, pk);
+        } else
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c < chunks) {
