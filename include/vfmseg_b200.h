@@ -148,6 +148,14 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
                            int crop_w, int lh, int lw, int H, int W, int n_img, uint8_t* labels,
                            float* logits_out, void* stream);
 
+/* Horizontal-flip test-time augmentation, combining step: a = slide(img), b = slide(flip(img, x)), both fp32
+ * [n_img, nc, H, W]; logits = (a + mirror_x(b)) / 2 (optional output, may alias a), labels = argmax, first maximum
+ * wins. Bit-identical to res = 0; res += a; res += flip(b); res / 2.
+ * Replaces rein/models/segmentors/hrda_encoder_decoder.py:196-229 (scales = [1], flip = True) + the
+ * postprocess_result argmax. */
+int vfm_tta_flip_mean_argmax(const float* a, const float* b, int n_img, int nc, int H, int W,
+                             uint8_t* labels, float* logits_out, void* stream);
+
 /* cm[(min(label, nc)) * nc + pred] += 1 over pixels with label != ignore_index; cm is int64
  * [(nc+1) * nc], accumulated (not zeroed). area_intersect = diag, area_pred = column sums over all
  * nc+1 rows, area_label = row sums of the first nc rows.

@@ -210,6 +210,19 @@ def slide_inference(inputs: Tensor, sd, cfg, *, crop, stride, return_lowres: boo
     return (out, lows) if return_lowres else out
 
 
+def tta_flip_combine(slide_fn, inputs: Tensor, flip: bool = True) -> Tensor:
+    """rein/models/segmentors/hrda_encoder_decoder.py:196-229 with `test_time_aug` on and scales = [1] (:198; the resizes
+    by scale_factor 1 are identities): res = zeros; res += slide(img); if flip: res += flip(slide(flip(img, [3])), [3]);
+    res / (2 if flip else 1). `slide_fn(img) -> [B,C,H,W]` is the plain slide inference."""
+    a = slide_fn(inputs)
+    res = torch.zeros_like(a)
+    res += a
+    if flip:
+        res += torch.flip(slide_fn(torch.flip(inputs, [3])), [3])
+        return res / 2
+    return res / 1
+
+
 def whole_inference(inputs: Tensor, sd, cfg) -> Tensor:
     """mmseg EncoderDecoder.whole_inference [3P] = encode_decode on the full image."""
     return encode_decode(inputs, sd, cfg)[0]

@@ -106,6 +106,35 @@ def test_tiny_slide_vs_golden_and_oracle():
     _check_labels(labels2, ref2, "tiny slide batch 2 labels vs oracle")
 
 
+def test_tiny_slide_tta_flip_vs_oracle():
+    """test_cfg.test_time_aug + flip (hrda_encoder_decoder.py:114-115, :196-229): both passes and the combining
+    kernel against the oracle; the combination itself bit-exact given the two passes' logits."""
+    from oracle import torch_ref
+    from vfmseg_b200 import synthetic
+    cfg = synthetic.tiny_config(stride=(32, 32))
+    model, sd = _build(cfg, seed=3)
+    img = synthetic.synthetic_images(2, 80, 112, seed=21)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    osd, ocfg = torch_ref.split_state_dict(sd), _oracle_cfg(cfg)
+    with torch.no_grad():
+        ref = torch_ref.tta_flip_combine(lambda im: torch_ref.slide_inference(im, osd, ocfg, crop=(64, 64), stride=(32, 32)), x)
+    plain_labels, plain = model.predict_labels(img.cuda(), want_logits=True)
+    _, mirrored = model.predict_labels(torch.flip(img, [3]).cuda(), want_logits=True)
+    model.test_cfg.test_time_aug = True
+    model.test_cfg.flip = True
+    labels, logits = model.predict_labels(img.cuda(), want_logits=True)
+    _check_logits(logits, ref, "tiny slide + flip TTA vs oracle")
+    _check_labels(labels, ref, "tiny slide + flip TTA labels vs oracle")
+    assert torch.equal(logits, (plain + torch.flip(mirrored, [3])) / 2)
+    assert torch.equal(labels.long().cpu(), logits.cpu().argmax(1))
+    labels_only, none = model.predict_labels(img.cuda())
+    assert none is None and torch.equal(labels_only, labels)
+    assert torch.equal(model.inference(x.cuda(), None), model.slide_inference(x.cuda(), None))
+    assert not torch.equal(logits, plain) and plain_labels.shape == labels.shape   # the augmentation is not a no-op
+    model.test_cfg.flip = False                        # test_time_aug alone: res / 1 (:228-229)
+    assert torch.equal(model.predict_labels(img.cuda(), want_logits=True)[1], plain)
+
+
 def test_tiny_whole_nonsquare_vs_golden():
     from vfmseg_b200 import synthetic
     cfg = synthetic.tiny_config(mode="whole")

@@ -240,6 +240,30 @@ def test_slide_merge_argmax(ops, H, W, crop, stride, n_img):
     assert none is None and torch.equal(labels, labels2)
 
 
+@pytest.mark.parametrize("B,nc,H,W", [(2, 19, 16, 64), (1, 19, 7, 13), (1, 3, 5, 4), (1, 19, 1024, 2048)])
+@pytest.mark.parametrize("want_logits", [True, False])
+def test_tta_flip_mean_argmax(ops, B, nc, H, W, want_logits):
+    """Bit-exact against the reference's statements (hrda_encoder_decoder.py:199-229, scales = [1]) on the CPU;
+    quantised values force ties, which must resolve to the first maximum like torch.argmax on the CPU."""
+    g = torch.Generator().manual_seed(7)
+    a = (torch.randn(B, nc, H, W, generator=g) * 4).round() / 4
+    b = (torch.randn(B, nc, H, W, generator=g) * 4).round() / 4
+    a[0, :, 0, :min(W, 4)] = 1.25        # whole-pixel ties across every class
+    b[0, :, 0, W - min(W, 4):] = 0.75
+    res = torch.zeros_like(a)
+    res += a
+    res += torch.flip(b, [3])
+    want = res / 2
+    labels, logits = ops.tta_flip_mean_argmax(a.cuda(), b.cuda(), want_logits=want_logits)
+    assert labels.dtype == torch.uint8 and labels.shape == (B, H, W)
+    assert torch.equal(labels.cpu().long(), want.argmax(1))
+    assert (labels[0, 0, :min(W, 4)] == 0).all()
+    if want_logits:
+        assert torch.equal(logits.cpu(), want)
+    else:
+        assert logits is None
+
+
 @pytest.mark.parametrize("n", [1024 * 2048, 16 * 1000 + 7, 5, 0])
 def test_confusion_matrix(ops, n):
     nc = 19

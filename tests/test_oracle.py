@@ -231,3 +231,34 @@ def test_sam_oracle_against_live_reference():
                                     global_attn_indexes=oc["global_attn_indexes"], out_indices=oc["out_indices"], lora_scale=oc["lora_scale"])
     for a, b in zip(got, ref):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ flip test-time augmentation
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree absent")
+@pytest.mark.parametrize("flip", [True, False])
+def test_tta_flip_oracle_against_live_reference(flip):
+    """oracle.tta_flip_combine against the reference's own HRDAEncoderDecoder.slide_inference
+    (hrda_encoder_decoder.py:194-229, unmodified), the per-window encode_decode supplied by the oracle."""
+    import torch.nn as nn
+    hrda = ref_shim.load("models.segmentors.hrda_encoder_decoder")
+    cfg = synthetic.tiny_config(stride=(32, 32))
+    sd, ocfg = _oracle_model(cfg, seed=3)
+    seg = hrda.HRDAEncoderDecoder.__new__(hrda.HRDAEncoderDecoder)
+    nn.Module.__init__(seg)
+    seg.test_cfg = ref_shim.ConfigDict(mode="slide", crop_size=(64, 64), stride=(32, 32), test_time_aug=True, flip=flip)
+    seg.test_time_aug, seg.flip = True, flip           # what __init__ copies out of test_cfg (:114-115)
+    seg.num_classes = seg.out_channels = cfg["decode_head"]["num_classes"]
+    seg.align_corners = False
+    seg.encode_decode = lambda crop, metas: torch_ref.encode_decode(crop, sd, ocfg)[0]
+    x = torch_ref.preprocess(synthetic.synthetic_images(2, 80, 112, seed=21), MEAN, STD, True)
+    meta = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)] * 2
+    with torch.no_grad():
+        want = seg.slide_inference(x, meta)
+        got = torch_ref.tta_flip_combine(lambda im: torch_ref.slide_inference(im, sd, ocfg, crop=(64, 64), stride=(32, 32)), x, flip)
+    assert torch.equal(got, want)
+    if flip:   # the augmentation is not a no-op for this model, and its result is mirror-equivariant by construction
+        plain = torch_ref.slide_inference(x, sd, ocfg, crop=(64, 64), stride=(32, 32))
+        assert not torch.allclose(got, plain, atol=1e-3)
+        got_m = torch_ref.tta_flip_combine(lambda im: torch_ref.slide_inference(im, sd, ocfg, crop=(64, 64), stride=(32, 32)),
+                                           torch.flip(x, [3]), True)
+        torch.testing.assert_close(torch.flip(got_m, [3]), got, rtol=0, atol=1e-6)

@@ -113,6 +113,11 @@ def main():
     cm = torch.zeros(20, 19, dtype=torch.int64, device=dev)
     ms, best = timeit(lambda: ops.confusion_matrix_(cm, pred, lab, 19), args.iters, flush=flush, label="confusion_matrix 2M px (random labels)")
     rec("confusion_matrix 2M px (random labels)", ms, best, None, 2.0 * 1024 * 2048)
+    la, lb_ = f32(1, 19, 1024, 2048), f32(1, 19, 1024, 2048)
+    ms, best = timeit(lambda: ops.tta_flip_mean_argmax(la, lb_, want_logits=True), args.iters, flush=flush, label="tta_flip_mean_argmax 1024x2048 (+logits)")
+    rec("tta_flip_mean_argmax 1024x2048 (+logits)", ms, best, None, 3.0 * la.numel() * 4 + 1024 * 2048)
+    ms, best = timeit(lambda: ops.tta_flip_mean_argmax(la, lb_), args.iters, flush=flush, label="tta_flip_mean_argmax 1024x2048 (labels)")
+    rec("tta_flip_mean_argmax 1024x2048 (labels)", ms, best, None, 2.0 * la.numel() * 4 + 1024 * 2048)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "bench_kernels.json").write_text(json.dumps(res, indent=1))
 

@@ -770,6 +770,29 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
   return VFM_OK;
 }
 
+int vfm_tta_flip_mean_argmax(const float* a, const float* b, int n_img, int nc, int H, int W, uint8_t* labels, float* logits_out,
+                             void* stream) {
+  if (!a || !b || !labels || n_img <= 0 || nc <= 0 || nc > 255 || H <= 0 || W <= 0)
+    return fail(VFM_ERR_INVALID, "tta_flip_mean_argmax: bad args (num_classes <= 255)");
+  if (logits_out == b) return fail(VFM_ERR_INVALID, "tta_flip_mean_argmax: logits_out may alias a, not b (b is read mirrored)");
+  const bool vec4 = (W % 4) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                                      reinterpret_cast<uintptr_t>(logits_out)) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(labels) & 3) == 0;
+  const long long items = static_cast<long long>(n_img) * H * (vec4 ? W / 4 : W);
+  long long blocks = (items + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;   // a multiple of the SM count, grid-stride beyond it
+  if (blocks > cap) blocks = cap;
+  {
+    LaunchScope scope("tta_flip_mean_argmax", S(stream));
+    if (vec4)
+      tta_flip_mean_argmax_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(a, b, n_img, nc, H, W, labels, logits_out);
+    else
+      tta_flip_mean_argmax_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, S(stream)>>>(a, b, n_img, nc, H, W, labels, logits_out);
+  }
+  VFM_LAUNCH_CHECK("tta_flip_mean_argmax");
+  return VFM_OK;
+}
+
 // ------------------------------------------------------------------------------ coarse-to-fine path (config 3)
 static unsigned grid_for(long long work_items, int per_sm = 16) {
   long long blocks = (work_items + 255) / 256;

@@ -321,4 +321,75 @@ confusion_matrix_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tta_flip_mean_argmax: horizontal-flip test-time augmentation, the combining step of
+// rein/models/segmentors/hrda_encoder_decoder.py:196-229 with scales = [1]:
+//   res = 0; res += slide(img); res += flip(slide(flip(img)), [3]); res / 2   -> argmax(dim=0), first maximum wins.
+// a = slide(img), b = slide(flip(img)) (NOT yet flipped back), both fp32 [n_img, nc, H, W]. 0 + a is exact and / 2 is an
+// exact halving, so (a + b_mirrored) * 0.5f is bit-identical to the reference's three statements. HBM-bound: two reads and
+// at most one write of the logits; a thread owns VEC consecutive pixels of one row for every class (16-byte accesses when
+// VEC = 4; the mirrored read is the same 128-byte lines in reverse lane order, so it coalesces as well).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+tta_flip_mean_argmax_kernel(const float* a, const float* __restrict__ b, int n_img, int nc, int H, int W,
+                            uint8_t* __restrict__ labels, float* logits_out /* may alias a */) {
+  constexpr int CH = 4;   // classes whose loads are issued together (8 x 16 B in flight per thread)
+  const int Wv = W / VEC;
+  const long long total = static_cast<long long>(n_img) * H * Wv;
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xv = static_cast<int>(idx % Wv);
+    const long long r = idx / Wv;
+    const int y = static_cast<int>(r % H);
+    const int img = static_cast<int>(r / H);
+    const int x = xv * VEC, xm = W - VEC - x;          // mirrored strip starts at W - 1 - (x + VEC - 1)
+    const size_t row = static_cast<size_t>(img) * nc * plane + static_cast<size_t>(y) * W;
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+    for (int c0 = 0; c0 < nc; c0 += CH) {
+      float va[CH][VEC], vb[CH][VEC];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (c0 + k < nc) {
+          const size_t off = row + static_cast<size_t>(c0 + k) * plane;
+          if constexpr (VEC == 4) {
+            const float4 fa = __ldcs(reinterpret_cast<const float4*>(a + off + x));
+            const float4 fb = __ldcs(reinterpret_cast<const float4*>(b + off + xm));
+            va[k][0] = fa.x; va[k][1] = fa.y; va[k][2] = fa.z; va[k][3] = fa.w;
+            vb[k][0] = fb.w; vb[k][1] = fb.z; vb[k][2] = fb.y; vb[k][3] = fb.x;
+          } else {
+            va[k][0] = __ldcs(a + off + x); vb[k][0] = __ldcs(b + off + xm);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        const int c = c0 + k;
+        if (c < nc) {
+          const size_t off = row + static_cast<size_t>(c) * plane;
+          float m[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            m[i] = __fadd_rn(va[k][i], vb[k][i]) * 0.5f;
+            if (m[i] > best[i] || c == 0) { best[i] = m[i]; arg[i] = c; }   // strict >: the first maximum wins
+          }
+          if (logits_out != nullptr) {
+            if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(logits_out + off + x), make_float4(m[0], m[1], m[2], m[3]));
+            else __stcs(logits_out + off + x, m[0]);
+          }
+        }
+      }
+    }
+    uint8_t* lp = labels + static_cast<size_t>(img) * plane + static_cast<size_t>(y) * W + x;
+    if constexpr (VEC == 4)
+      *reinterpret_cast<uint32_t*>(lp) = static_cast<uint32_t>(arg[0]) | (static_cast<uint32_t>(arg[1]) << 8) |
+                                         (static_cast<uint32_t>(arg[2]) << 16) | (static_cast<uint32_t>(arg[3]) << 24);
+    else
+      *lp = static_cast<uint8_t>(arg[0]);
+  }
+}
+
 }  // namespace vfm

@@ -117,9 +117,22 @@ class LoraBackboneEncoderDecoder(nn.Module):
         _, logits, _ = self.engine().whole(self._as_input(inputs), want_logits=True)
         return logits
 
+    def _slide(self, x: torch.Tensor, want_logits: bool):
+        """Slide inference, optionally with the horizontal-flip test-time augmentation of
+        rein/models/segmentors/hrda_encoder_decoder.py:196-229 (`test_cfg.test_time_aug` and `test_cfg.flip`, :114-115;
+        scales = [1]): logits = (slide(img) + flip(slide(flip(img)))) / 2, combined and arg-maxed in one kernel."""
+        eng = self.engine()
+        crop, stride = self.test_cfg.crop_size, self.test_cfg.stride
+        if not (self.test_cfg.get("test_time_aug", False) and self.test_cfg.get("flip", False)):
+            labels, logits, _ = eng.slide(x, crop, stride, want_logits=want_logits)
+            return labels, logits
+        from .. import ops
+        _, a, _ = eng.slide(x, crop, stride, want_logits=True)
+        _, b, _ = eng.slide(torch.flip(x, [3]), crop, stride, want_logits=True)
+        return ops.tta_flip_mean_argmax(a, b, want_logits=want_logits)
+
     def slide_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
-        _, logits, _ = self.engine().slide(self._as_input(inputs), self.test_cfg.crop_size, self.test_cfg.stride, want_logits=True)
-        return logits
+        return self._slide(self._as_input(inputs), True)[1]
 
     def whole_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
         return self.encode_decode(inputs, batch_img_metas)
@@ -142,7 +155,7 @@ class LoraBackboneEncoderDecoder(nn.Module):
         eng = self.engine()
         x = self._as_input(inputs)
         if mode == "slide":
-            labels, logits, _ = eng.slide(x, self.test_cfg.crop_size, self.test_cfg.stride, want_logits=want_logits)
+            labels, logits = self._slide(x, want_logits)
         else:
             labels, logits, _ = eng.whole(x, want_logits=want_logits)
         return labels, logits

@@ -166,6 +166,16 @@ def slide_merge_argmax(lowres, boxes, n_img, crop_hw, out_hw, want_logits=False)
     return labels, logits
 
 
+def tta_flip_mean_argmax(a, b, want_logits=False):
+    """a = slide(img), b = slide(flip(img, x)): fp32 [B, nc, H, W]. Returns (uint8 labels [B,H,W], logits or None) of
+    (a + flip(b, x)) / 2; the logits are written over `a` (hrda_encoder_decoder.py:196-229, scales = [1])."""
+    assert a.shape == b.shape and a.dtype == b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    B, nc, H, W = a.shape
+    labels = torch.empty(B, H, W, device=a.device, dtype=torch.uint8)
+    _C.call("vfm_tta_flip_mean_argmax", _f32(a), _f32(b), B, nc, H, W, _ptr(labels), _f32(a) if want_logits else None, _stream())
+    return labels, (a if want_logits else None)
+
+
 def confusion_matrix_(cm, pred, label, num_classes, ignore_index=255):
     """cm: int64 [(nc+1), nc], accumulated in place."""
     assert cm.dtype == torch.int64 and cm.numel() == (num_classes + 1) * num_classes
