@@ -240,6 +240,23 @@ def test_slide_merge_argmax(ops, H, W, crop, stride, n_img):
     assert none is None and torch.equal(labels, labels2)
 
 
+@pytest.mark.parametrize("n,P,C,cls", [(3, 64, 256, 1), (2, 1024, 1024, 1), (3, 96, 128, 0), (5, 16, 256, 1), (2, 24, 64, 0)])
+def test_patch_embed_gemm_paths(ops, n, P, C, cls):
+    """Patch-embed GEMM + bias + pos-embed: the fp32 TMA-store epilogue (patches % 32 == 0: boxes shifted past the cls
+    rows in front of them) and the column-per-lane fallback, with and without a cls row (DINOv2 / SAM)."""
+    a = _rand(n * P, 768, seed=41, dtype=torch.bfloat16)
+    w = _rand(C, 768, scale=768 ** -0.5, seed=42, dtype=torch.bfloat16)
+    bias, pos = _rand(C, seed=43), _rand(P + cls, C, seed=44)
+    if cls:
+        x = ops.gemm_patch_embed(a, w, bias, pos, n, P)
+        x.view(n, P + 1, C)[:, 0] = 7.0                      # cls rows are not written by the GEMM
+        got = x.view(n, P + 1, C)[:, 1:]
+    else:
+        got = ops.gemm_patch_embed_nocls(a, w, bias, pos, n, P).view(n, P, C)
+    ref = (a.float() @ w.float().t() + bias).view(n, P, C) + pos[cls:]
+    _close(got.reshape(-1, C), ref.reshape(-1, C), 2e-3, 2e-3, f"patch_embed n={n} P={P} C={C} cls={cls}")
+
+
 @pytest.mark.parametrize("B,nc,H,W", [(2, 19, 16, 64), (1, 19, 7, 13), (1, 3, 5, 4), (1, 19, 1024, 2048)])
 @pytest.mark.parametrize("want_logits", [True, False])
 def test_tta_flip_mean_argmax(ops, B, nc, H, W, want_logits):

@@ -162,7 +162,7 @@ int sm_count() {
   return n;
 }
 
-struct OutDesc { const void* ptr = nullptr; int ld = 0; int convt_w = 0; int convt_rows = 0; };   // destination of the TMA-store epilogues
+struct OutDesc { const void* ptr = nullptr; int ld = 0; int convt_w = 0; int convt_rows = 0; int rows = 0; };   // destination of the TMA-store epilogues
 
 template <int BLOCK_N, int CTA_GROUP, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi, cudaStream_t st,
@@ -184,7 +184,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
     }
   } else if constexpr (Epi::kMode == EPI_TMA_RED_F32) {
-    if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4))) return rc;
+    if ((rc = make_tmap_ex(&tout, od.ptr, od.rows > 0 ? od.rows : M, N, od.ld, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4))) return rc;
   }
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, CTA_GROUP, Epi>;
   static bool attr_done = false;  // per template instantiation
@@ -334,6 +334,12 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
 int vfm_gemm_patch_embed_ex(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
                             int patches, int cls_rows, int M, int N, int K, void* stream) {
   if (!x || !bias || !pos || patches <= 0 || (M % patches) || (cls_rows & ~1)) return fail(VFM_ERR_INVALID, "gemm_patch_embed: bad args");
+  if ((patches % 32) == 0 && (N % 4) == 0) {   // a 32-row TMA box stays inside one crop: fp32 TMA stores
+    EpiTmaPatchEmbed e{bias, pos, N, FastDiv(patches), cls_rows};
+    OutDesc od{x, N};
+    od.rows = M / patches * (patches + cls_rows);
+    return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed", od);
+  }
   EpiPatchEmbed e{x, N, bias, pos, FastDiv(patches), cls_rows};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_patch_embed");
 }

@@ -107,6 +107,11 @@ struct EpiBiasGeluBf16 {        // out = bf16(gelu_erf(acc + bias))  (fc1; mlp.p
 template <class E, class = void> struct epi_needs_row : std::false_type {};
 template <class E> struct epi_needs_row<E, std::enable_if_t<E::kNeedsRow>> : std::true_type {};
 
+// EPI_TMA_RED_F32 epilogues that declare kPlainStore write the box with a plain TMA store at row out_row(row_base)
+// instead of reduce-adding it at row_base
+template <class E, class = void> struct epi_plain_store : std::false_type {};
+template <class E> struct epi_plain_store<E, std::enable_if_t<E::kPlainStore>> : std::true_type {};
+
 template <bool kGelu>
 struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf GELU (fc1) or identity (qkv, fusion conv)
   static constexpr int kMode = EPI_TMA_BF16;
@@ -218,6 +223,32 @@ struct EpiResidual {
       if (tok != 0) tap[static_cast<size_t>(row - crop - 1) * tap_ld + tap_col0 + col] = __float2bfloat16_rn(o);
     }
   }
+};
+
+// Patch-embed with fp32 TMA stores (patches % 32 == 0, so a warp's 32-row box never straddles two crops):
+// x[crop, cls + p, :] = acc + bias + pos_embed[cls + p, :]. Math row-per-thread in registers (each thread reads its pos-embed
+// row as 8 x 16 B, the table is 4 MB and L1/L2-resident), the box leaves through the TMA engine at the row shifted by the
+// cls rows in front of it. The column-per-lane version below spent 370 us per 36-window launch waiting on one pos-embed load
+// per row (ptxas serialised the 32 loads at the 168-register cap; profiles/r1_prof_patch_embed.txt).
+struct EpiTmaPatchEmbed {
+  static constexpr int kMode = EPI_TMA_RED_F32;
+  static constexpr bool kNeedsRow = true;
+  static constexpr bool kPlainStore = true;
+  const float* bias; const float* pos; int ldp; FastDiv patches; int cls;
+  __device__ __forceinline__ void apply_row(int row, int col0, float (&v)[32]) const {
+    const int p = row - patches.div(row) * patches.d;
+    const float4* pp = reinterpret_cast<const float4*>(pos + static_cast<size_t>(cls + p) * ldp + col0);
+    float4 pe[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pe[i] = __ldg(pp + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+      v[4 * i] = v[4 * i] + b.x + pe[i].x; v[4 * i + 1] = v[4 * i + 1] + b.y + pe[i].y;
+      v[4 * i + 2] = v[4 * i + 2] + b.z + pe[i].z; v[4 * i + 3] = v[4 * i + 3] + b.w + pe[i].w;
+    }
+  }
+  __device__ __forceinline__ int out_row(int row_base) const { return row_base + (patches.div(row_base) + 1) * cls; }
 };
 
 // Patch-embed: x[crop, 1 + p, :] = acc + bias + pos_embed[1 + p, :]   (dino_v2.py:219,225-226;
@@ -435,7 +466,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           VFM_ACC(1, t0, t1);
           const int col0 = n_blk * BLOCK_N + half * kColsPerSplit + c;
           if constexpr (Epi::kMode == EPI_TMA_BF16 || Epi::kMode == EPI_TMA_RED_F32) {
-            if (col0 < N) {   // warp-uniform
+            if (col0 < N && (!epi_plain_store<Epi>::value || row_base < M)) {   // warp-uniform
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -452,7 +483,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (elect_one_sync()) { tma_reduce_add_2d(&tmap_out, box, col0, row_base); tma_store_commit(); }
+                if (elect_one_sync()) {
+                  if constexpr (epi_plain_store<Epi>::value) tma_store_2d(&tmap_out, box, col0, epi.out_row(row_base));
+                  else tma_reduce_add_2d(&tmap_out, box, col0, row_base);
+                  tma_store_commit();
+                }
               } else {
                 const int hbox = (c >> 5) & 1;   // even chunk -> left 64 B of the 128-B rows, odd chunk -> right 64 B
                 if (hbox == 0) { tma_store_wait_read<0>(); __syncwarp(); }
