@@ -293,3 +293,34 @@ def test_relpos_onehot_matrix():
         got = e[:n] @ torch.cat([rel, torch.zeros(e.shape[1] - bh - bw)])
         ref = (rel[:k_h, None] + rel[None, bh:bh + k_w]).reshape(-1)      # rel_h[kh] + rel_w[kw], key = kh * k_w + kw
         assert torch.allclose(got, ref)
+
+
+def test_gelu_polynomial_in_the_kernel_source():
+    """The constants of gelu_erf() (csrc/sm100_ptx.cuh) evaluated in fp32 on the CPU against the exact-erf GELU
+    (dino_layers/mlp.py:22 = nn.GELU()): absolute error < 2e-6, relative error under half a bf16 ulp above 1e-5."""
+    import math
+    import re
+    from pathlib import Path
+
+    import numpy as np
+    from scipy.special import erf
+    src = (Path(__file__).resolve().parent.parent / "vfmseg_b200" / "csrc" / "sm100_ptx.cuh").read_text()
+    body = src[src.index("float gelu_erf(float x) {"):]
+    body = body[:body.index("\n}\n")]
+    clamp = np.float32(float(re.search(r"fminf\(fabsf\(x\), ([0-9.eE+-]+)f\)", body).group(1)))
+    first = re.search(r"float q = fmaf\(([0-9.eE+-]+)f, t, ([0-9.eE+-]+)f\);", body)
+    rest = re.findall(r"q = fmaf\(q, t, ([0-9.eE+-]+)f\);", body)
+    co = [np.float32(float(v)) for v in (first.group(1), first.group(2), *rest)]
+    assert len(co) >= 5 and "fmaf(-fabsf(x), e, fmaxf(x, 0.f))" in body
+    x = np.linspace(-9, 9, 400001).astype(np.float32)
+    t = np.minimum(np.abs(x), clamp)
+    q = np.full_like(t, co[0])
+    for v in co[1:]:
+        q = (q * t + v).astype(np.float32)
+    e = np.exp2(q.astype(np.float64)).astype(np.float32)
+    got = (np.maximum(x, 0) - np.abs(x) * e).astype(np.float64)
+    want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / math.sqrt(2)))
+    err = np.abs(got - want)
+    assert err.max() < 2e-6
+    m = np.abs(want) > 1e-5
+    assert (err[m] / np.abs(want[m])).max() < 2e-3

@@ -365,25 +365,23 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) (torch nn.GELU() default; dino_layers/mlp.py:22), with ONE MUFU op:
-//   erfc(a) = 2^q(a), q = degree-6 polynomial fitted to log2(erfc) on [0, 6] (weighted so the ABSOLUTE error of erfc is
-//   minimised; fit + error scan in tools/fit_gelu.py), a = |x| / sqrt 2;   1 + erf(x / sqrt 2) = x < 0 ? erfc(a) : 2 - erfc(a).
-// Max |error| of the GELU value 4.7e-7 (fp32 evaluation, x in [-9, 9]); relative error < 1.3e-4 for x >= -4 (below, the
-// value itself is < 1.3e-4 in magnitude). The previous Abramowitz-Stegun 7.1.26 form needed a reciprocal as well: two
-// MUFU ops per element made the fc1 epilogue MUFU-bound (256 elements per thread x 2 x 8 clk = the tile's MMA time).
-// Evaluated as relu(x) - |x| * 0.5 erfc(|x| / sqrt 2) with the 1/sqrt 2 and the 0.5 folded into the coefficients (q is a
-// polynomial in |x|, constant term - 1): 11 instructions per element with the bias add instead of 15 (no |x| scaling, no
-// sign select, no final 0.5 x product). The fc1 epilogue runs two warps per scheduler at ~19 instructions per element against
-// a 8192-clk main loop per tile, so it was partly exposed (isolated: 0.87 of the burst peak against 0.97 for the qkv GEMM).
-// Same fit, same error: max |error| 3.9e-7 on [-9, 9] (fp32 Horner, scanned on the CPU).
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)) (torch nn.GELU() default; dino_layers/mlp.py:22), with ONE MUFU op, as
+//   gelu(x) = relu(x) - |x| * h(|x|),   h(t) = 0.5 erfc(t / sqrt 2) = 2^q(t),
+// q = degree-5 polynomial in t = |x| on [0, 6 sqrt 2], fitted to log2(h) with weight t * h, i.e. minimising the ABSOLUTE
+// error of the GELU value (fit + error scan: tools/fit_gelu.py). Max |error| 1.2e-6 on [-9, 9]; relative error < 1.5e-3
+// wherever |gelu| > 1e-5 (fp32 Horner, scanned on the CPU) — under half an ulp (2e-3) of the bf16 value the epilogue stores.
+// 10 instructions per element with the bias add: FADD, FMNMX (clamp), 5 FFMA, MUFU.EX2, FMNMX (relu), FFMA. History: an
+// Abramowitz-Stegun 7.1.26 form needed a reciprocal as well (two MUFU ops per element made the fc1 epilogue MUFU-bound);
+// erfc(a) = 2^q(a) in a = |x| / sqrt 2 with x < 0 ? e : 2 - e and a final 0.5 x s took 15 instructions (degree 6, 4e-7).
+// The fc1 epilogue runs two warps per scheduler against an 8192-clk main loop per tile and is partly exposed, so the
+// instruction count shows: isolated fc1 GEMM 0.87 (15 instr) -> 0.92 (11, degree 6) of the burst peak, qkv GEMM 0.97.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float t = fminf(fabsf(x), 8.48528137423857f);   // 6 sqrt 2
-  float q = fmaf(2.8207001378177665e-05f, t, -0.0007193940109573305f);
-  q = fmaf(q, t, 0.007900431752204895f);
-  q = fmaf(q, t, -0.0531185120344162f);
-  q = fmaf(q, t, -0.4589919149875641f);
-  q = fmaf(q, t, -1.1511324644088745f);
-  q = fmaf(q, t, -0.999999463558197f);
+  float q = fmaf(-0.0004108866269234568f, t, 0.006676612421870232f);
+  q = fmaf(q, t, -0.050883423537015915f);
+  q = fmaf(q, t, -0.4609318673610687f);
+  q = fmaf(q, t, -1.1504031419754028f);
+  q = fmaf(q, t, -1.000085711479187f);
   const float e = fast_exp2(q);                         // 0.5 erfc(|x| / sqrt 2)
   return fmaf(-fabsf(x), e, fmaxf(x, 0.f));
 }
