@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "attention_sm100.cuh"
+#include "attention_pp_sm100.cuh"
 #include "sam_ops.cuh"
 #include "attention_win_sm100.cuh"
 #include "attention_glob_sm100.cuh"
@@ -386,11 +387,52 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
                      int kv_total, int heads, int mode, cudaStream_t st) {
   if (!q || !k || !v || !out || n_seq <= 0 || q_total <= 0 || kv_total <= 0 || heads <= 0)
     return fail(VFM_ERR_INVALID, "attention: bad args");
-  if (mode < 0 || mode > 3) return fail(VFM_ERR_INVALID, "attention: mode must be 0, 1, 2 or 3");
+  if (mode < 0 || mode > 5) return fail(VFM_ERR_INVALID, "attention: mode must be 0..5");
   if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
   if (mode == 0) {   // experiment knob (tools/): VFM_ATT_MODE=1|2|3 overrides the automatic choice
     static const int forced = [] { const char* e = std::getenv("VFM_ATT_MODE"); return e ? std::atoi(e) : 0; }();
-    if (forced >= 1 && forced <= 3 && !(forced == 2 && (q_total != kv_total || kv_total < 2))) mode = forced;
+    if (forced >= 1 && forced <= 5 && !((forced == 2 || forced == 5) && (q_total != kv_total || kv_total < 2))) mode = forced;
+  }
+  if (mode == 4 || mode == 5) {
+    // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM
+    const int ex = mode == 5 ? 1 : 0;
+    if (ex && (q_total != kv_total || kv_total < 2)) return fail(VFM_ERR_INVALID, "attention: extra-token mode needs q_total == kv_total >= 2");
+    if (ex && kv_total > APP_MAX_EXTRA_KEYS) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
+    AttParams p{};
+    p.extra = ex;
+    p.q_len = q_total - ex; p.kv_len = kv_total - ex;
+    p.q_seq_rows = q_seq_rows; p.kv_seq_rows = kv_seq_rows;
+    p.q_row_off = ex; p.kv_row_off = ex;
+    p.heads = heads;
+    p.q_tiles = (p.q_len + APP_UNIT_Q - 1) / APP_UNIT_Q;   // units per (sequence, head)
+    p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
+    p.q_ptr = BF(q); p.q_ld = q_ld;
+    p.k_ptr = BF(k); p.v_ptr = BF(v); p.k_ld = k_ld; p.v_ld = v_ld;
+    p.out = BF(out); p.out_ld = out_ld;
+    const uint64_t q_rows = static_cast<uint64_t>(n_seq - 1) * q_seq_rows + q_total;
+    const uint64_t kv_rows = static_cast<uint64_t>(n_seq - 1) * kv_seq_rows + kv_total;
+    CUtensorMap tq, tk, tv;   // 128-row boxes
+    int rc;
+    if ((rc = make_tmap(&tq, q, q_rows, q_col0 + heads * ATT_D, q_ld, 128))) return rc;
+    if ((rc = make_tmap(&tk, k, kv_rows, k_col0 + heads * ATT_D, k_ld, 128))) return rc;
+    if ((rc = make_tmap(&tv, v, kv_rows, v_col0 + heads * ATT_D, v_ld, 128))) return rc;
+    static bool attr_pp = false;
+    if (!attr_pp) {
+      VFM_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
+      attr_pp = true;
+    }
+    const long long units = static_cast<long long>(n_seq) * heads * p.q_tiles;
+    if (units > 0x7fffffffLL) return fail(VFM_ERR_INVALID, "attention: too many units");
+    p.n_units = static_cast<int>(units);
+    const int n_sm = sm_count();
+    if (n_sm <= 0) return fail(VFM_ERR_CUDA, "attention: no CUDA device");
+    const unsigned grid = static_cast<unsigned>(units < n_sm ? units : n_sm);
+    {
+      LaunchScope scope("attention_pp", st);
+      attention_pp_kernel<<<grid, APP_THREADS, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    }
+    VFM_LAUNCH_CHECK("attention_pp");
+    return VFM_OK;
   }
   bool extra = mode == 2;
   // mode 0: plain tiles. The split saves a ninth query tile and a seventeenth key tile at 1025 tokens, but measured

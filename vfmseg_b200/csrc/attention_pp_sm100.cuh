@@ -1,0 +1,490 @@
+// Fused multi-head attention (non-causal, head_dim 64) on tcgen05 for sm_100a — "ping-pong" kernel, round 2.
+//
+// Same contract as attention_fwd_kernel (attention_sm100.cuh): replaces the q@k^T / softmax / @v core of
+// rein/models/backbones/dino_layers/attention.py:56-66 and rein/models/heads/Transformer.py:113-136.
+//
+// What changed against the round-1 kernel, and why (profiles/r1_attention_timeline.txt): that kernel ran two CTAs per
+// SM with 64-key tiles; a softmax warp spent ~620 clk of fixed cost per 64-key tile (barrier wake-up, fences, row max,
+// reference check, store + arrive) around ~700 clk of exponentials, the MUFU pipe (the real ceiling at head_dim 64:
+// 1024 clk of ex2 per 128 x 128 scores against 512 clk of MMA) was busy ~half of the time.
+// Here ONE persistent CTA per SM owns all 512 TMEM columns and works on units of 256 query rows:
+//   * two softmax warpgroups A / B (128 rows each, one row per thread) share every K / V tile and run half a tile
+//     period apart, so the fixed per-tile cost of one hides under the exponentials of the other;
+//   * 128-key tiles: half as many barrier round trips per score, S = Q K^T as N = 128 MMAs (64.5 clk per k-step
+//     against 2 x 48.5 for two N = 64 ones: the N = 64 form is bound by the shared-memory read of A);
+//   * S, P and O all have their own TMEM columns (S_A S_B 2 x 128 fp32, P_A P_B 2 x 64 packed bf16, O_A O_B 2 x 64
+//     fp32 = 512), so S_X(t+1) is issued the moment warpgroup X has copied S_X(t) to registers — not behind
+//     P_X(t) -> PV_X(t) as the aliased layout forces — and is ready long before X comes back for it;
+//   * the row sums are kept in registers (packed FADD2), the row max uses the 3-input FMNMX, the scale/subtract is a
+//     packed FFMA2, P is rounded to nearest (cvt.rn.bf16x2), not truncated;
+//   * the S MMAs and the PV MMAs are issued by two different warps (tcgen05.mma blocks its issuing thread while the
+//     pipe is busy), each serving A then B in a fixed order.
+// "Extra token" mode (ViT sequences = 1 cls token + n x 128 patch tokens): the tensor tiles cover the body tokens; the
+// cls KEY is one dot product per query row on the CUDA cores (before the loop) and one AXPY in the epilogue; the cls
+// QUERY row of each (sequence, head) is computed by warp 3 of the CTAs straight from global memory while the tensor
+// pipeline runs (1/1025 of the work; no second launch).
+//
+// Warps (384 threads): warpgroup 0 = {TMA producer, S issuer (+ TMEM allocator), PV issuer, extra-query rows},
+// setmaxnreg-trimmed; warpgroups 1, 2 = softmax A, B (TMEM lane quadrant = warp % 4).
+#pragma once
+#include "attention_sm100.cuh"
+
+namespace vfm {
+
+constexpr int APP_TILE_Q = 128;                       // query rows per softmax warpgroup
+constexpr int APP_UNIT_Q = 2 * APP_TILE_Q;            // query rows per unit
+constexpr int APP_BLOCK_KV = 128;
+constexpr int APP_THREADS = 384;
+constexpr int APP_Q_STAGES = 2, APP_K_STAGES = 3, APP_V_STAGES = 3;
+constexpr int APP_TILE_BYTES = 128 * ATT_D * 2;       // 16 KB: one Q tile, one K tile, one V tile
+constexpr int APP_MAX_EXTRA_KEYS = 4224;              // score scratch of the extra-query warp (floats)
+constexpr int APP_BAR_BYTES = 512;
+constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES) * APP_TILE_BYTES +
+                               APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */;
+constexpr uint32_t APP_TMEM_COLS = 512;
+constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 128 / 64 / 64 for warpgroup X
+
+#ifndef VFM_APP_POLY
+#define VFM_APP_POLY 0      // n > 0: one exponential in n is evaluated on the FMA pipe (poly_exp2) instead of MUFU
+#endif
+#ifndef VFM_APP_STAGGER
+#define VFM_APP_STAGGER 1   // warpgroup B starts half a tile behind A
+#endif
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// (d0, d1) = (a0, a1) * b + c as one packed FFMA2
+__device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+// (d0, d1) += (a0, a1) as one packed FADD2
+__device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float a1) {
+  asm("{\n\t.reg .b64 ra, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rd, {%0, %1};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+
+// The query row of the extra token (cls) of one (sequence, head) against all kv_len + 1 keys, by ONE warp, from global
+// memory (2 x 64 x (kv_len + 1) MACs: 1/1025 of the attention work of a ViT window). Pass 1: one key per lane and step
+// (eight 16-byte loads in flight per lane), scores (log2 units) to shared memory; pass 2: the lane owns output columns
+// 2 lane, 2 lane + 1 and streams the V rows (one coalesced 128-byte row per load instruction, 16 in flight).
+__device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, int seq, int head, float* sc, float* qs) {
+  const int lane = threadIdx.x & 31;
+  const int kv_total = p.kv_len + 1;
+  const size_t kv_row = static_cast<size_t>(seq) * p.kv_seq_rows;
+  const __nv_bfloat16* kb = p.k_ptr + kv_row * p.k_ld + p.k_col0 + head * ATT_D;
+  const __nv_bfloat16* vb = p.v_ptr + kv_row * p.v_ld + p.v_col0 + head * ATT_D;
+  {
+    const uint32_t qv = __ldg(reinterpret_cast<const uint32_t*>(p.q_ptr + static_cast<size_t>(seq) * p.q_seq_rows * p.q_ld + p.q_col0 + head * ATT_D) + lane);
+    qs[2 * lane] = bf16lo(qv);
+    qs[2 * lane + 1] = bf16hi(qv);
+  }
+  __syncwarp();
+  float m = -INFINITY;
+  for (int base = 0; base < kv_total; base += 32) {
+    const int key = base + lane;
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(min(key, kv_total - 1)) * p.k_ld);
+    uint4 kv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kv[c] = __ldg(kr + c);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(qs + 8 * c);
+      const float4 q1 = *reinterpret_cast<const float4*>(qs + 8 * c + 4);
+      a0 = fmaf(q0.x, bf16lo(kv[c].x), a0); a1 = fmaf(q0.y, bf16hi(kv[c].x), a1);
+      a0 = fmaf(q0.z, bf16lo(kv[c].y), a0); a1 = fmaf(q0.w, bf16hi(kv[c].y), a1);
+      a0 = fmaf(q1.x, bf16lo(kv[c].z), a0); a1 = fmaf(q1.y, bf16hi(kv[c].z), a1);
+      a0 = fmaf(q1.z, bf16lo(kv[c].w), a0); a1 = fmaf(q1.w, bf16hi(kv[c].w), a1);
+    }
+    const float s = (a0 + a1) * 1.4426950408889634f;
+    if (key < kv_total) { sc[key] = s; m = fmaxf(m, s); }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncwarp();
+  float l = 0.f;
+  for (int key = lane; key < kv_total; key += 32) {
+    const float w = fast_exp2(sc[key] - m);
+    sc[key] = w;
+    l += w;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  const uint32_t* vr = reinterpret_cast<const uint32_t*>(vb) + lane;
+  const size_t v_pitch = static_cast<size_t>(p.v_ld) / 2;   // in uint32
+  for (int base = 0; base < kv_total; base += 16) {
+    uint32_t vv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) vv[i] = __ldg(vr + static_cast<size_t>(min(base + i, kv_total - 1)) * v_pitch);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float w = base + i < kv_total ? sc[base + i] : 0.f;
+      o0 = fmaf(w, bf16lo(vv[i]), o0);
+      o1 = fmaf(w, bf16hi(vv[i]), o1);
+    }
+  }
+  const float inv = 1.f / l;
+  reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(seq) * p.q_seq_rows * p.out_ld + head * ATT_D)[lane] =
+      pack_bf16x2(o0 * inv, o1 * inv);
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(APP_THREADS, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                                               // [stage][tile A | tile B]
+  uint8_t* smem_k = smem_q + 2 * APP_Q_STAGES * APP_TILE_BYTES;
+  uint8_t* smem_v = smem_k + APP_K_STAGES * APP_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + APP_V_STAGES * APP_TILE_BYTES);
+  uint64_t* q_full = bars;                          // [2] TMA -> S issuer, softmax (extra key)
+  uint64_t* q_empty = q_full + APP_Q_STAGES;        // [2] S issuer (last S of the unit executed) [+ softmax warps] -> TMA
+  uint64_t* k_full = q_empty + APP_Q_STAGES;        // [3] TMA -> S issuer
+  uint64_t* k_empty = k_full + APP_K_STAGES;        // [3] S issuer (S_A, S_B of the tile executed) -> TMA
+  uint64_t* v_full = k_empty + APP_K_STAGES;        // [3] TMA -> PV issuer
+  uint64_t* v_empty = v_full + APP_V_STAGES;        // [3] PV issuer (PV_A, PV_B of the tile executed) -> TMA
+  uint64_t* s_full = v_empty + APP_V_STAGES;        // [2] S issuer -> softmax X   (S_X(t) in TMEM)
+  uint64_t* s_free = s_full + 2;                    // [2] softmax X -> S issuer   (S_X(t) copied to registers)
+  uint64_t* p_full = s_free + 2;                    // [2] softmax X -> PV issuer  (P_X(t) in TMEM, O_X rescaled if needed)
+  uint64_t* p_free = p_full + 2;                    // [2] PV issuer -> softmax X  (O_X += P_X(t) V(t) executed)
+  uint64_t* o_free = p_free + 2;                    // [2] softmax X -> PV issuer  (O_X of the finished unit copied out)
+  uint64_t* stagger = o_free + 2;                   // [1] softmax A -> softmax B, once
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
+  float* extra_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + APP_BAR_BYTES);   // [APP_MAX_EXTRA_KEYS] (+ 64 for q)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int kv_tiles = (p.kv_len + APP_BLOCK_KV - 1) / APP_BLOCK_KV;
+  const int q_pairs = p.q_tiles;   // units per (sequence, head)
+  const int first_unit = blockIdx.x, unit_step = gridDim.x;
+  const int n_my = (p.n_units - first_unit + unit_step - 1) / unit_step;   // >= 1 (grid <= units)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 9 : 1); }
+    for (int s = 0; s < APP_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < APP_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
+      mbar_init(&o_free[x], 4);
+    }
+    mbar_init(stagger, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  struct Unit { int q_row0, kv_row0, head, seq, qp; };
+  auto unit_of = [&](int k) {
+    const int u = first_unit + k * unit_step;
+    Unit r;
+    r.qp = u % q_pairs;
+    r.head = (u / q_pairs) % p.heads;
+    r.seq = u / (q_pairs * p.heads);
+    r.q_row0 = r.seq * p.q_seq_rows + p.q_row_off + r.qp * APP_UNIT_Q;
+    r.kv_row0 = r.seq * p.kv_seq_rows + p.kv_row_off;
+    return r;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      int t = 0;
+      for (int k = 0; k < n_my; ++k) {
+        const Unit un = unit_of(k);
+        const int qs = k % APP_Q_STAGES;
+        mbar_wait(&q_empty[qs], ((k / APP_Q_STAGES) & 1) ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&q_full[qs], 2 * APP_TILE_BYTES);
+          tma_load_2d(smem_q + (2 * qs) * APP_TILE_BYTES, &tmap_q, &q_full[qs], p.q_col0 + un.head * ATT_D, un.q_row0);
+          tma_load_2d(smem_q + (2 * qs + 1) * APP_TILE_BYTES, &tmap_q, &q_full[qs], p.q_col0 + un.head * ATT_D, un.q_row0 + APP_TILE_Q);
+        }
+        __syncwarp();
+        for (int j = 0; j < kv_tiles; ++j, ++t) {
+          const int ks = t % APP_K_STAGES, vs = t % APP_V_STAGES;
+          mbar_wait(&k_empty[ks], ((t / APP_K_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&k_full[ks], APP_TILE_BYTES);
+            tma_load_2d(smem_k + ks * APP_TILE_BYTES, &tmap_k, &k_full[ks], p.k_col0 + un.head * ATT_D, un.kv_row0 + j * APP_BLOCK_KV);
+          }
+          __syncwarp();
+          mbar_wait(&v_empty[vs], ((t / APP_V_STAGES) & 1) ^ 1);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&v_full[vs], APP_TILE_BYTES);
+            tma_load_2d(smem_v + vs * APP_TILE_BYTES, &tmap_v, &v_full[vs], p.v_col0 + un.head * ATT_D, un.kv_row0 + j * APP_BLOCK_KV);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== S issuer: S_X(t) = Q_X K(t)^T, X = A then B =====================
+      constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
+      const uint64_t dq0 = make_sw128_desc(smem_u32(smem_q));
+      const uint64_t dk0 = make_sw128_desc(smem_u32(smem_k));
+      int t = 0;
+      for (int k = 0; k < n_my; ++k) {
+        const int qs = k % APP_Q_STAGES;
+        for (int j = 0; j < kv_tiles; ++j, ++t) {
+          const int ks = t % APP_K_STAGES;
+          const bool last = j == kv_tiles - 1;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (x == 0) {
+              if (j == 0) mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
+              mbar_wait(&k_full[ks], (t / APP_K_STAGES) & 1);
+            }
+            if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // warpgroup X has S_X(t-1) in registers
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t dq = dq0 + static_cast<uint64_t>((2 * qs + x) * (APP_TILE_BYTES >> 4));
+              const uint64_t dk = dk0 + static_cast<uint64_t>(ks * (APP_TILE_BYTES >> 4));
+              const uint32_t tmem_s = tmem_base + APP_COL_S + x * APP_BLOCK_KV;
+#pragma unroll
+              for (int kk = 0; kk < ATT_D / 16; ++kk) umma_ss(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+              tc_commit(&s_full[x]);
+              if (x == 1) {
+                tc_commit(&k_empty[ks]);
+                if (last) tc_commit(&q_empty[qs]);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ===================== PV issuer: O_X += P_X(t) V(t), X = A then B =====================
+      constexpr uint32_t idesc_pv = make_idesc_bf16(APP_TILE_Q, ATT_D, 0, 1);   // B = V is MN-major
+      const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
+      const int tail_ksteps = (p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV + 15) >> 4;
+      int t = 0;
+      for (int k = 0; k < n_my; ++k) {
+        for (int j = 0; j < kv_tiles; ++j, ++t) {
+          const int vs = t % APP_V_STAGES;
+          const int ksteps = j == kv_tiles - 1 ? tail_ksteps : APP_BLOCK_KV / 16;
+          mbar_wait(&v_full[vs], (t / APP_V_STAGES) & 1);
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            if (j == 0 && k > 0) mbar_wait(&o_free[x], (k - 1) & 1);   // the previous unit's O_X has been copied out
+            mbar_wait(&p_full[x], t & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t dv = dv0 + static_cast<uint64_t>(vs * (APP_TILE_BYTES >> 4));
+              const uint32_t tmem_o = tmem_base + APP_COL_O + x * ATT_D;
+              const uint32_t tmem_p = tmem_base + APP_COL_P + x * (APP_BLOCK_KV / 2);
+              // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
+              for (int kk = 0; kk < ksteps; ++kk) umma_ts(tmem_o, tmem_p + 8 * kk, dv + 128 * kk, idesc_pv, (j | kk) != 0);
+              tc_commit(&p_free[x]);
+              if (x == 1) tc_commit(&v_empty[vs]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (p.extra) {
+      // ===================== extra-token query rows (CUDA cores, background) =====================
+      const int pairs = p.n_units / q_pairs;   // (sequence, head) pairs
+      for (int i = blockIdx.x; i < pairs; i += gridDim.x)
+        attention_extra_query_warp(p, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ===================== softmax + output: warpgroup X = A (warps 4..7) or B (warps 8..11) =====================
+    const int x = (warp >> 2) - 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + APP_COL_S + x * APP_BLOCK_KV;
+    const uint32_t tmem_p = tmem_base + lane_base + APP_COL_P + x * (APP_BLOCK_KV / 2);
+    const uint32_t tmem_o = tmem_base + lane_base + APP_COL_O + x * ATT_D;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
+    constexpr int kPoly = VFM_APP_POLY;
+    int t = 0;
+#if VFM_APP_STAGGER
+    if (x == 1) mbar_wait(stagger, 0);
+#endif
+    for (int k = 0; k < n_my; ++k) {
+      const Unit un = unit_of(k);
+      const int q_tile0 = un.qp * APP_UNIT_Q + x * APP_TILE_Q;   // body index of this warpgroup's first query row
+      const bool warp_live = q_tile0 + quad * 32 < p.q_len;      // warp-uniform
+      float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f;
+      if (p.extra) {
+        // the extra key: s = q_row . k_extra on the CUDA cores; it starts the running softmax with weight 1
+        const int qs = k % APP_Q_STAGES;
+        mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
+        const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
+        const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + un.head * ATT_D);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
+          const uint4 kv = __ldg(kx + c);
+          acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
+          acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
+          acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
+          acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
+        }
+        m_ref = (acc0 + acc1) * kLog2e;
+        w_extra = 1.f;
+        l0 = 1.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the Q tile from shared memory
+      }
+
+      for (int j = 0; j < kv_tiles; ++j, ++t) {
+        mbar_wait(&s_full[x], t & 1);
+        tc_fence_after();
+        if (!warp_live) {
+          // all 32 query rows of this warp lie past the end of the sequence: keep the barrier phases moving only
+          // (p_full(t) only after PV_X(t-1): an arrival must never land in the previous, still open phase)
+          if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&s_free[x]); mbar_arrive(&p_full[x]); }
+#if VFM_APP_STAGGER
+          if (x == 0 && t == 0 && lane == 0) mbar_arrive(stagger);
+#endif
+          continue;
+        }
+        uint32_t s[128];
+        tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+        tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[x]);   // S_X(t+1) may overwrite the score columns now
+
+        const int valid = p.kv_len - j * APP_BLOCK_KV;
+        if (valid < APP_BLOCK_KV) {               // tail tile only: mask keys past the sequence end
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= valid) s[i] = 0xff800000u;   // -inf
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) m4[c] = fmax3(m4[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
+        }
+        const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+        {
+          const bool jump = m_tile > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
+          if (__any_sync(0xffffffffu, jump)) {   // rare after the first tile: rescale O in TMEM
+            const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
+            if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; }
+            if (j > 0) {
+              mbar_wait(&p_free[x], (t - 1) & 1);   // every PV_X up to tile t-1 has executed
+              tc_fence_after();
+#pragma unroll 1
+              for (int c = 0; c < ATT_D / 16; ++c) {
+                uint32_t r[16];
+                tmem_ld16(tmem_o + c * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                tmem_st16(tmem_o + c * 16, r);
+              }
+            }
+          }
+        }
+        if (t > 0) {                                     // PV_X(t-1) has read P_X: the buffer may be rewritten
+          mbar_wait(&p_free[x], (t - 1) & 1);
+          tc_fence_after();
+        }
+        const float neg_m = -m_ref;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0, x1;
+            ffma2_bc(x0, x1, __uint_as_float(s[32 * c + 2 * i]), __uint_as_float(s[32 * c + 2 * i + 1]), kLog2e, neg_m);
+            const float e0 = fast_exp2(x0);
+            const float e1 = (kPoly != 0 && ((16 * c + i) % (kPoly ? kPoly : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1);
+            fadd2_acc(l0, l1, e0, e1);
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(tmem_p + c * 16, pk);
+#if VFM_APP_STAGGER
+          if (c == 1 && x == 0 && t == 0) {   // once per CTA: let warpgroup B start half a tile behind
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stagger);
+          }
+#endif
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);
+      }
+
+      // ---- unit epilogue: copy O out of TMEM, hand the accumulator back, then normalise and store
+      mbar_wait(&p_free[x], (t - 1) & 1);   // the last PV_X of the unit (commits are ordered: all earlier ones too)
+      tc_fence_after();
+      if (!warp_live) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[x]);
+        continue;
+      }
+      uint32_t o[64];
+      tmem_ld32(tmem_o + 0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+      tmem_ld32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
+      const float inv = 1.f / (l0 + l1);
+      const int q_idx = q_tile0 + row;
+      if (q_idx < p.q_len) {
+        const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + un.head * ATT_D);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
+          if (p.extra) {
+            const uint4 xv = __ldg(vx + i);
+            v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
+            v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
+            v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
+            v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= inv;
+          dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<APP_TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace vfm
