@@ -134,5 +134,24 @@ int main(int argc, char** argv) {
            ok ? "OK " : "BAD", max_err, max_ref, worst_row, nan_ct, med, ts.empty() ? 0.f : ts[0], med > 0 ? flop / med / 1e9 : 0.0);
     fflush(stdout);
   }
+  // debug builds (-DVFM_APP_TRACE): dump the event timeline of CTA 0 of the last ping-pong launch
+  typedef int (*trace_fn)(long long*);
+  trace_fn tr = (trace_fn)dlsym(h, "vfm_debug_app_trace");
+  if (tr) {
+    std::vector<long long> buf(2052);
+    tr(buf.data());
+    const long long t0 = buf[2048];
+    printf("trace: kernel clk %lld ns %lld -> %.3f GHz\n", buf[2050] - buf[2048], buf[2051] - buf[2049],
+           (double)(buf[2050] - buf[2048]) / (double)std::max(1LL, buf[2051] - buf[2049]));
+    const char* names[4] = {"softmaxA", "softmaxB", "S-issuer", "PV-issuer"};
+    for (int w = 0; w < 4; ++w) {
+      printf("%s\n", names[w]);
+      for (int t = 0; t < 40; ++t) {
+        printf("  t%2d", t);
+        for (int e = 0; e < 8; ++e) printf(" %7lld", buf[(w * 64 + t) * 8 + e] ? buf[(w * 64 + t) * 8 + e] - t0 : -1LL);
+        printf("\n");
+      }
+    }
+  }
   return bad;
 }

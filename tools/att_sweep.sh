@@ -22,7 +22,7 @@ run $L 7 1025 16 4,5 3
 run $L 2 1025 3 4,5 3 3.0      # peaked scores: rescale path
 echo "---- timing, 36 windows x 16 heads x 1025 tokens"
 run $L 36 1025 16 1,2,4,5 20
-for v in poly2 poly4 nostag; do
+for v in nohand poly4; do
   [ -f vfmseg_b200/lib/libvfm_$v.so ] && run vfmseg_b200/lib/libvfm_$v.so 36 1025 16 4,5 20
 done
 echo "---- 18 windows"

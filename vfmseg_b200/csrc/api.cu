@@ -270,6 +270,15 @@ int vfm_prof_report(char* buf, size_t buf_bytes) {
   return VFM_OK;
 }
 
+#ifdef VFM_APP_TRACE
+// debug build only: timeline of CTA 0 of the last attention_pp_kernel launch: 4 x 64 x 8 clock64 values + 4 clock / ns values
+extern "C" int vfm_debug_app_trace(long long* out2052) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out2052, vfm::g_app_trace, 4 * 64 * 8 * sizeof(long long));
+  cudaMemcpyFromSymbol(out2052 + 2048, vfm::g_app_clk, 4 * sizeof(long long));
+  return 0;
+}
+#endif
 #ifdef VFM_EPI_TIMING
 extern "C" int vfm_debug_att_trace(long long* out640) {
   cudaDeviceSynchronize();
@@ -400,6 +409,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     if (ex && kv_total > APP_MAX_EXTRA_KEYS) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
     AttParams p{};
     p.extra = ex;
+    p.sched_mask = -1;
     p.q_len = q_total - ex; p.kv_len = kv_total - ex;
     p.q_seq_rows = q_seq_rows; p.kv_seq_rows = kv_seq_rows;
     p.q_row_off = ex; p.kv_row_off = ex;

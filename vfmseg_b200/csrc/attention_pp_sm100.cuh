@@ -24,8 +24,10 @@
 // QUERY row of each (sequence, head) is computed by warp 3 of the CTAs straight from global memory while the tensor
 // pipeline runs (1/1025 of the work; no second launch).
 //
-// Warps (384 threads): warpgroup 0 = {TMA producer, S issuer (+ TMEM allocator), PV issuer, extra-query rows},
-// setmaxnreg-trimmed; warpgroups 1, 2 = softmax A, B (TMEM lane quadrant = warp % 4).
+// Warps (384 threads): warpgroups 0, 1 = softmax A, B (TMEM lane quadrant = warp % 4); warpgroup 2 = {TMA producer,
+// S issuer (+ TMEM allocator), PV issuer, extra-query rows}, setmaxnreg-trimmed. The service warps have the HIGHEST warp
+// ids on purpose: the scheduler of an SM sub-partition prefers the higher warp id among ready warps, and an issuer warp
+// that is late by a few hundred clocks stalls a whole softmax warpgroup.
 #pragma once
 #include "attention_sm100.cuh"
 
@@ -39,7 +41,7 @@ constexpr int APP_Q_STAGES = 2, APP_K_STAGES = 3, APP_V_STAGES = 3;
 constexpr int APP_TILE_BYTES = 128 * ATT_D * 2;       // 16 KB: one Q tile, one K tile, one V tile
 constexpr int APP_MAX_EXTRA_KEYS = 4224;              // score scratch of the extra-query warp (floats)
 constexpr int APP_BAR_BYTES = 512;
-constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES) * APP_TILE_BYTES +
+constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES + 2 /* extra-query staging */) * APP_TILE_BYTES +
                                APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */;
 constexpr uint32_t APP_TMEM_COLS = 512;
 constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 128 / 64 / 64 for warpgroup X
@@ -47,14 +49,40 @@ constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 1
 #ifndef VFM_APP_POLY
 #define VFM_APP_POLY 0      // n > 0: one exponential in n is evaluated on the FMA pipe (poly_exp2) instead of MUFU
 #endif
-#ifndef VFM_APP_STAGGER
-#define VFM_APP_STAGGER 1   // warpgroup B starts half a tile behind A
+#ifndef VFM_APP_ALUPACK
+#define VFM_APP_ALUPACK 0   // 1: pack P with two integer adds + PRMT instead of F2FP (measured slower: 0.325 vs 0.301 ms)
+#endif
+#ifndef VFM_APP_HANDOFF
+#define VFM_APP_HANDOFF 1   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token)
+#endif
+
+#ifdef VFM_APP_TRACE
+// debug build: event timeline of CTA 0 — rows 0/1 softmax A/B (quad 0, lane 0), 2 S issuer, 3 PV issuer; [tile][event]
+__device__ long long g_app_trace[4][64][8];
+__device__ unsigned long long g_app_clk[4];   // clock64 / globaltimer at kernel start and end of CTA 0
+#define APP_TRACE(who, tile, ev) do { if (blockIdx.x == 0 && lane == 0 && (tile) < 64) g_app_trace[who][tile][ev] = clock64(); } while (0)
+#else
+#define APP_TRACE(who, tile, ev)
 #endif
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+// v | (later & 0x80000000): v itself whenever `later` is non-negative, but data-dependent on `later` (one LOP3)
+__device__ __forceinline__ uint32_t sign_gate(uint32_t v, uint32_t later) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xF8;" : "=r"(d) : "r"(v), "r"(later));
+  return d;
+}
+// Two non-negative fp32 bit patterns -> packed bf16x2 (lo, hi), rounded half up, on the integer pipe: two adds and one
+// PRMT. cvt.rn.bf16x2.f32 (F2FP) would be one instruction, but it executes on the same quarter-rate unit as MUFU.EX2:
+// with it the 64 packs of a tile cost the MUFU pipe another 512 clk on top of the 1024 of the 128 exponentials
+// (second GPU trace: 790 clk for the 64 FADD2 + 64 F2FP of a tile while the other warpgroup ran its exponentials).
+// Half-up differs from round-to-nearest-even only on exact ties (probability 2^-16 per value).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(uint32_t lo_bits, uint32_t hi_bits) {
+  return __byte_perm(lo_bits + 0x8000u, hi_bits + 0x8000u, 0x7632u);
 }
 // (d0, d1) = (a0, a1) * b + c as one packed FFMA2
 __device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {
@@ -73,16 +101,36 @@ __device__ __forceinline__ void fadd2_acc(float& d0, float& d1, float a0, float 
       : "f"(a0), "f"(a1));
 }
 
-// The query row of the extra token (cls) of one (sequence, head) against all kv_len + 1 keys, by ONE warp, from global
-// memory (2 x 64 x (kv_len + 1) MACs: 1/1025 of the attention work of a ViT window). Pass 1: one key per lane and step
-// (eight 16-byte loads in flight per lane), scores (log2 units) to shared memory; pass 2: the lane owns output columns
-// 2 lane, 2 lane + 1 and streams the V rows (one coalesced 128-byte row per load instruction, 16 in flight).
-__device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, int seq, int head, float* sc, float* qs) {
+// The query row of the extra token (cls) of one (sequence, head) against all kv_len + 1 keys, by ONE warp on the CUDA
+// cores (2 x 64 x (kv_len + 1) MACs: 1/1025 of the attention work of a ViT window) while the tensor pipeline of the CTA
+// runs. The K rows, then the V rows of the pair stream through a private double buffer of 128-row TMA boxes (same tensor
+// maps as the main pipeline, SWIZZLE_128B), so the warp never waits out a global-memory round trip per step: the first
+// version read K / V with plain loads (8 x 16 B per lane in flight) and took ~137 k clk per pair — four pairs per CTA
+// made it the longest chain of the kernel (0.349 ms per 36-window launch with it, ~0.25 ms worth of tile work).
+// Pass 1: lane owns keys lane, lane + 32, lane + 64, lane + 96 of a chunk: scores (log2 units) to shared memory.
+// Pass 2: lane owns output columns 2 lane, 2 lane + 1 and walks the 128 rows of a V chunk.
+// ld / use: running counts of chunk loads issued / consumed by this warp (buffer = count & 1, parity = (count >> 1) & 1).
+__device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, const CUtensorMap* tmap_k, const CUtensorMap* tmap_v,
+                                                           int seq, int head, float* sc, float* qs, uint8_t* stage,
+                                                           uint64_t* full, uint32_t& ld, uint32_t& use) {
   const int lane = threadIdx.x & 31;
   const int kv_total = p.kv_len + 1;
-  const size_t kv_row = static_cast<size_t>(seq) * p.kv_seq_rows;
-  const __nv_bfloat16* kb = p.k_ptr + kv_row * p.k_ld + p.k_col0 + head * ATT_D;
-  const __nv_bfloat16* vb = p.v_ptr + kv_row * p.v_ld + p.v_col0 + head * ATT_D;
+  const int n_chunks = (kv_total + 127) >> 7;
+  const int row0 = seq * p.kv_seq_rows;
+  auto issue = [&](int c) {   // chunk c of the pair's stream: K chunks, then V chunks
+    if (c < 2 * n_chunks) {
+      const uint32_t b = ld & 1u;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full[b], APP_TILE_BYTES);
+        if (c < n_chunks) tma_load_2d(stage + b * APP_TILE_BYTES, tmap_k, &full[b], p.k_col0 + head * ATT_D, row0 + c * 128);
+        else tma_load_2d(stage + b * APP_TILE_BYTES, tmap_v, &full[b], p.v_col0 + head * ATT_D, row0 + (c - n_chunks) * 128);
+      }
+      __syncwarp();
+      ++ld;
+    }
+  };
+  issue(0);
+  issue(1);
   {
     const uint32_t qv = __ldg(reinterpret_cast<const uint32_t*>(p.q_ptr + static_cast<size_t>(seq) * p.q_seq_rows * p.q_ld + p.q_col0 + head * ATT_D) + lane);
     qs[2 * lane] = bf16lo(qv);
@@ -90,28 +138,35 @@ __device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, i
   }
   __syncwarp();
   float m = -INFINITY;
-  for (int base = 0; base < kv_total; base += 32) {
-    const int key = base + lane;
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(min(key, kv_total - 1)) * p.k_ld);
-    uint4 kv[8];
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint32_t b = use & 1u;
+    mbar_wait(&full[b], (use >> 1) & 1u);
+    const uint8_t* tile = stage + b * APP_TILE_BYTES;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) kv[c] = __ldg(kr + c);
-    float a0 = 0.f, a1 = 0.f;
+    for (int r4 = 0; r4 < 4; ++r4) {
+      const int r = lane + 32 * r4;
+      const uint8_t* krow = tile + r * 128;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 q0 = *reinterpret_cast<const float4*>(qs + 8 * c);
-      const float4 q1 = *reinterpret_cast<const float4*>(qs + 8 * c + 4);
-      a0 = fmaf(q0.x, bf16lo(kv[c].x), a0); a1 = fmaf(q0.y, bf16hi(kv[c].x), a1);
-      a0 = fmaf(q0.z, bf16lo(kv[c].y), a0); a1 = fmaf(q0.w, bf16hi(kv[c].y), a1);
-      a0 = fmaf(q1.x, bf16lo(kv[c].z), a0); a1 = fmaf(q1.y, bf16hi(kv[c].z), a1);
-      a0 = fmaf(q1.z, bf16lo(kv[c].w), a0); a1 = fmaf(q1.w, bf16hi(kv[c].w), a1);
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 kv = *reinterpret_cast<const uint4*>(krow + ((ch ^ (r & 7)) << 4));
+        const float4 q0 = *reinterpret_cast<const float4*>(qs + 8 * ch);
+        const float4 q1 = *reinterpret_cast<const float4*>(qs + 8 * ch + 4);
+        a0 = fmaf(q0.x, bf16lo(kv.x), a0); a1 = fmaf(q0.y, bf16hi(kv.x), a1);
+        a0 = fmaf(q0.z, bf16lo(kv.y), a0); a1 = fmaf(q0.w, bf16hi(kv.y), a1);
+        a0 = fmaf(q1.x, bf16lo(kv.z), a0); a1 = fmaf(q1.y, bf16hi(kv.z), a1);
+        a0 = fmaf(q1.z, bf16lo(kv.w), a0); a1 = fmaf(q1.w, bf16hi(kv.w), a1);
+      }
+      const int key = c * 128 + r;
+      const float sv = (a0 + a1) * 1.4426950408889634f;
+      if (key < kv_total) { sc[key] = sv; m = fmaxf(m, sv); }
     }
-    const float s = (a0 + a1) * 1.4426950408889634f;
-    if (key < kv_total) { sc[key] = s; m = fmaxf(m, s); }
+    ++use;
+    __syncwarp();          // every lane has read the buffer: it may be refilled
+    issue(c + 2);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __syncwarp();
   float l = 0.f;
   for (int key = lane; key < kv_total; key += 32) {
     const float w = fast_exp2(sc[key] - m);
@@ -121,23 +176,37 @@ __device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, i
 #pragma unroll
   for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
   __syncwarp();
-  float o0 = 0.f, o1 = 0.f;
-  const uint32_t* vr = reinterpret_cast<const uint32_t*>(vb) + lane;
-  const size_t v_pitch = static_cast<size_t>(p.v_ld) / 2;   // in uint32
-  for (int base = 0; base < kv_total; base += 16) {
-    uint32_t vv[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) vv[i] = __ldg(vr + static_cast<size_t>(min(base + i, kv_total - 1)) * v_pitch);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float w = base + i < kv_total ? sc[base + i] : 0.f;
-      o0 = fmaf(w, bf16lo(vv[i]), o0);
-      o1 = fmaf(w, bf16hi(vv[i]), o1);
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint32_t b = use & 1u;
+    mbar_wait(&full[b], (use >> 1) & 1u);
+    const uint8_t* tile = stage + b * APP_TILE_BYTES;
+    const int n_valid = min(128, kv_total - c * 128);
+    const float* w = sc + c * 128;
+    // the lane's 4 bytes of row r: 16-byte chunk lane >> 2 (swizzled with r & 7), word lane & 3
+    const int cw = lane >> 2, wo = (lane & 3) * 4;
+    if (n_valid == 128) {
+#pragma unroll 8
+      for (int r = 0; r < 128; r += 2) {
+        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(tile + r * 128 + ((cw ^ (r & 7)) << 4) + wo);
+        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(tile + (r + 1) * 128 + ((cw ^ ((r + 1) & 7)) << 4) + wo);
+        const float2 ww = *reinterpret_cast<const float2*>(w + r);
+        o0 = fmaf(ww.x, bf16lo(v0), o0); o1 = fmaf(ww.x, bf16hi(v0), o1);
+        o2 = fmaf(ww.y, bf16lo(v1), o2); o3 = fmaf(ww.y, bf16hi(v1), o3);
+      }
+    } else {
+      for (int r = 0; r < n_valid; ++r) {
+        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(tile + r * 128 + ((cw ^ (r & 7)) << 4) + wo);
+        o0 = fmaf(w[r], bf16lo(v0), o0); o1 = fmaf(w[r], bf16hi(v0), o1);
+      }
     }
+    ++use;
+    __syncwarp();
+    issue(n_chunks + c + 2);
   }
   const float inv = 1.f / l;
   reinterpret_cast<uint32_t*>(p.out + static_cast<size_t>(seq) * p.q_seq_rows * p.out_ld + head * ATT_D)[lane] =
-      pack_bf16x2(o0 * inv, o1 * inv);
+      pack_bf16x2((o0 + o2) * inv, (o1 + o3) * inv);
   __syncwarp();
 }
 
@@ -149,7 +218,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* smem_q = smem;                                               // [stage][tile A | tile B]
   uint8_t* smem_k = smem_q + 2 * APP_Q_STAGES * APP_TILE_BYTES;
   uint8_t* smem_v = smem_k + APP_K_STAGES * APP_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_v + APP_V_STAGES * APP_TILE_BYTES);
+  uint8_t* smem_x = smem_v + APP_V_STAGES * APP_TILE_BYTES;             // [2] K / V chunks of the extra-query warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_x + 2 * APP_TILE_BYTES);
   uint64_t* q_full = bars;                          // [2] TMA -> S issuer, softmax (extra key)
   uint64_t* q_empty = q_full + APP_Q_STAGES;        // [2] S issuer (last S of the unit executed) [+ softmax warps] -> TMA
   uint64_t* k_full = q_empty + APP_Q_STAGES;        // [3] TMA -> S issuer
@@ -161,8 +231,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* p_full = s_free + 2;                    // [2] softmax X -> PV issuer  (P_X(t) in TMEM, O_X rescaled if needed)
   uint64_t* p_free = p_full + 2;                    // [2] PV issuer -> softmax X  (O_X += P_X(t) V(t) executed)
   uint64_t* o_free = p_free + 2;                    // [2] softmax X -> PV issuer  (O_X of the finished unit copied out)
-  uint64_t* stagger = o_free + 2;                   // [1] softmax A -> softmax B, once
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + 1);
+  uint64_t* x_full = o_free + 2;                   // [2] TMA -> extra-query warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
   float* extra_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + APP_BAR_BYTES);   // [APP_MAX_EXTRA_KEYS] (+ 64 for q)
 
   const int warp = threadIdx.x >> 5;
@@ -173,7 +243,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int first_unit = blockIdx.x, unit_step = gridDim.x;
   const int n_my = (p.n_units - first_unit + unit_step - 1) / unit_step;   // >= 1 (grid <= units)
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
@@ -184,14 +254,21 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
       mbar_init(&o_free[x], 4);
     }
-    mbar_init(stagger, 4);
+    mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef VFM_APP_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_app_clk[0] = clock64(); g_app_clk[1] = ns;
+  }
+#endif
 
   struct Unit { int q_row0, kv_row0, head, seq, qp; };
   auto unit_of = [&](int k) {
@@ -205,9 +282,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     return r;
   };
 
-  if (warp < 4) {
+  if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    if (warp == 0) {
+    if (warp == 8) {
       // ===================== TMA producer =====================
       int t = 0;
       for (int k = 0; k < n_my; ++k) {
@@ -236,7 +313,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           __syncwarp();
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
       // ===================== S issuer: S_X(t) = Q_X K(t)^T, X = A then B =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
       const uint64_t dq0 = make_sw128_desc(smem_u32(smem_q));
@@ -253,8 +330,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               if (j == 0) mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
               mbar_wait(&k_full[ks], (t / APP_K_STAGES) & 1);
             }
+            APP_TRACE(2, t, 3 * x);
             if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // warpgroup X has S_X(t-1) in registers
             tc_fence_after();
+            APP_TRACE(2, t, 3 * x + 1);
             if (elect_one_sync()) {
               const uint64_t dq = dq0 + static_cast<uint64_t>((2 * qs + x) * (APP_TILE_BYTES >> 4));
               const uint64_t dk = dk0 + static_cast<uint64_t>(ks * (APP_TILE_BYTES >> 4));
@@ -268,10 +347,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               }
             }
             __syncwarp();
+            APP_TRACE(2, t, 3 * x + 2);
           }
         }
       }
-    } else if (warp == 2) {
+    } else if (warp == 10) {
       // ===================== PV issuer: O_X += P_X(t) V(t), X = A then B =====================
       constexpr uint32_t idesc_pv = make_idesc_bf16(APP_TILE_Q, ATT_D, 0, 1);   // B = V is MN-major
       const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
@@ -284,9 +364,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           mbar_wait(&v_full[vs], (t / APP_V_STAGES) & 1);
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
+            APP_TRACE(3, t, 3 * x);
             if (j == 0 && k > 0) mbar_wait(&o_free[x], (k - 1) & 1);   // the previous unit's O_X has been copied out
             mbar_wait(&p_full[x], t & 1);
             tc_fence_after();
+            APP_TRACE(3, t, 3 * x + 1);
             if (elect_one_sync()) {
               const uint64_t dv = dv0 + static_cast<uint64_t>(vs * (APP_TILE_BYTES >> 4));
               const uint32_t tmem_o = tmem_base + APP_COL_O + x * ATT_D;
@@ -297,19 +379,35 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               if (x == 1) tc_commit(&v_empty[vs]);
             }
             __syncwarp();
+            APP_TRACE(3, t, 3 * x + 2);
           }
         }
       }
     } else if (p.extra) {
       // ===================== extra-token query rows (CUDA cores, background) =====================
       const int pairs = p.n_units / q_pairs;   // (sequence, head) pairs
+      uint32_t ld = 0, use = 0;
       for (int i = blockIdx.x; i < pairs; i += gridDim.x)
-        attention_extra_query_warp(p, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS);
+        attention_extra_query_warp(p, &tmap_k, &tmap_v, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS, smem_x,
+                                   x_full, ld, use);
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    // ===================== softmax + output: warpgroup X = A (warps 4..7) or B (warps 8..11) =====================
-    const int x = (warp >> 2) - 1;
+    // ===================== softmax + output: warpgroup X = A (warps 0..3) or B (warps 4..7) =====================
+    // Per key tile t (one query row per thread, its 128 scores in registers s[]):
+    //   reference check   m_ref moves (and O_X is rescaled) only when the tile max exceeds it by > 2^24
+    //   token             named barrier: the MUFU pipe is ours
+    //   MUFU pass         64 FFMA2 + 128 MUFU.EX2, in place in s[]; nothing else, so the pipe runs at 8 clk / instruction
+    //   token release
+    //   consumer pass     FADD2 row sums + F2FP packs + 4 x tcgen05.st of P(t) — and, chunk by chunk into the registers
+    //                     this frees, the tcgen05.ld of S(t+1), which the S issuer finished long ago; then its row max.
+    // so the only work of a tile that is not hidden behind the OTHER warpgroup's MUFU pass is what sits between the
+    // token release and the next token request. (First version of this loop: barrier wake-up, TMEM load, row max and
+    // P-buffer wait were all in front of the MUFU pass, ~1700 clk per tile against a 1240 clk MUFU pass of the other
+    // warpgroup: ncu source view of that build, profiles/r2_attn_pp_notes.txt.)
+    // Warps whose 32 rows lie past the end of the sequence are not special-cased: their rows are computed and never
+    // stored (MMA rows are independent); ViT shapes have none.
+    const int x = warp >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -319,15 +417,53 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
     constexpr int kPoly = VFM_APP_POLY;
-    int t = 0;
-#if VFM_APP_STAGGER
-    if (x == 1) mbar_wait(stagger, 0);
+    const uint32_t sched_mask = static_cast<uint32_t>(p.sched_mask);
+    const int total_tiles = n_my * kv_tiles;
+    const int tail_valid = p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV;   // keys in the last tile of a sequence (1..128)
+
+    uint32_t s[128];
+    // row max (times log2e) of the tile in s[]; keys past the end of the sequence (tail tile) are masked to -inf first
+    auto row_max = [&](int valid) {
+      if (valid < APP_BLOCK_KV) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) s[i] = 0xff800000u;
+      }
+      float m8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) m8[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
+#pragma unroll
+      for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m8[c] = fmax3(m8[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
+      }
+      return fmaxf(fmax3(m8[0], m8[1], m8[2]), fmaxf(fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * kLog2e;
+    };
+
+    // ---- prologue: the first tile of this CTA's stream
+    mbar_wait(&s_full[x], 0);
+    tc_fence_after();
+    tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+    tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+    tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_free[x]);
+    float m_next = row_max(kv_tiles == 1 ? tail_valid : APP_BLOCK_KV);
+#if VFM_APP_HANDOFF
+    // MUFU passes alternate A(t), B(t), A(t+1), ...: warpgroup X enters its pass through named barrier 1 + X (256
+    // threads: its own 128 bar.sync + the other warpgroup's 128 bar.arrive at the end of ITS pass). B opens the first
+    // A pass here. Without the token the two warpgroups drift into phase: both in their exponentials (sharing the
+    // pipe), then both in their bookkeeping (pipe idle) — 3300 clk per 256 x 128 scores in the first traces.
+    if (x == 1) named_bar_arrive(1, 256);
 #endif
+    int t = 0;
     for (int k = 0; k < n_my; ++k) {
       const Unit un = unit_of(k);
       const int q_tile0 = un.qp * APP_UNIT_Q + x * APP_TILE_Q;   // body index of this warpgroup's first query row
-      const bool warp_live = q_tile0 + quad * 32 < p.q_len;      // warp-uniform
-      float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f;
+      float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row sum = l0 + l1 + l2 + l3
       if (p.extra) {
         // the extra key: s = q_row . k_extra on the CUDA cores; it starts the running softmax with weight 1
         const int qs = k % APP_Q_STAGES;
@@ -352,47 +488,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       }
 
       for (int j = 0; j < kv_tiles; ++j, ++t) {
-        mbar_wait(&s_full[x], t & 1);
-        tc_fence_after();
-        if (!warp_live) {
-          // all 32 query rows of this warp lie past the end of the sequence: keep the barrier phases moving only
-          // (p_full(t) only after PV_X(t-1): an arrival must never land in the previous, still open phase)
-          if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);
-          __syncwarp();
-          if (lane == 0) { mbar_arrive(&s_free[x]); mbar_arrive(&p_full[x]); }
-#if VFM_APP_STAGGER
-          if (x == 0 && t == 0 && lane == 0) mbar_arrive(stagger);
-#endif
-          continue;
-        }
-        uint32_t s[128];
-        tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-        tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-        tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
-        tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[x]);   // S_X(t+1) may overwrite the score columns now
-
-        const int valid = p.kv_len - j * APP_BLOCK_KV;
-        if (valid < APP_BLOCK_KV) {               // tail tile only: mask keys past the sequence end
-#pragma unroll
-          for (int i = 0; i < 128; ++i)
-            if (i >= valid) s[i] = 0xff800000u;   // -inf
-        }
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < 128; i += 8) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) m4[c] = fmax3(m4[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
-        }
-        const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+        if (quad == 0) APP_TRACE(x, t, 0);
+        const float m_tile = m_next;
         {
           const bool jump = m_tile > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
           if (__any_sync(0xffffffffu, jump)) {   // rare after the first tile: rescale O in TMEM
             const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
-            if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; }
+            if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha; }
             if (j > 0) {
               mbar_wait(&p_free[x], (t - 1) & 1);   // every PV_X up to tile t-1 has executed
               tc_fence_after();
@@ -405,83 +507,122 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
                 tmem_st16(tmem_o + c * 16, r);
               }
+              tmem_st_wait();
             }
           }
         }
-        if (t > 0) {                                     // PV_X(t-1) has read P_X: the buffer may be rewritten
-          mbar_wait(&p_free[x], (t - 1) & 1);
-          tc_fence_after();
-        }
-        const float neg_m = -m_ref;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x0, x1;
-            ffma2_bc(x0, x1, __uint_as_float(s[32 * c + 2 * i]), __uint_as_float(s[32 * c + 2 * i + 1]), kLog2e, neg_m);
-            const float e0 = fast_exp2(x0);
-            const float e1 = (kPoly != 0 && ((16 * c + i) % (kPoly ? kPoly : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1);
-            fadd2_acc(l0, l1, e0, e1);
-            pk[i] = pack_bf16x2(e0, e1);
-          }
-          tmem_st16(tmem_p + c * 16, pk);
-#if VFM_APP_STAGGER
-          if (c == 1 && x == 0 && t == 0) {   // once per CTA: let warpgroup B start half a tile behind
-            __syncwarp();
-            if (lane == 0) mbar_arrive(stagger);
-          }
+        if (quad == 0) APP_TRACE(x, t, 3);
+#if VFM_APP_HANDOFF
+        named_bar_sync(1 + x, 256);         // the other warpgroup has issued the last exponential of its pass
 #endif
+        if (quad == 0) APP_TRACE(x, t, 4);
+        const float neg_m = -m_ref;
+        // The two passes sit under branches on bits of a kernel parameter (AttParams::sched_mask, all ones at run time).
+        // Left alone, ptxas schedules every consumer of an exponential directly behind it (the FADD2 chain looks
+        // critical to it) and the in-order warp sits out the MUFU latency once per pair: measured 28 clk per pair
+        // instead of the 16 the pipe needs. A fake data dependence on a later exponential (round 1's trick) only
+        // moves the wait, and warp-level barriers are scheduled across; real control flow is what ptxas respects.
+        const bool more = t + 1 < total_tiles;
+        if (sched_mask & 1u) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            float x0, x1;
+            ffma2_bc(x0, x1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), kLog2e, neg_m);
+            s[2 * i] = __float_as_uint(fast_exp2(x0));
+            s[2 * i + 1] = __float_as_uint((kPoly != 0 && (i % (kPoly ? kPoly : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1));
+          }
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[x]);
+        if (sched_mask & 2u) {
+#if VFM_APP_HANDOFF
+          named_bar_arrive(2 - x, 256);     // the pipe goes to the other warpgroup
+#endif
+          if (quad == 0) APP_TRACE(x, t, 7);
+          if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
+          if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int kk = 16 * c + i;
+              if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+              else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+#if VFM_APP_ALUPACK
+              pk[i] = pack_bf16x2_alu(s[2 * kk], s[2 * kk + 1]);
+#else
+              pk[i] = pack_bf16x2(__uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+#endif
+            }
+            tmem_st16(tmem_p + c * 16, pk);
+            if (more) tmem_ld32(tmem_s + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));   // into the registers just consumed
+          }
+          if (quad == 0) APP_TRACE(x, t, 5);
+          if (more) {
+            // the row max of tile t+1 is what stands between this warpgroup and its next token request: first
+            tmem_ld_wait();
+            const int jn = j + 1 == kv_tiles ? 0 : j + 1;
+            m_next = row_max(jn == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&p_full[x]);
+            if (more) mbar_arrive(&s_free[x]);   // S_X(t+2) may overwrite the score columns now
+          }
+          if (quad == 0) APP_TRACE(x, t, 6);
+        }
       }
 
-      // ---- unit epilogue: copy O out of TMEM, hand the accumulator back, then normalise and store
+      // ---- unit epilogue: O_X out of TMEM in 16-column chunks (s[] already holds the next unit's first tile),
+      // normalise, store; then hand the accumulator back
       mbar_wait(&p_free[x], (t - 1) & 1);   // the last PV_X of the unit (commits are ordered: all earlier ones too)
       tc_fence_after();
-      if (!warp_live) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[x]);
-        continue;
+      const float inv = 1.f / ((l0 + l1) + (l2 + l3));
+      const int q_idx = q_tile0 + row;
+      const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + un.head * ATT_D);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
+#pragma unroll 1
+      for (int c = 0; c < ATT_D / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld16(tmem_o + c * 16, o);
+        tmem_ld_wait();
+        if (q_idx < p.q_len) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
+            if (p.extra) {
+              const uint4 xv = __ldg(vx + 2 * c + i);
+              v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
+              v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
+              v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
+              v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= inv;
+            dst[2 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+        }
       }
-      uint32_t o[64];
-      tmem_ld32(tmem_o + 0, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      tmem_ld32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&o[32]));
-      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
-      const float inv = 1.f / (l0 + l1);
-      const int q_idx = q_tile0 + row;
-      if (q_idx < p.q_len) {
-        const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + un.head * ATT_D);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
-          if (p.extra) {
-            const uint4 xv = __ldg(vx + i);
-            v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
-            v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
-            v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
-            v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= inv;
-          dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
-      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+#ifdef VFM_APP_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    g_app_clk[2] = clock64(); g_app_clk[3] = ns;
+  }
+#endif
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<APP_TMEM_COLS>(tmem_base);
   }

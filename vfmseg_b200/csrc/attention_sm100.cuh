@@ -68,6 +68,7 @@ struct AttParams {
   int q_col0, k_col0, v_col0;   // column of (head 0, d 0) in the Q / K / V matrices
   int extra;                    // 1: row 0 of each K/V sequence is one more key, handled on the CUDA cores
   int n_units;                  // (sequence, head, query tile) units, dealt round-robin to the persistent CTAs
+  int sched_mask;               // all ones; the ping-pong kernel branches on its bits to pin its instruction schedule
   const __nv_bfloat16* q_ptr; int q_ld;
   const __nv_bfloat16* k_ptr;   // raw pointers for the extra key / value row
   const __nv_bfloat16* v_ptr;
