@@ -42,7 +42,7 @@ constexpr int APP_TILE_BYTES = 128 * ATT_D * 2;       // 16 KB: one Q tile, one 
 constexpr int APP_MAX_EXTRA_KEYS = 4224;              // score scratch of the extra-query warp (floats)
 constexpr int APP_BAR_BYTES = 512;
 constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES + 2 /* extra-query staging */) * APP_TILE_BYTES +
-                               APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */;
+                               APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */ + 2 * 2 * 2 * 128 * 4 /* row max / sum exchange */;
 constexpr uint32_t APP_TMEM_COLS = 512;
 constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 128 / 64 / 64 for warpgroup X
 
@@ -210,7 +210,189 @@ __device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, c
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(APP_THREADS, 1)
+__device__ __forceinline__ bool named_bar_red_or(int id, int count, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "barrier.cta.red.or.pred p, %2, %3, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "r"(id), "r"(count)
+      : "memory");
+  return out != 0;
+}
+
+// Softmax + output role of attention_pp_kernel<2>: 16 warps. Warp w: TMEM lane quadrant quad = w & 3, query tile X =
+// (w >> 2) & 1 (A or B), column half h = w >> 3. A thread owns one query row of tile X and the key columns [64 h, 64 h + 64)
+// of every key tile; its partner (same lane, warp w ^ 8) owns the other half of the same row. Both keep the same
+// reference max m_ref: a tile's two half maxima are only exchanged (shared memory + a 64-thread named barrier) when one
+// of the 64 rows x 2 halves of the warp pair needs the reference moved, which one barrier.red.or per tile finds out.
+// Why: with one row per thread (kSplit = 1) two softmax warps share an SM sub-partition and each warp's per-tile chain —
+// barrier polls, TMEM load, row max, 64 packs, TMEM store, arrives: ~1700 clk around a 1050 clk MUFU pass — is mostly
+// latency that only the ONE other warp can cover (ncu: issue slots 38 % busy, MUFU 50 %, nothing saturated). Four
+// warps per sub-partition cover it the way a GPU is meant to.
+__device__ __forceinline__ void attention_pp_softmax_split(const AttParams& p, uint32_t tmem_base, const uint8_t* smem_q, uint64_t* q_full,
+                                                           uint64_t* q_empty, uint64_t* s_full, uint64_t* s_free, uint64_t* p_full,
+                                                           uint64_t* p_free, uint64_t* o_free, float* xch, int first_unit, int unit_step,
+                                                           int n_my, int kv_tiles, int q_pairs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, x = (warp >> 2) & 1, h = warp >> 3;
+  const int row = quad * 32 + lane;
+  const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+  const uint32_t tmem_s = tmem_base + lane_base + APP_COL_S + x * APP_BLOCK_KV + h * 64;
+  const uint32_t tmem_p = tmem_base + lane_base + APP_COL_P + x * (APP_BLOCK_KV / 2) + h * 32;
+  const uint32_t tmem_o = tmem_base + lane_base + APP_COL_O + x * ATT_D + h * 32;   // this half's 32 output columns
+  const int pair_bar = 1 + x * 4 + quad;                                           // named barrier of the warp pair (64 threads)
+  float* xm_mine = xch + ((0 * 2 + x) * 2 + h) * 128 + row;
+  float* xm_other = xch + ((0 * 2 + x) * 2 + (h ^ 1)) * 128 + row;
+  float* xl_mine = xch + ((1 * 2 + x) * 2 + h) * 128 + row;
+  float* xl_other = xch + ((1 * 2 + x) * 2 + (h ^ 1)) * 128 + row;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
+  const int tail_valid = p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV;   // keys in the last tile of a sequence (1..128)
+  int t = 0;
+  for (int k = 0; k < n_my; ++k) {
+    const int u = first_unit + k * unit_step;
+    const int qp = u % q_pairs, head = (u / q_pairs) % p.heads, seq = u / (q_pairs * p.heads);
+    const int q_idx = qp * APP_UNIT_Q + x * APP_TILE_Q + row;   // body index of this thread's query row
+    float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f;
+    if (p.extra) {
+      // the extra key: s = q_row . k_extra on the CUDA cores (both halves compute it; half 0 carries its weight 1)
+      const int qs = k % APP_Q_STAGES;
+      mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
+      const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
+      const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + head * ATT_D);
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
+        const uint4 kv = __ldg(kx + c);
+        acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
+        acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
+        acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
+        acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
+      }
+      m_ref = (acc0 + acc1) * kLog2e;
+      w_extra = 1.f;
+      if (h == 0) l0 = 1.f;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the Q tile from shared memory
+    }
+
+    for (int j = 0; j < kv_tiles; ++j, ++t) {
+      mbar_wait(&s_full[x], t & 1);
+      tc_fence_after();
+      uint32_t s[64];
+      tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[x]);   // S_X(t+1) may overwrite the score columns now
+      const int valid = (j == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV) - 64 * h;   // live keys in this half (<= 0: none)
+      if (valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) s[i] = 0xff800000u;   // -inf
+      }
+      float m4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m4[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
+#pragma unroll
+      for (int i = 8; i < 64; i += 8) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m4[c] = fmax3(m4[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
+      }
+      const float m_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+      // does any row of the warp pair need its reference moved? (always on a unit's first tile)
+      const bool want = m_half > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
+      if (named_bar_red_or(pair_bar, 64, want)) {
+        *xm_mine = m_half;
+        named_bar_sync(pair_bar, 64);
+        const float m_tile = fmaxf(m_half, *xm_other);
+        const bool jump = m_tile > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
+        const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
+        if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; }
+        if (j > 0) {   // rescale this half's 32 columns of O_X (every PV_X up to tile t-1 has executed)
+          mbar_wait(&p_free[x], (t - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[16];
+            tmem_ld16(tmem_o + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(tmem_o + c * 16, r);
+          }
+        }
+      }
+      if (t > 0) {   // PV_X(t-1) has read P_X: the buffer may be rewritten
+        mbar_wait(&p_free[x], (t - 1) & 1);
+        tc_fence_after();
+      }
+      const float neg_m = -m_ref;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0, x1;
+          ffma2_bc(x0, x1, __uint_as_float(s[32 * c + 2 * i]), __uint_as_float(s[32 * c + 2 * i + 1]), kLog2e, neg_m);
+          const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          fadd2_acc(l0, l1, e0, e1);
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+        tmem_st16(tmem_p + c * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+
+    // ---- unit epilogue: row sum = both halves' partial sums; this half normalises and stores 32 of the 64 columns
+    *xl_mine = l0 + l1;
+    named_bar_sync(pair_bar, 64);
+    const float inv = 1.f / ((l0 + l1) + *xl_other);
+    mbar_wait(&p_free[x], (t - 1) & 1);   // the last PV_X of the unit (commits are ordered: all earlier ones too)
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld32(tmem_o, o);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
+    if (q_idx < p.q_len) {
+      const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + head * ATT_D) + 4 * h;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + head * ATT_D) + 4 * h;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
+        if (p.extra) {
+          const uint4 xv = __ldg(vx + i);
+          v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
+          v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
+          v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
+          v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= inv;
+        dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
+    }
+  }
+}
+
+
+// kSplit = 1: 8 softmax warps, one query row (128 scores per key tile) per thread.
+// kSplit = 2: 16 softmax warps, two threads per query row — warps w and w + 8 own the same 32 rows, key columns
+//             [0, 64) and [64, 128) of every tile — so four softmax warps share each SM sub-partition instead of two.
+template <int kSplit>
+__global__ void __launch_bounds__(32 * (8 * kSplit + 4), 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -235,6 +417,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
   float* extra_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + APP_BAR_BYTES);   // [APP_MAX_EXTRA_KEYS] (+ 64 for q)
 
+  float* xch = extra_sc + APP_MAX_EXTRA_KEYS + 64;   // [2 kinds][2 X][2 halves][128 rows]: row max / row sum exchange (kSplit = 2)
+
+  constexpr int kSW = 8 * kSplit;                   // softmax warps; the four service warps follow
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -243,21 +428,21 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int first_unit = blockIdx.x, unit_step = gridDim.x;
   const int n_my = (p.n_units - first_unit + unit_step - 1) / unit_step;   // >= 1 (grid <= units)
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kSW && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 9 : 1); }
+    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 1 + kSW : 1); }
     for (int s = 0; s < APP_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < APP_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
-      mbar_init(&o_free[x], 4);
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4 * kSplit); mbar_init(&p_full[x], 4 * kSplit); mbar_init(&p_free[x], 1);
+      mbar_init(&o_free[x], 4 * kSplit);
     }
     mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
+  if (warp == kSW + 1) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -282,9 +467,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     return r;
   };
 
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    if (warp == 8) {
+  if (warp >= kSW) {
+    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == kSW) {
       // ===================== TMA producer =====================
       int t = 0;
       for (int k = 0; k < n_my; ++k) {
@@ -313,7 +499,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           __syncwarp();
         }
       }
-    } else if (warp == 9) {
+    } else if (warp == kSW + 1) {
       // ===================== S issuer: S_X(t) = Q_X K(t)^T, X = A then B =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
       const uint64_t dq0 = make_sw128_desc(smem_u32(smem_q));
@@ -351,7 +537,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
-    } else if (warp == 10) {
+    } else if (warp == kSW + 2) {
       // ===================== PV issuer: O_X += P_X(t) V(t), X = A then B =====================
       constexpr uint32_t idesc_pv = make_idesc_bf16(APP_TILE_Q, ATT_D, 0, 1);   // B = V is MN-major
       const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
@@ -391,6 +577,10 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         attention_extra_query_warp(p, &tmap_k, &tmap_v, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS, smem_x,
                                    x_full, ld, use);
     }
+  } else if constexpr (kSplit == 2) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    attention_pp_softmax_split(p, tmem_base, smem_q, q_full, q_empty, s_full, s_free, p_full, p_free, o_free, xch, first_unit, unit_step,
+                               n_my, kv_tiles, q_pairs);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ===================== softmax + output: warpgroup X = A (warps 0..3) or B (warps 4..7) =====================
@@ -622,7 +812,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     g_app_clk[2] = clock64(); g_app_clk[3] = ns;
   }
 #endif
-  if (warp == 9) {
+  if (warp == kSW + 1) {
     tc_fence_after();
     tmem_dealloc<APP_TMEM_COLS>(tmem_base);
   }
