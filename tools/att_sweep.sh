@@ -2,7 +2,7 @@
 # Correctness matrix + timing of the attention kernels through the C ABI (tools/att_bench.cu). Run under gpurun.
 cd "$(dirname "$0")/.."
 B=tools/bin/att_bench; L=vfmseg_b200/lib/libvfmseg_b200.so
-run() { echo "== $*"; timeout 90 $B "$@"; rc=$?; [ $rc -ne 0 ] && echo "   exit code $rc"; return $rc; }
+run() { echo "== $*"; timeout 25 $B "$@"; rc=$?; [ $rc -ne 0 ] && echo "   exit code $rc"; [ $rc -eq 124 ] && { echo "TIMEOUT: abort"; exit 1; }; return $rc; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv,noheader
 run $L 1 128 1 1,4 3 || exit 1
 run $L 2 256 2 1,4 3 || exit 1

@@ -396,17 +396,15 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
                      int kv_total, int heads, int mode, cudaStream_t st) {
   if (!q || !k || !v || !out || n_seq <= 0 || q_total <= 0 || kv_total <= 0 || heads <= 0)
     return fail(VFM_ERR_INVALID, "attention: bad args");
-  if (mode < 0 || mode > 7) return fail(VFM_ERR_INVALID, "attention: mode must be 0..7");
+  if (mode < 0 || mode > 5) return fail(VFM_ERR_INVALID, "attention: mode must be 0..5");
   if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
   if (mode == 0) {   // experiment knob (tools/): VFM_ATT_MODE=1|2|3 overrides the automatic choice
     static const int forced = [] { const char* e = std::getenv("VFM_ATT_MODE"); return e ? std::atoi(e) : 0; }();
-    if (forced >= 1 && forced <= 7 && !((forced == 2 || forced == 5 || forced == 7) && (q_total != kv_total || kv_total < 2))) mode = forced;
+    if (forced >= 1 && forced <= 5 && !((forced == 2 || forced == 5) && (q_total != kv_total || kv_total < 2))) mode = forced;
   }
   if (mode >= 4) {
-    // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM;
-    // 4 / 5: one thread per query row, 6 / 7: two threads per row (16 softmax warps); odd = extra-token split
+    // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM; 5 = extra-token split
     const int ex = mode & 1;
-    const bool split = mode >= 6;
     if (ex && (q_total != kv_total || kv_total < 2)) return fail(VFM_ERR_INVALID, "attention: extra-token mode needs q_total == kv_total >= 2");
     if (ex && kv_total > APP_MAX_EXTRA_KEYS) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
     AttParams p{};
@@ -430,8 +428,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     if ((rc = make_tmap(&tv, v, kv_rows, v_col0 + heads * ATT_D, v_ld, 128))) return rc;
     static bool attr_pp = false;
     if (!attr_pp) {
-      VFM_CUDA(cudaFuncSetAttribute(attention_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
-      VFM_CUDA(cudaFuncSetAttribute(attention_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
+      VFM_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
       attr_pp = true;
     }
     const long long units = static_cast<long long>(n_seq) * heads * p.q_tiles;
@@ -442,8 +439,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     const unsigned grid = static_cast<unsigned>(units < n_sm ? units : n_sm);
     {
       LaunchScope scope("attention_pp", st);
-      if (split) attention_pp_kernel<2><<<grid, 32 * 20, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
-      else attention_pp_kernel<1><<<grid, 32 * 12, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
+      attention_pp_kernel<<<grid, APP_THREADS, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
     }
     VFM_LAUNCH_CHECK("attention_pp");
     return VFM_OK;

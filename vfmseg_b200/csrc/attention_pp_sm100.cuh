@@ -8,26 +8,37 @@
 // reference check, store + arrive) around ~700 clk of exponentials, the MUFU pipe (the real ceiling at head_dim 64:
 // 1024 clk of ex2 per 128 x 128 scores against 512 clk of MMA) was busy ~half of the time.
 // Here ONE persistent CTA per SM owns all 512 TMEM columns and works on units of 256 query rows:
-//   * two softmax warpgroups A / B (128 rows each, one row per thread) share every K / V tile and run half a tile
-//     period apart, so the fixed per-tile cost of one hides under the exponentials of the other;
+//   * two softmax warpgroups A / B (128 rows each, one row per thread) share every K / V tile and take turns on the MUFU
+//     pipe (a named-barrier token per SM sub-partition), so the bookkeeping of one hides under the exponentials of the
+//     other;
 //   * 128-key tiles: half as many barrier round trips per score, S = Q K^T as N = 128 MMAs (64.5 clk per k-step
 //     against 2 x 48.5 for two N = 64 ones: the N = 64 form is bound by the shared-memory read of A);
 //   * S, P and O all have their own TMEM columns (S_A S_B 2 x 128 fp32, P_A P_B 2 x 64 packed bf16, O_A O_B 2 x 64
-//     fp32 = 512), so S_X(t+1) is issued the moment warpgroup X has copied S_X(t) to registers — not behind
+//     fp32 = 512), so S_X(t+1) is issued the moment S_X(t) has been copied to registers — not behind
 //     P_X(t) -> PV_X(t) as the aliased layout forces — and is ready long before X comes back for it;
-//   * the row sums are kept in registers (packed FADD2), the row max uses the 3-input FMNMX, the scale/subtract is a
-//     packed FFMA2, P is rounded to nearest (cvt.rn.bf16x2), not truncated;
+//   * a HELPER warpgroup (one warp per TMEM lane quadrant) takes everything off the softmax warps that is not
+//     exponentials and packing: it computes the row maxima of every S tile straight from TMEM as soon as the tile
+//     lands (a whole tile period before the softmax warp needs them) and publishes them through shared memory, and it
+//     writes the finished units out (O from TMEM, extra key's value row, 1 / row sum, store). Second trace of the
+//     first ping-pong version (profiles/r2_attn_pp_*): per tile a softmax warp spent ~1100-1250 clk in its
+//     exponential pass and ~1850 clk outside it (two mbarrier waits ~100 clk each even when complete, TMEM load wait +
+//     43-instruction row max ~220, 4 pack/store chunks ~460, fences + arrives ~150, loop + vote ~120), and the unit
+//     epilogue — wait for the last PV, four dependent TMEM load -> global load -> store rounds, next unit's key row
+//     from global memory — another ~7900 clk per unit (21 % of the kernel): the chain of ONE warp, not the MUFU pipe
+//     (2 x 1024 clk per tile pair), set the pace. The softmax chain outside the pass must be shorter than the other
+//     warpgroup's pass for the pipe to stay busy;
+//   * the row sums are kept in registers (packed FADD2), the scale/subtract is a packed FFMA2, P is rounded to
+//     nearest (cvt.rn.bf16x2), not truncated;
 //   * the S MMAs and the PV MMAs are issued by two different warps (tcgen05.mma blocks its issuing thread while the
 //     pipe is busy), each serving A then B in a fixed order.
 // "Extra token" mode (ViT sequences = 1 cls token + n x 128 patch tokens): the tensor tiles cover the body tokens; the
-// cls KEY is one dot product per query row on the CUDA cores (before the loop) and one AXPY in the epilogue; the cls
-// QUERY row of each (sequence, head) is computed by warp 3 of the CTAs straight from global memory while the tensor
-// pipeline runs (1/1025 of the work; no second launch).
+// cls KEY is one dot product per query row on the CUDA cores (key row staged in shared memory by the TMA warp) and one
+// AXPY in the epilogue; the cls QUERY row of each (sequence, head) is computed by a service warp on the CUDA cores while
+// the tensor pipeline runs (1/1025 of the work; no second launch).
 //
-// Warps (384 threads): warpgroups 0, 1 = softmax A, B (TMEM lane quadrant = warp % 4); warpgroup 2 = {TMA producer,
-// S issuer (+ TMEM allocator), PV issuer, extra-query rows}, setmaxnreg-trimmed. The service warps have the HIGHEST warp
-// ids on purpose: the scheduler of an SM sub-partition prefers the higher warp id among ready warps, and an issuer warp
-// that is late by a few hundred clocks stalls a whole softmax warpgroup.
+// Warps (512 threads): 0-3 softmax A, 4-7 softmax B (TMEM lane quadrant = warp % 4); 8 TMA producer, 9 S issuer
+// (+ TMEM allocator), 10 PV issuer, 11 extra-query rows; 12-15 helper (quadrant = warp % 4). setmaxnreg: softmax 200,
+// everything else 56 (256 x 200 + 256 x 56 = 65536 = the pool of a 512-thread CTA launched at 128 registers).
 #pragma once
 #include "attention_sm100.cuh"
 
@@ -36,13 +47,16 @@ namespace vfm {
 constexpr int APP_TILE_Q = 128;                       // query rows per softmax warpgroup
 constexpr int APP_UNIT_Q = 2 * APP_TILE_Q;            // query rows per unit
 constexpr int APP_BLOCK_KV = 128;
-constexpr int APP_THREADS = 384;
+constexpr int APP_THREADS = 512;
 constexpr int APP_Q_STAGES = 2, APP_K_STAGES = 3, APP_V_STAGES = 3;
+constexpr int APP_XR_STAGES = 8;                     // ring of (extra key row | extra value row) pairs, one per unit (see the helper's epilogue)
 constexpr int APP_TILE_BYTES = 128 * ATT_D * 2;       // 16 KB: one Q tile, one K tile, one V tile
 constexpr int APP_MAX_EXTRA_KEYS = 4224;              // score scratch of the extra-query warp (floats)
 constexpr int APP_BAR_BYTES = 512;
+constexpr int APP_XCH_BYTES = 2 * 128 * 4 /* row max [X][row] */ + 2 * 2 * 128 * 8 /* (row sum, extra weight) [X][unit parity][row] */;
 constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES + 2 /* extra-query staging */) * APP_TILE_BYTES +
-                               APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */ + 2 * 2 * 2 * 128 * 4 /* row max / sum exchange */;
+                               APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */ + APP_XCH_BYTES +
+                               APP_XR_STAGES * 256 /* extra key row | extra value row of a unit */;
 constexpr uint32_t APP_TMEM_COLS = 512;
 constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 128 / 64 / 64 for warpgroup X
 
@@ -51,10 +65,25 @@ constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 1
 #endif
 #ifndef VFM_APP_ALUPACK
 #define VFM_APP_ALUPACK 0   // 1: pack P with two integer adds + PRMT instead of F2FP (measured slower: 0.325 vs 0.301 ms)
-#endif
+#endif                      // 2: one PRMT (truncation) of exponentials pre-scaled by 1 + kTruncEps (see kTruncEps)
+// ALUPACK 2: P = trunc_bf16(e (1 + eps)) with the factor folded into the exponent argument (free), so the truncation's
+// mean loss of half a bf16 ulp (2^-8 / (1 + f) relative, f the mantissa fraction) is cancelled in the mean: weighted by
+// the value itself E[ulp / 2] / E[x] = 2^-8 / 1.5. The fp32 row sums are accumulated from the SAME pre-scaled values and
+// divided by 1 + eps in the epilogue. Error per weight: uniform in about (-0.5, 0.5] ulp like round-to-nearest.
+// Measured (tools/micro/xu_share_bench.cu): F2FP does NOT share the MUFU pipe (ex2 8.09 clk / warp instruction with or
+// without a co-resident F2FP stream at 2.08), so the variant only saves issue slots: 0.299 vs 0.297 ms, not the default.
+constexpr float kTruncEps = 0.00390625f / 1.5f;
+constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #ifndef VFM_APP_HANDOFF
-#define VFM_APP_HANDOFF 1   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token)
+#define VFM_APP_HANDOFF 2   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token):
+#endif                      // 1 = one token per warpgroup pair (256 threads), 2 = one per SM sub-partition (warp pair, 64 threads)
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x the register count ptxas reports for
+// the kernel), not the 64 K of the SM; a sum above the pool dead-locks the last warp's setmaxnreg.inc.
+#ifndef VFM_APP_SOFTMAX_REGS
+#define VFM_APP_SOFTMAX_REGS 200
+#define VFM_APP_SERVICE_REGS 56
 #endif
+static_assert(256 * VFM_APP_SOFTMAX_REGS + 256 * VFM_APP_SERVICE_REGS <= 512 * 128, "setmaxnreg budget exceeds the CTA's register pool");
 
 #ifdef VFM_APP_TRACE
 // debug build: event timeline of CTA 0 — rows 0/1 softmax A/B (quad 0, lane 0), 2 S issuer, 3 PV issuer; [tile][event]
@@ -210,189 +239,17 @@ __device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, c
   __syncwarp();
 }
 
-__device__ __forceinline__ bool named_bar_red_or(int id, int count, bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.u32 q, %1, 0;\n\t"
-      "barrier.cta.red.or.pred p, %2, %3, q;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(out)
-      : "r"(static_cast<uint32_t>(pred)), "r"(id), "r"(count)
-      : "memory");
-  return out != 0;
-}
 
-// Softmax + output role of attention_pp_kernel<2>: 16 warps. Warp w: TMEM lane quadrant quad = w & 3, query tile X =
-// (w >> 2) & 1 (A or B), column half h = w >> 3. A thread owns one query row of tile X and the key columns [64 h, 64 h + 64)
-// of every key tile; its partner (same lane, warp w ^ 8) owns the other half of the same row. Both keep the same
-// reference max m_ref: a tile's two half maxima are only exchanged (shared memory + a 64-thread named barrier) when one
-// of the 64 rows x 2 halves of the warp pair needs the reference moved, which one barrier.red.or per tile finds out.
-// Why: with one row per thread (kSplit = 1) two softmax warps share an SM sub-partition and each warp's per-tile chain —
-// barrier polls, TMEM load, row max, 64 packs, TMEM store, arrives: ~1700 clk around a 1050 clk MUFU pass — is mostly
-// latency that only the ONE other warp can cover (ncu: issue slots 38 % busy, MUFU 50 %, nothing saturated). Four
-// warps per sub-partition cover it the way a GPU is meant to.
-__device__ __forceinline__ void attention_pp_softmax_split(const AttParams& p, uint32_t tmem_base, const uint8_t* smem_q, uint64_t* q_full,
-                                                           uint64_t* q_empty, uint64_t* s_full, uint64_t* s_free, uint64_t* p_full,
-                                                           uint64_t* p_free, uint64_t* o_free, float* xch, int first_unit, int unit_step,
-                                                           int n_my, int kv_tiles, int q_pairs) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = warp & 3, x = (warp >> 2) & 1, h = warp >> 3;
-  const int row = quad * 32 + lane;
-  const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-  const uint32_t tmem_s = tmem_base + lane_base + APP_COL_S + x * APP_BLOCK_KV + h * 64;
-  const uint32_t tmem_p = tmem_base + lane_base + APP_COL_P + x * (APP_BLOCK_KV / 2) + h * 32;
-  const uint32_t tmem_o = tmem_base + lane_base + APP_COL_O + x * ATT_D + h * 32;   // this half's 32 output columns
-  const int pair_bar = 1 + x * 4 + quad;                                           // named barrier of the warp pair (64 threads)
-  float* xm_mine = xch + ((0 * 2 + x) * 2 + h) * 128 + row;
-  float* xm_other = xch + ((0 * 2 + x) * 2 + (h ^ 1)) * 128 + row;
-  float* xl_mine = xch + ((1 * 2 + x) * 2 + h) * 128 + row;
-  float* xl_other = xch + ((1 * 2 + x) * 2 + (h ^ 1)) * 128 + row;
-  constexpr float kLog2e = 1.4426950408889634f;
-  constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
-  const int tail_valid = p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV;   // keys in the last tile of a sequence (1..128)
-  int t = 0;
-  for (int k = 0; k < n_my; ++k) {
-    const int u = first_unit + k * unit_step;
-    const int qp = u % q_pairs, head = (u / q_pairs) % p.heads, seq = u / (q_pairs * p.heads);
-    const int q_idx = qp * APP_UNIT_Q + x * APP_TILE_Q + row;   // body index of this thread's query row
-    float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f;
-    if (p.extra) {
-      // the extra key: s = q_row . k_extra on the CUDA cores (both halves compute it; half 0 carries its weight 1)
-      const int qs = k % APP_Q_STAGES;
-      mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
-      const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
-      const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + head * ATT_D);
-      float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
-        const uint4 kv = __ldg(kx + c);
-        acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
-        acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
-        acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
-        acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
-      }
-      m_ref = (acc0 + acc1) * kLog2e;
-      w_extra = 1.f;
-      if (h == 0) l0 = 1.f;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the Q tile from shared memory
-    }
-
-    for (int j = 0; j < kv_tiles; ++j, ++t) {
-      mbar_wait(&s_full[x], t & 1);
-      tc_fence_after();
-      uint32_t s[64];
-      tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-      tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[x]);   // S_X(t+1) may overwrite the score columns now
-      const int valid = (j == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV) - 64 * h;   // live keys in this half (<= 0: none)
-      if (valid < 64) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i >= valid) s[i] = 0xff800000u;   // -inf
-      }
-      float m4[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) m4[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
-#pragma unroll
-      for (int i = 8; i < 64; i += 8) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) m4[c] = fmax3(m4[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
-      }
-      const float m_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
-      // does any row of the warp pair need its reference moved? (always on a unit's first tile)
-      const bool want = m_half > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
-      if (named_bar_red_or(pair_bar, 64, want)) {
-        *xm_mine = m_half;
-        named_bar_sync(pair_bar, 64);
-        const float m_tile = fmaxf(m_half, *xm_other);
-        const bool jump = m_tile > m_ref + (j == 0 ? 0.f : kRescaleThreshold);
-        const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
-        if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; }
-        if (j > 0) {   // rescale this half's 32 columns of O_X (every PV_X up to tile t-1 has executed)
-          mbar_wait(&p_free[x], (t - 1) & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[16];
-            tmem_ld16(tmem_o + c * 16, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st16(tmem_o + c * 16, r);
-          }
-        }
-      }
-      if (t > 0) {   // PV_X(t-1) has read P_X: the buffer may be rewritten
-        mbar_wait(&p_free[x], (t - 1) & 1);
-        tc_fence_after();
-      }
-      const float neg_m = -m_ref;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float x0, x1;
-          ffma2_bc(x0, x1, __uint_as_float(s[32 * c + 2 * i]), __uint_as_float(s[32 * c + 2 * i + 1]), kLog2e, neg_m);
-          const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
-          fadd2_acc(l0, l1, e0, e1);
-          pk[i] = pack_bf16x2(e0, e1);
-        }
-        tmem_st16(tmem_p + c * 16, pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
-    }
-
-    // ---- unit epilogue: row sum = both halves' partial sums; this half normalises and stores 32 of the 64 columns
-    *xl_mine = l0 + l1;
-    named_bar_sync(pair_bar, 64);
-    const float inv = 1.f / ((l0 + l1) + *xl_other);
-    mbar_wait(&p_free[x], (t - 1) & 1);   // the last PV_X of the unit (commits are ordered: all earlier ones too)
-    tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(tmem_o, o);
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
-    if (q_idx < p.q_len) {
-      const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + head * ATT_D) + 4 * h;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + head * ATT_D) + 4 * h;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
-        if (p.extra) {
-          const uint4 xv = __ldg(vx + i);
-          v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
-          v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
-          v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
-          v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= inv;
-        dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      }
-    }
-  }
-}
-
-
-// kSplit = 1: 8 softmax warps, one query row (128 scores per key tile) per thread.
-// kSplit = 2: 16 softmax warps, two threads per query row — warps w and w + 8 own the same 32 rows, key columns
-//             [0, 64) and [64, 128) of every tile — so four softmax warps share each SM sub-partition instead of two.
-template <int kSplit>
-__global__ void __launch_bounds__(32 * (8 * kSplit + 4), 1)
+// See the file header for the roles. Barrier protocol (all mbarriers; parity = use count of the slot & 1):
+//   q_full / q_empty [2]   TMA -> S issuer, softmax (extra key) / S issuer (last S of the unit) [+ 8 softmax warps] -> TMA
+//   k_full / k_empty [3]   TMA -> S issuer / S issuer (S_A, S_B of the tile executed) -> TMA;   v_full / v_empty likewise (PV)
+//   s_full [X]             S issuer -> helper               S_X(t) is in TMEM
+//   m_full [X][quad]       helper warp -> softmax warp      row maxima of S_X(t) are in shared memory (=> S_X(t) is in TMEM)
+//   s_free [X]             4 softmax + 4 helper warps -> S issuer   S_X(t) has been read: S_X(t+1) may overwrite it
+//   p_full [X] / p_free [X]  softmax -> PV issuer (P_X(t) stored) / PV issuer -> softmax (PV_X(t) executed)
+//   l_full [X][quad]       softmax warp -> helper warp      the unit's row sums are in shared memory
+//   o_ready [X] / o_free [X]  PV issuer -> helper (last PV_X of the unit executed) / helper -> PV issuer (O_X copied out)
+__global__ void __launch_bounds__(APP_THREADS, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -402,24 +259,28 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* smem_v = smem_k + APP_K_STAGES * APP_TILE_BYTES;
   uint8_t* smem_x = smem_v + APP_V_STAGES * APP_TILE_BYTES;             // [2] K / V chunks of the extra-query warp
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_x + 2 * APP_TILE_BYTES);
-  uint64_t* q_full = bars;                          // [2] TMA -> S issuer, softmax (extra key)
-  uint64_t* q_empty = q_full + APP_Q_STAGES;        // [2] S issuer (last S of the unit executed) [+ softmax warps] -> TMA
-  uint64_t* k_full = q_empty + APP_Q_STAGES;        // [3] TMA -> S issuer
-  uint64_t* k_empty = k_full + APP_K_STAGES;        // [3] S issuer (S_A, S_B of the tile executed) -> TMA
-  uint64_t* v_full = k_empty + APP_K_STAGES;        // [3] TMA -> PV issuer
-  uint64_t* v_empty = v_full + APP_V_STAGES;        // [3] PV issuer (PV_A, PV_B of the tile executed) -> TMA
-  uint64_t* s_full = v_empty + APP_V_STAGES;        // [2] S issuer -> softmax X   (S_X(t) in TMEM)
-  uint64_t* s_free = s_full + 2;                    // [2] softmax X -> S issuer   (S_X(t) copied to registers)
-  uint64_t* p_full = s_free + 2;                    // [2] softmax X -> PV issuer  (P_X(t) in TMEM, O_X rescaled if needed)
-  uint64_t* p_free = p_full + 2;                    // [2] PV issuer -> softmax X  (O_X += P_X(t) V(t) executed)
-  uint64_t* o_free = p_free + 2;                    // [2] softmax X -> PV issuer  (O_X of the finished unit copied out)
-  uint64_t* x_full = o_free + 2;                   // [2] TMA -> extra-query warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_full + 2);
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = q_full + APP_Q_STAGES;
+  uint64_t* k_full = q_empty + APP_Q_STAGES;
+  uint64_t* k_empty = k_full + APP_K_STAGES;
+  uint64_t* v_full = k_empty + APP_K_STAGES;
+  uint64_t* v_empty = v_full + APP_V_STAGES;
+  uint64_t* s_full = v_empty + APP_V_STAGES;        // [2]
+  uint64_t* s_free = s_full + 2;                    // [2]
+  uint64_t* p_full = s_free + 2;                    // [2]
+  uint64_t* p_free = p_full + 2;                    // [2]
+  uint64_t* o_ready = p_free + 2;                   // [2]
+  uint64_t* o_free = o_ready + 2;                   // [2]
+  uint64_t* x_full = o_free + 2;                    // [2] TMA -> extra-query warp
+  uint64_t* m_full = x_full + 2;                    // [2][4]
+  uint64_t* l_full = m_full + 8;                    // [2][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_full + 8);
+  static_assert((2 + 2 + 3 * APP_K_STAGES / 3 * 0 + 2 * APP_K_STAGES + 2 * APP_V_STAGES + 7 * 2 + 16) * 8 + 8 <= APP_BAR_BYTES, "barrier block too small");
   float* extra_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + APP_BAR_BYTES);   // [APP_MAX_EXTRA_KEYS] (+ 64 for q)
+  float* m_smem = extra_sc + APP_MAX_EXTRA_KEYS + 64;                       // [X][row]: row max (log2 units) of the current S_X tile
+  float2* lw_smem = reinterpret_cast<float2*>(m_smem + 2 * 128);           // [X][unit parity][row]: (row sum, extra key's weight)
+  uint8_t* smem_xr = reinterpret_cast<uint8_t*>(lw_smem + 2 * 2 * 128);    // [APP_XR_STAGES][extra key row | extra value row] (64 bf16 each)
 
-  float* xch = extra_sc + APP_MAX_EXTRA_KEYS + 64;   // [2 kinds][2 X][2 halves][128 rows]: row max / row sum exchange (kSplit = 2)
-
-  constexpr int kSW = 8 * kSplit;                   // softmax warps; the four service warps follow
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -427,22 +288,24 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int q_pairs = p.q_tiles;   // units per (sequence, head)
   const int first_unit = blockIdx.x, unit_step = gridDim.x;
   const int n_my = (p.n_units - first_unit + unit_step - 1) / unit_step;   // >= 1 (grid <= units)
+  const int total_tiles = n_my * kv_tiles;
+  const int tail_valid = p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV;         // keys in the last tile of a sequence (1..128)
 
-  if (warp == kSW && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 1 + kSW : 1); }
+    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 9 : 1); }
     for (int s = 0; s < APP_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < APP_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4 * kSplit); mbar_init(&p_full[x], 4 * kSplit); mbar_init(&p_free[x], 1);
-      mbar_init(&o_free[x], 4 * kSplit);
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 8); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
+      mbar_init(&o_ready[x], 1); mbar_init(&o_free[x], 4); mbar_init(&x_full[x], 1);
     }
-    mbar_init(&x_full[0], 1); mbar_init(&x_full[1], 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&m_full[i], 1); mbar_init(&l_full[i], 1); }
     fence_barrier_init();
   }
-  if (warp == kSW + 1) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
+  if (warp == 9) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -467,10 +330,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     return r;
   };
 
-  if (warp >= kSW) {
-    if constexpr (kSplit == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == kSW) {
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(VFM_APP_SERVICE_REGS));
+    if (warp == 8) {
       // ===================== TMA producer =====================
       int t = 0;
       for (int k = 0; k < n_my; ++k) {
@@ -478,9 +340,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int qs = k % APP_Q_STAGES;
         mbar_wait(&q_empty[qs], ((k / APP_Q_STAGES) & 1) ^ 1);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&q_full[qs], 2 * APP_TILE_BYTES);
+          mbar_arrive_expect_tx(&q_full[qs], 2 * APP_TILE_BYTES + (p.extra ? 256 : 0));
           tma_load_2d(smem_q + (2 * qs) * APP_TILE_BYTES, &tmap_q, &q_full[qs], p.q_col0 + un.head * ATT_D, un.q_row0);
           tma_load_2d(smem_q + (2 * qs + 1) * APP_TILE_BYTES, &tmap_q, &q_full[qs], p.q_col0 + un.head * ATT_D, un.q_row0 + APP_TILE_Q);
+          if (p.extra) {   // row 0 of the sequence's K and V (this head): read from shared memory by the softmax / helper threads
+            uint8_t* xr = smem_xr + (k % APP_XR_STAGES) * 256;
+            bulk_load_1d(xr, p.k_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + un.head * ATT_D, 128, &q_full[qs]);
+            bulk_load_1d(xr + 128, p.v_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + un.head * ATT_D, 128, &q_full[qs]);
+          }
         }
         __syncwarp();
         for (int j = 0; j < kv_tiles; ++j, ++t) {
@@ -499,7 +366,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           __syncwarp();
         }
       }
-    } else if (warp == kSW + 1) {
+    } else if (warp == 9) {
       // ===================== S issuer: S_X(t) = Q_X K(t)^T, X = A then B =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
       const uint64_t dq0 = make_sw128_desc(smem_u32(smem_q));
@@ -517,7 +384,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               mbar_wait(&k_full[ks], (t / APP_K_STAGES) & 1);
             }
             APP_TRACE(2, t, 3 * x);
-            if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // warpgroup X has S_X(t-1) in registers
+            if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // S_X(t-1) has been read by the softmax and the helper warps
             tc_fence_after();
             APP_TRACE(2, t, 3 * x + 1);
             if (elect_one_sync()) {
@@ -537,16 +404,17 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
-    } else if (warp == kSW + 2) {
+    } else if (warp == 10) {
       // ===================== PV issuer: O_X += P_X(t) V(t), X = A then B =====================
       constexpr uint32_t idesc_pv = make_idesc_bf16(APP_TILE_Q, ATT_D, 0, 1);   // B = V is MN-major
       const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
-      const int tail_ksteps = (p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV + 15) >> 4;
+      const int tail_ksteps = (tail_valid + 15) >> 4;
       int t = 0;
       for (int k = 0; k < n_my; ++k) {
         for (int j = 0; j < kv_tiles; ++j, ++t) {
           const int vs = t % APP_V_STAGES;
-          const int ksteps = j == kv_tiles - 1 ? tail_ksteps : APP_BLOCK_KV / 16;
+          const bool last = j == kv_tiles - 1;
+          const int ksteps = last ? tail_ksteps : APP_BLOCK_KV / 16;
           mbar_wait(&v_full[vs], (t / APP_V_STAGES) & 1);
 #pragma unroll
           for (int x = 0; x < 2; ++x) {
@@ -562,6 +430,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               // A: 16 bf16 of P per step = 8 TMEM columns; B: 16 key rows of V = 2048 B
               for (int kk = 0; kk < ksteps; ++kk) umma_ts(tmem_o, tmem_p + 8 * kk, dv + 128 * kk, idesc_pv, (j | kk) != 0);
               tc_commit(&p_free[x]);
+              if (last) tc_commit(&o_ready[x]);
               if (x == 1) tc_commit(&v_empty[vs]);
             }
             __syncwarp();
@@ -569,32 +438,118 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
-    } else if (p.extra) {
+    } else if (warp == 11) {
       // ===================== extra-token query rows (CUDA cores, background) =====================
-      const int pairs = p.n_units / q_pairs;   // (sequence, head) pairs
-      uint32_t ld = 0, use = 0;
-      for (int i = blockIdx.x; i < pairs; i += gridDim.x)
-        attention_extra_query_warp(p, &tmap_k, &tmap_v, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS, smem_x,
-                                   x_full, ld, use);
+      if (p.extra) {
+        const int pairs = p.n_units / q_pairs;   // (sequence, head) pairs
+        uint32_t ld = 0, use = 0;
+        for (int i = blockIdx.x; i < pairs; i += gridDim.x)
+          attention_extra_query_warp(p, &tmap_k, &tmap_v, i / p.heads, i % p.heads, extra_sc, extra_sc + APP_MAX_EXTRA_KEYS, smem_x,
+                                     x_full, ld, use);
+      }
+    } else {
+      // ===================== helper: row maxima of every S tile, output of every finished unit =====================
+      const int quad = warp & 3;
+      const int row = quad * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+      constexpr float kLog2e = 1.4426950408889634f;
+      // Output of unit k: O_X out of TMEM in 16-column chunks, + the extra key's value row, normalised, stored; then the
+      // accumulator goes back to the PV issuer. Runs two tiles after the unit's last one (the unit's last PV has
+      // completed by then, so nothing here waits), between two row-maximum jobs.
+      auto unit_output = [&](int k) {
+        const Unit un = unit_of(k);
+        const uint4* vx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256 + 128);
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&l_full[x * 4 + quad], k & 1);
+          const float2 lw = lw_smem[(x * 2 + (k & 1)) * 128 + row];
+          mbar_wait(&o_ready[x], k & 1);
+          tc_fence_after();
+          const float inv = 1.f / lw.x;
+          const int q_idx = un.qp * APP_UNIT_Q + x * APP_TILE_Q + row;   // body index of this thread's query row
+          const bool live = q_idx < p.q_len;
+          uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
+          const uint32_t tmem_o = tmem_base + lane_base + APP_COL_O + x * ATT_D;
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + c * 16, o);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
+                if (p.extra) {
+                  const uint4 xv = vx[2 * c + i];
+                  v[0] = fmaf(lw.y, bf16lo(xv.x), v[0]); v[1] = fmaf(lw.y, bf16hi(xv.x), v[1]);
+                  v[2] = fmaf(lw.y, bf16lo(xv.y), v[2]); v[3] = fmaf(lw.y, bf16hi(xv.y), v[3]);
+                  v[4] = fmaf(lw.y, bf16lo(xv.z), v[4]); v[5] = fmaf(lw.y, bf16hi(xv.z), v[5]);
+                  v[6] = fmaf(lw.y, bf16lo(xv.w), v[6]); v[7] = fmaf(lw.y, bf16hi(xv.w), v[7]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= inv;
+                dst[2 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
+        }
+      };
+      int t = 0;
+      for (int k = 0; k < n_my; ++k) {
+        for (int j = 0; j < kv_tiles; ++j, ++t) {
+          const int valid = j == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV;
+#pragma unroll 1
+          for (int x = 0; x < 2; ++x) {
+            mbar_wait(&s_full[x], t & 1);
+            tc_fence_after();
+            const uint32_t tmem_s = tmem_base + lane_base + APP_COL_S + x * APP_BLOCK_KV;
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tmem_s + 32 * c, r);
+              tmem_ld_wait();
+              if (valid < 32 * c + 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (32 * c + i >= valid) r[i] = 0xff800000u;   // keys past the end of the sequence
+              }
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) m4[e] = fmax3(m4[e], __uint_as_float(r[i + 2 * e]), __uint_as_float(r[i + 2 * e + 1]));
+              }
+            }
+            m_smem[x * 128 + row] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(&m_full[x * 4 + quad]);
+              mbar_arrive(&s_free[x]);
+            }
+          }
+          // the unit that ended two tiles ago (its last PV has executed by now; see the deadlock note at APP_XR_STAGES)
+          if (t >= 2 && (t - 2) % kv_tiles == kv_tiles - 1) unit_output((t - 2) / kv_tiles);
+        }
+      }
+      for (int tt = total_tiles; tt < total_tiles + 2; ++tt)
+        if (tt >= 2 && (tt - 2) % kv_tiles == kv_tiles - 1 && (tt - 2) / kv_tiles < n_my) unit_output((tt - 2) / kv_tiles);
     }
-  } else if constexpr (kSplit == 2) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    attention_pp_softmax_split(p, tmem_base, smem_q, q_full, q_empty, s_full, s_free, p_full, p_free, o_free, xch, first_unit, unit_step,
-                               n_my, kv_tiles, q_pairs);
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    // ===================== softmax + output: warpgroup X = A (warps 0..3) or B (warps 4..7) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(VFM_APP_SOFTMAX_REGS));
+    // ===================== softmax: warpgroup X = A (warps 0..3) or B (warps 4..7) =====================
     // Per key tile t (one query row per thread, its 128 scores in registers s[]):
-    //   reference check   m_ref moves (and O_X is rescaled) only when the tile max exceeds it by > 2^24
+    //   reference check   m_ref moves (and O_X is rescaled) only when the tile max (from the helper) exceeds it by > 2^24
     //   token             named barrier: the MUFU pipe is ours
     //   MUFU pass         64 FFMA2 + 128 MUFU.EX2, in place in s[]; nothing else, so the pipe runs at 8 clk / instruction
     //   token release
     //   consumer pass     FADD2 row sums + F2FP packs + 4 x tcgen05.st of P(t) — and, chunk by chunk into the registers
-    //                     this frees, the tcgen05.ld of S(t+1), which the S issuer finished long ago; then its row max.
-    // so the only work of a tile that is not hidden behind the OTHER warpgroup's MUFU pass is what sits between the
-    // token release and the next token request. (First version of this loop: barrier wake-up, TMEM load, row max and
-    // P-buffer wait were all in front of the MUFU pass, ~1700 clk per tile against a 1240 clk MUFU pass of the other
-    // warpgroup: ncu source view of that build, profiles/r2_attn_pp_notes.txt.)
+    //                     this frees, the tcgen05.ld of S(t+1), which the S issuer finished long ago.
     // Warps whose 32 rows lie past the end of the sequence are not special-cased: their rows are computed and never
     // stored (MMA rows are independent); ViT shapes have none.
     const int x = warp >> 2;
@@ -608,30 +563,26 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
     constexpr int kPoly = VFM_APP_POLY;
     const uint32_t sched_mask = static_cast<uint32_t>(p.sched_mask);
-    const int total_tiles = n_my * kv_tiles;
-    const int tail_valid = p.kv_len - (kv_tiles - 1) * APP_BLOCK_KV;   // keys in the last tile of a sequence (1..128)
+    uint64_t* my_m_full = &m_full[x * 4 + quad];
+    const float* my_m = m_smem + x * 128 + row;
+#if VFM_APP_HANDOFF == 2
+    const int bar_mine = 1 + 2 * quad + x, bar_other = 1 + 2 * quad + (x ^ 1);
+    constexpr int kBarThreads = 64;
+#else
+    const int bar_mine = 1 + x, bar_other = 2 - x;
+    constexpr int kBarThreads = 256;
+#endif
 
     uint32_t s[128];
-    // row max (times log2e) of the tile in s[]; keys past the end of the sequence (tail tile) are masked to -inf first
-    auto row_max = [&](int valid) {
-      if (valid < APP_BLOCK_KV) {
+    auto mask_tail = [&]() {   // keys past the end of the sequence (tail tile) count as -inf
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= valid) s[i] = 0xff800000u;
-      }
-      float m8[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) m8[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
-#pragma unroll
-      for (int i = 16; i < 128; i += 16) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) m8[c] = fmax3(m8[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
-      }
-      return fmaxf(fmax3(m8[0], m8[1], m8[2]), fmaxf(fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * kLog2e;
+      for (int i = 0; i < 128; ++i)
+        if (i >= tail_valid) s[i] = 0xff800000u;
     };
 
     // ---- prologue: the first tile of this CTA's stream
-    mbar_wait(&s_full[x], 0);
+    mbar_wait(my_m_full, 0);
+    float m_next = *my_m;
     tc_fence_after();
     tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
     tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -641,30 +592,30 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_free[x]);
-    float m_next = row_max(kv_tiles == 1 ? tail_valid : APP_BLOCK_KV);
+    if (kv_tiles == 1 && tail_valid < APP_BLOCK_KV) mask_tail();
 #if VFM_APP_HANDOFF
-    // MUFU passes alternate A(t), B(t), A(t+1), ...: warpgroup X enters its pass through named barrier 1 + X (256
-    // threads: its own 128 bar.sync + the other warpgroup's 128 bar.arrive at the end of ITS pass). B opens the first
-    // A pass here. Without the token the two warpgroups drift into phase: both in their exponentials (sharing the
-    // pipe), then both in their bookkeeping (pipe idle) — 3300 clk per 256 x 128 scores in the first traces.
-    if (x == 1) named_bar_arrive(1, 256);
+    // MUFU passes alternate A(t), B(t), A(t+1), ...: a warp enters its pass through a named barrier (its own bar.sync +
+    // the bar.arrive of its partner at the end of ITS pass). B opens the first A pass here. Without the token the two
+    // warpgroups drift into phase: both in their exponentials (sharing the pipe), then both in their bookkeeping (pipe
+    // idle) — 3300 clk per 256 x 128 scores in the first traces. HANDOFF 2: the token is per SM sub-partition (the A and B
+    // warps of one TMEM lane quadrant share a scheduler and a MUFU unit; the four pairs need not wait for each other).
+    if (x == 1) named_bar_arrive(bar_other, kBarThreads);
 #endif
     int t = 0;
     for (int k = 0; k < n_my; ++k) {
-      const Unit un = unit_of(k);
-      const int q_tile0 = un.qp * APP_UNIT_Q + x * APP_TILE_Q;   // body index of this warpgroup's first query row
+      const int qs = k % APP_Q_STAGES;
       float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row sum = l0 + l1 + l2 + l3
       if (p.extra) {
-        // the extra key: s = q_row . k_extra on the CUDA cores; it starts the running softmax with weight 1
-        const int qs = k % APP_Q_STAGES;
+        // the extra key: s = q_row . k_extra on the CUDA cores (both rows from shared memory); it starts the running
+        // softmax with weight 1
         mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
         const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
-        const uint4* kx = reinterpret_cast<const uint4*>(p.k_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.k_ld + p.k_col0 + un.head * ATT_D);
+        const uint4* kx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256);
         float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
-          const uint4 kv = __ldg(kx + c);
+          const uint4 kv = kx[c];
           acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
           acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
           acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
@@ -672,9 +623,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         m_ref = (acc0 + acc1) * kLog2e;
         w_extra = 1.f;
+#if VFM_APP_ALUPACK != 2
         l0 = 1.f;
+#endif
         __syncwarp();
-        if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the Q tile from shared memory
+        if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the stage's Q tile
       }
 
       for (int j = 0; j < kv_tiles; ++j, ++t) {
@@ -703,10 +656,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         if (quad == 0) APP_TRACE(x, t, 3);
 #if VFM_APP_HANDOFF
-        named_bar_sync(1 + x, 256);         // the other warpgroup has issued the last exponential of its pass
+        named_bar_sync(bar_mine, kBarThreads);   // the partner has issued the last exponential of its pass
 #endif
         if (quad == 0) APP_TRACE(x, t, 4);
+#if VFM_APP_ALUPACK == 2
+        const float neg_m = kTruncLog2 - m_ref;
+#else
         const float neg_m = -m_ref;
+#endif
         // The two passes sit under branches on bits of a kernel parameter (AttParams::sched_mask, all ones at run time).
         // Left alone, ptxas schedules every consumer of an exponential directly behind it (the FADD2 chain looks
         // critical to it) and the in-order warp sits out the MUFU latency once per pair: measured 28 clk per pair
@@ -724,12 +681,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         if (sched_mask & 2u) {
 #if VFM_APP_HANDOFF
-          named_bar_arrive(2 - x, 256);     // the pipe goes to the other warpgroup
+          named_bar_arrive(bar_other, kBarThreads);   // the pipe goes to the partner
 #endif
           if (quad == 0) APP_TRACE(x, t, 7);
-          if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
           if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
+          if (more) {
+            mbar_wait(my_m_full, (t + 1) & 1);   // S_X(t+1) is in TMEM and its row maxima are published
+            m_next = *my_m;
+          }
           tc_fence_after();
+          if (quad == 0) APP_TRACE(x, t, 1);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[16];
@@ -738,7 +699,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               const int kk = 16 * c + i;
               if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
               else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
-#if VFM_APP_ALUPACK
+#if VFM_APP_ALUPACK == 2
+              pk[i] = __byte_perm(s[2 * kk], s[2 * kk + 1], 0x7632u);
+#elif VFM_APP_ALUPACK
               pk[i] = pack_bf16x2_alu(s[2 * kk], s[2 * kk + 1]);
 #else
               pk[i] = pack_bf16x2(__uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
@@ -748,12 +711,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (more) tmem_ld32(tmem_s + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));   // into the registers just consumed
           }
           if (quad == 0) APP_TRACE(x, t, 5);
-          if (more) {
-            // the row max of tile t+1 is what stands between this warpgroup and its next token request: first
-            tmem_ld_wait();
-            const int jn = j + 1 == kv_tiles ? 0 : j + 1;
-            m_next = row_max(jn == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV);
-          }
+          tmem_ld_wait();
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -761,45 +719,20 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_arrive(&p_full[x]);
             if (more) mbar_arrive(&s_free[x]);   // S_X(t+2) may overwrite the score columns now
           }
+          if (more && tail_valid < APP_BLOCK_KV && (j + 1 == kv_tiles ? kv_tiles == 1 : j + 2 == kv_tiles)) mask_tail();
           if (quad == 0) APP_TRACE(x, t, 6);
         }
       }
 
-      // ---- unit epilogue: O_X out of TMEM in 16-column chunks (s[] already holds the next unit's first tile),
-      // normalise, store; then hand the accumulator back
-      mbar_wait(&p_free[x], (t - 1) & 1);   // the last PV_X of the unit (commits are ordered: all earlier ones too)
-      tc_fence_after();
-      const float inv = 1.f / ((l0 + l1) + (l2 + l3));
-      const int q_idx = q_tile0 + row;
-      const uint4* vx = reinterpret_cast<const uint4*>(p.v_ptr + static_cast<size_t>(un.seq) * p.kv_seq_rows * p.v_ld + p.v_col0 + un.head * ATT_D);
-      uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
-#pragma unroll 1
-      for (int c = 0; c < ATT_D / 16; ++c) {
-        uint32_t o[16];
-        tmem_ld16(tmem_o + c * 16, o);
-        tmem_ld_wait();
-        if (q_idx < p.q_len) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
-            if (p.extra) {
-              const uint4 xv = __ldg(vx + 2 * c + i);
-              v[0] = fmaf(w_extra, bf16lo(xv.x), v[0]); v[1] = fmaf(w_extra, bf16hi(xv.x), v[1]);
-              v[2] = fmaf(w_extra, bf16lo(xv.y), v[2]); v[3] = fmaf(w_extra, bf16hi(xv.y), v[3]);
-              v[4] = fmaf(w_extra, bf16lo(xv.z), v[4]); v[5] = fmaf(w_extra, bf16hi(xv.z), v[5]);
-              v[6] = fmaf(w_extra, bf16lo(xv.w), v[6]); v[7] = fmaf(w_extra, bf16hi(xv.w), v[7]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] *= inv;
-            dst[2 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          }
-        }
-      }
-      tc_fence_before();
+      // ---- the unit's row sums go to the helper warp of this quadrant, which writes the unit out
+#if VFM_APP_ALUPACK == 2
+      const float l_total = ((l0 + l1) + (l2 + l3)) * (1.f / (1.f + kTruncEps)) + w_extra;
+#else
+      const float l_total = (l0 + l1) + (l2 + l3);
+#endif
+      lw_smem[(x * 2 + (k & 1)) * 128 + row] = make_float2(l_total, w_extra);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
+      if (lane == 0) mbar_arrive(&l_full[x * 4 + quad]);
     }
   }
 
@@ -812,7 +745,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     g_app_clk[2] = clock64(); g_app_clk[3] = ns;
   }
 #endif
-  if (warp == kSW + 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<APP_TMEM_COLS>(tmem_base);
   }
