@@ -130,14 +130,21 @@ def _attn_ref(qkv, n_seq, S, heads):
     # counts per unit (buffer / phase parity across unit boundaries), one- and two-tile units, extra-token mode
     (20, 257, 12, 0), (20, 257, 12, 2), (40, 65, 8, 1), (600, 17, 1, 0), (300, 129, 2, 2), (7, 1025, 16, 0),
     # mode 3: the serial four-CTAs-per-SM kernel
-    (1, 128, 1, 3), (3, 1025, 4, 3), (2, 197, 2, 3), (1, 2049, 2, 3), (2, 17, 2, 3), (20, 257, 12, 3)])
+    (1, 128, 1, 3), (3, 1025, 4, 3), (2, 197, 2, 3), (1, 2049, 2, 3), (2, 17, 2, 3), (20, 257, 12, 3),
+    # modes 4 / 5: the ping-pong kernel (256-query units, 128-key tiles, one CTA per SM; 5 = extra-token split, what mode 0
+    # picks for ViT windows). Ragged query / key tails, several units per CTA, ONE key tile per unit (40 x 65: a softmax warp
+    # can run two units ahead of the output warps — the barrier-parity case that dead-locked during development), 36 windows
+    (1, 128, 1, 4), (2, 256, 2, 4), (1, 1024, 2, 4), (3, 1025, 4, 4), (3, 1025, 4, 5), (2, 197, 2, 4), (2, 197, 2, 5),
+    (1, 2049, 2, 4), (1, 2049, 2, 5), (2, 17, 2, 4), (2, 17, 2, 5), (2, 2, 1, 5), (1, 385, 3, 5), (2, 641, 2, 4),
+    (20, 257, 12, 4), (20, 257, 12, 5), (40, 65, 8, 4), (40, 65, 8, 5), (600, 17, 1, 5), (300, 129, 2, 4), (300, 129, 2, 5),
+    (7, 1025, 16, 5), (36, 1025, 16, 0)])
 def test_attention(ops, n_seq, S, heads, mode):
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=21, dtype=torch.bfloat16)
     out = ops.attention_fwd(qkv, n_seq, S, heads, mode)
     _close(out, _attn_ref(qkv, n_seq, S, heads), 2e-2, 2e-2, f"attention S={S} heads={heads} mode={mode}")
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 4, 5])
 def test_attention_peaked(ops, mode):
     # large-magnitude scores: exercises the online-softmax rescaling (and the rescaling of the split-off key's weight)
     n_seq, S, heads = 1, 1025, 2
@@ -153,8 +160,9 @@ def test_attention_modes_agree(ops):
     n_seq, S, heads = 2, 1025, 3
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=31, dtype=torch.bfloat16)
     a = ops.attention_fwd(qkv, n_seq, S, heads, 1).float()
-    b = ops.attention_fwd(qkv, n_seq, S, heads, 2).float()
-    assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item()
+    for mode in (2, 4, 5):
+        b = ops.attention_fwd(qkv, n_seq, S, heads, mode).float()
+        assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item(), mode
 
 
 @pytest.mark.parametrize("n_seq,Lq,Lkv,heads", [(2, 1024, 1024, 8), (1, 100, 333, 2), (3, 256, 64, 1)])

@@ -402,6 +402,15 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     static const int forced = [] { const char* e = std::getenv("VFM_ATT_MODE"); return e ? std::atoi(e) : 0; }();
     if (forced >= 1 && forced <= 5 && !((forced == 2 || forced == 5) && (q_total != kv_total || kv_total < 2))) mode = forced;
   }
+  if (mode == 0) {
+    // Automatic choice. ViT windows (1 cls token + a multiple of 256 patch tokens, self attention): the ping-pong kernel in
+    // extra-token mode, whatever the number of windows (the choice must not depend on the batch: a window gives the same
+    // bits alone and inside a pass of 36, tests/test_e2e_gpu.py) — 0.263 ms per 36 x 16 x 1025 launch against 0.303
+    // (mode 1), 0.320 (mode 4) and 0.269 for cuDNN's SDPA on the same box (profiles/r2_attn_library_comparator.json).
+    // Everything else: the round-1 kernel over every token.
+    const int body = kv_total - 1;
+    if (q_total == kv_total && body >= 512 && body % APP_UNIT_Q == 0 && kv_total <= APP_MAX_EXTRA_KEYS) mode = 5;
+  }
   if (mode >= 4) {
     // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM; 5 = extra-token split
     const int ex = mode & 1;
@@ -438,7 +447,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     if (n_sm <= 0) return fail(VFM_ERR_CUDA, "attention: no CUDA device");
     const unsigned grid = static_cast<unsigned>(units < n_sm ? units : n_sm);
     {
-      LaunchScope scope("attention_pp", st);
+      LaunchScope scope("attention_fwd", st);   // same family as the round-1 kernel in the per-launch profile (bench.py roofline.families)
       attention_pp_kernel<<<grid, APP_THREADS, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
     }
     VFM_LAUNCH_CHECK("attention_pp");
@@ -447,7 +456,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
   bool extra = mode == 2;
   // mode 0: plain tiles. The split saves a ninth query tile and a seventeenth key tile at 1025 tokens, but measured
   // 0.189 vs 0.167 ms on B200: its per-CTA prologue/epilogue loads and the appended query CTAs cost more than the tiles.
-  if (mode == 0) extra = false;
+  if (mode == 0) extra = false;   // (unreachable with mode 5 chosen above; kept for the non-ViT shapes: mode 0 == mode 1)
   if (extra && (q_total != kv_total || kv_total < 2)) return fail(VFM_ERR_INVALID, "attention: extra-token mode needs q_total == kv_total >= 2");
   AttParams p{};
   p.extra = extra ? 1 : 0;

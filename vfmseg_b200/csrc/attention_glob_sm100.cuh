@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(GLB_THREADS, 2)
 attention_glob_kernel(const __grid_constant__ CUtensorMap tmap64, const __grid_constant__ CUtensorMap tmap16,
                       const __grid_constant__ CUtensorMap tmap_e, const GlobParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (an integer round trip makes every access generic)
   uint8_t* sQ0 = smem;                       // SWIZZLE_128B tiles first
   uint8_t* sQB = sQ0 + GLB_Q64;              // [NA][128 x 64] bias terms of the query rows: rel_h (bh cols) | rel_w (bw cols)
   uint8_t* sK0 = sQB + NA * GLB_Q64;

@@ -16,17 +16,14 @@
 //   * S, P and O all have their own TMEM columns (S_A S_B 2 x 128 fp32, P_A P_B 2 x 64 packed bf16, O_A O_B 2 x 64
 //     fp32 = 512), so S_X(t+1) is issued the moment S_X(t) has been copied to registers — not behind
 //     P_X(t) -> PV_X(t) as the aliased layout forces — and is ready long before X comes back for it;
-//   * a HELPER warpgroup (one warp per TMEM lane quadrant) takes everything off the softmax warps that is not
-//     exponentials and packing: it computes the row maxima of every S tile straight from TMEM as soon as the tile
-//     lands (a whole tile period before the softmax warp needs them) and publishes them through shared memory, and it
-//     writes the finished units out (O from TMEM, extra key's value row, 1 / row sum, store). Second trace of the
-//     first ping-pong version (profiles/r2_attn_pp_*): per tile a softmax warp spent ~1100-1250 clk in its
-//     exponential pass and ~1850 clk outside it (two mbarrier waits ~100 clk each even when complete, TMEM load wait +
-//     43-instruction row max ~220, 4 pack/store chunks ~460, fences + arrives ~150, loop + vote ~120), and the unit
-//     epilogue — wait for the last PV, four dependent TMEM load -> global load -> store rounds, next unit's key row
-//     from global memory — another ~7900 clk per unit (21 % of the kernel): the chain of ONE warp, not the MUFU pipe
-//     (2 x 1024 clk per tile pair), set the pace. The softmax chain outside the pass must be shorter than the other
-//     warpgroup's pass for the pipe to stay busy;
+//   * four OUTPUT warps (one per TMEM lane quadrant) write the finished units out (O from TMEM, + the extra key's value
+//     row, x 1 / row sum, store) while the softmax warps are already in the next unit. In the first ping-pong version the
+//     softmax warps did it themselves between two units: wait for the last PV, four dependent TMEM load -> global load ->
+//     store rounds, then the next unit's key row from global memory — ~7900 clk per unit, 21 % of the kernel
+//     (profiles/r2_attn_pp_trace_*). Tried and dropped: the same warps also computing the row maxima of every S tile
+//     straight from TMEM for the softmax warps (profiles/r2_attn_pp_trace_helper_wg.txt): S is then read from TMEM twice,
+//     the TMEM read port (64 B / clk per sub-partition, 256 clk per warp and tile) is shared with the softmax warps'
+//     own loads and the maxima arrive late — 0.324 ms against 0.285;
 //   * the row sums are kept in registers (packed FADD2), the scale/subtract is a packed FFMA2, P is rounded to
 //     nearest (cvt.rn.bf16x2), not truncated;
 //   * the S MMAs and the PV MMAs are issued by two different warps (tcgen05.mma blocks its issuing thread while the
@@ -37,7 +34,7 @@
 // the tensor pipeline runs (1/1025 of the work; no second launch).
 //
 // Warps (512 threads): 0-3 softmax A, 4-7 softmax B (TMEM lane quadrant = warp % 4); 8 TMA producer, 9 S issuer
-// (+ TMEM allocator), 10 PV issuer, 11 extra-query rows; 12-15 helper (quadrant = warp % 4). setmaxnreg: softmax 200,
+// (+ TMEM allocator), 10 PV issuer, 11 extra-query rows; 12-15 output (quadrant = warp % 4). setmaxnreg: softmax 200,
 // everything else 56 (256 x 200 + 256 x 56 = 65536 = the pool of a 512-thread CTA launched at 128 registers).
 #pragma once
 #include "attention_sm100.cuh"
@@ -53,7 +50,7 @@ constexpr int APP_XR_STAGES = 8;                     // ring of (extra key row |
 constexpr int APP_TILE_BYTES = 128 * ATT_D * 2;       // 16 KB: one Q tile, one K tile, one V tile
 constexpr int APP_MAX_EXTRA_KEYS = 4224;              // score scratch of the extra-query warp (floats)
 constexpr int APP_BAR_BYTES = 512;
-constexpr int APP_XCH_BYTES = 2 * 128 * 4 /* row max [X][row] */ + 2 * 2 * 128 * 8 /* (row sum, extra weight) [X][unit parity][row] */;
+constexpr int APP_XCH_BYTES = 2 * 2 * 128 * 8 /* (row sum, extra weight) [X][unit parity][row] */ + 2 * 2 * 128 * 4 /* extra key's score [X][unit parity][row] */;
 constexpr int APP_SMEM_BYTES = 1024 /* alignment slack */ + (2 * APP_Q_STAGES + APP_K_STAGES + APP_V_STAGES + 2 /* extra-query staging */) * APP_TILE_BYTES +
                                APP_BAR_BYTES + APP_MAX_EXTRA_KEYS * 4 + 64 * 4 /* extra query row */ + APP_XCH_BYTES +
                                APP_XR_STAGES * 256 /* extra key row | extra value row of a unit */;
@@ -74,8 +71,19 @@ constexpr uint32_t APP_COL_S = 0, APP_COL_P = 256, APP_COL_O = 384;   // + X * 1
 // without a co-resident F2FP stream at 2.08), so the variant only saves issue slots: 0.299 vs 0.297 ms, not the default.
 constexpr float kTruncEps = 0.00390625f / 1.5f;
 constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
+#ifndef VFM_APP_BACKOFF
+#define VFM_APP_BACKOFF 0   // 1: the TMA / output warps sleep between polls of their barriers
+#endif
+#if VFM_APP_BACKOFF
+#define APP_WAIT_BG mbar_wait_backoff
+#else
+#define APP_WAIT_BG mbar_wait
+#endif
+#ifndef VFM_APP_SCORES_ON_OUTPUT
+#define VFM_APP_SCORES_ON_OUTPUT 0   // the extra key's scores are computed by the softmax warps at unit start (0) or, a unit
+#endif                               // ahead, by the output warps (1: measured slower, 0.277 against 0.263 ms)
 #ifndef VFM_APP_HANDOFF
-#define VFM_APP_HANDOFF 2   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token):
+#define VFM_APP_HANDOFF 1   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token):
 #endif                      // 1 = one token per warpgroup pair (256 threads), 2 = one per SM sub-partition (warp pair, 64 threads)
 // setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (threads x the register count ptxas reports for
 // the kernel), not the 64 K of the SM; a sum above the pool dead-locks the last warp's setmaxnreg.inc.
@@ -243,17 +251,22 @@ __device__ __forceinline__ void attention_extra_query_warp(const AttParams& p, c
 // See the file header for the roles. Barrier protocol (all mbarriers; parity = use count of the slot & 1):
 //   q_full / q_empty [2]   TMA -> S issuer, softmax (extra key) / S issuer (last S of the unit) [+ 8 softmax warps] -> TMA
 //   k_full / k_empty [3]   TMA -> S issuer / S issuer (S_A, S_B of the tile executed) -> TMA;   v_full / v_empty likewise (PV)
-//   s_full [X]             S issuer -> helper               S_X(t) is in TMEM
-//   m_full [X][quad]       helper warp -> softmax warp      row maxima of S_X(t) are in shared memory (=> S_X(t) is in TMEM)
-//   s_free [X]             4 softmax + 4 helper warps -> S issuer   S_X(t) has been read: S_X(t+1) may overwrite it
+//   s_full [X] / s_free [X]  S issuer -> softmax (S_X(t) is in TMEM) / softmax -> S issuer (S_X(t) is in registers)
 //   p_full [X] / p_free [X]  softmax -> PV issuer (P_X(t) stored) / PV issuer -> softmax (PV_X(t) executed)
-//   l_full [X][quad]       softmax warp -> helper warp      the unit's row sums are in shared memory
-//   o_ready [X] / o_free [X]  PV issuer -> helper (last PV_X of the unit executed) / helper -> PV issuer (O_X copied out)
+//   l_full [unit parity][X][quad]   softmax warp -> output warp   the unit's row sums are in shared memory. TWO barrier sets,
+//                          alternating by unit: with one key tile per unit a softmax warp can finish unit k + 1 before the
+//                          output warp has looked at unit k (its P store only needs PV(k), which needs the output of
+//                          k - 1), and a single barrier's parity would then alias (observed as a hang). e_full likewise.
+//   o_ready [X] / o_free [X]  PV issuer -> output warps (last PV_X of the unit executed) / output warps -> PV issuer (O_X copied out)
+// The extra key / value rows live in a ring of APP_XR_STAGES = 8 units: the TMA warp refills slot k % 8 for unit k after
+// the softmax warps have entered unit k - 2, which implies (through p_free -> o_free) that unit k - 5 has been written
+// out even with one key tile per unit; an output-warp arrival on q_empty instead would dead-lock that case (the
+// output of unit k would wait for the last PV of unit k while the Q tile of unit k + 2 waits for the output).
 __global__ void __launch_bounds__(APP_THREADS, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (an integer round trip makes every access generic)
   uint8_t* smem_q = smem;                                               // [stage][tile A | tile B]
   uint8_t* smem_k = smem_q + 2 * APP_Q_STAGES * APP_TILE_BYTES;
   uint8_t* smem_v = smem_k + APP_K_STAGES * APP_TILE_BYTES;
@@ -272,14 +285,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* o_ready = p_free + 2;                   // [2]
   uint64_t* o_free = o_ready + 2;                   // [2]
   uint64_t* x_full = o_free + 2;                    // [2] TMA -> extra-query warp
-  uint64_t* m_full = x_full + 2;                    // [2][4]
-  uint64_t* l_full = m_full + 8;                    // [2][4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_full + 8);
-  static_assert((2 + 2 + 3 * APP_K_STAGES / 3 * 0 + 2 * APP_K_STAGES + 2 * APP_V_STAGES + 7 * 2 + 16) * 8 + 8 <= APP_BAR_BYTES, "barrier block too small");
+  uint64_t* l_full = x_full + 2;                    // [unit parity][2][4]
+  uint64_t* e_full = l_full + 16;                   // [unit parity][2][4] output warp -> softmax warp: the unit's extra-key scores are in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e_full + 16);
+  static_assert((2 * APP_Q_STAGES + 2 * APP_K_STAGES + 2 * APP_V_STAGES + 7 * 2 + 32) * 8 + 8 <= APP_BAR_BYTES, "barrier block too small");
   float* extra_sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + APP_BAR_BYTES);   // [APP_MAX_EXTRA_KEYS] (+ 64 for q)
-  float* m_smem = extra_sc + APP_MAX_EXTRA_KEYS + 64;                       // [X][row]: row max (log2 units) of the current S_X tile
-  float2* lw_smem = reinterpret_cast<float2*>(m_smem + 2 * 128);           // [X][unit parity][row]: (row sum, extra key's weight)
-  uint8_t* smem_xr = reinterpret_cast<uint8_t*>(lw_smem + 2 * 2 * 128);    // [APP_XR_STAGES][extra key row | extra value row] (64 bf16 each)
+  float2* lw_smem = reinterpret_cast<float2*>(extra_sc + APP_MAX_EXTRA_KEYS + 64);   // [X][unit parity][row]: (row sum, extra key's weight)
+  float* es_smem = reinterpret_cast<float*>(lw_smem + 2 * 2 * 128);        // [X][unit parity][row]: q_row . k_extra (log2 units)
+  uint8_t* smem_xr = reinterpret_cast<uint8_t*>(es_smem + 2 * 2 * 128);    // [APP_XR_STAGES][extra key row | extra value row] (64 bf16 each)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,14 +308,14 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? 9 : 1); }
+    for (int s = 0; s < APP_Q_STAGES; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], p.extra ? (VFM_APP_SCORES_ON_OUTPUT ? 5 : 9) : 1); }
     for (int s = 0; s < APP_K_STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < APP_V_STAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 8); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
+      mbar_init(&s_full[x], 1); mbar_init(&s_free[x], 4); mbar_init(&p_full[x], 4); mbar_init(&p_free[x], 1);
       mbar_init(&o_ready[x], 1); mbar_init(&o_free[x], 4); mbar_init(&x_full[x], 1);
     }
-    for (int i = 0; i < 8; ++i) { mbar_init(&m_full[i], 1); mbar_init(&l_full[i], 1); }
+    for (int i = 0; i < 16; ++i) { mbar_init(&l_full[i], 1); mbar_init(&e_full[i], 1); }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
@@ -338,7 +351,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int k = 0; k < n_my; ++k) {
         const Unit un = unit_of(k);
         const int qs = k % APP_Q_STAGES;
-        mbar_wait(&q_empty[qs], ((k / APP_Q_STAGES) & 1) ^ 1);
+        APP_WAIT_BG(&q_empty[qs], ((k / APP_Q_STAGES) & 1) ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&q_full[qs], 2 * APP_TILE_BYTES + (p.extra ? 256 : 0));
           tma_load_2d(smem_q + (2 * qs) * APP_TILE_BYTES, &tmap_q, &q_full[qs], p.q_col0 + un.head * ATT_D, un.q_row0);
@@ -352,13 +365,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         __syncwarp();
         for (int j = 0; j < kv_tiles; ++j, ++t) {
           const int ks = t % APP_K_STAGES, vs = t % APP_V_STAGES;
-          mbar_wait(&k_empty[ks], ((t / APP_K_STAGES) & 1) ^ 1);
+          APP_WAIT_BG(&k_empty[ks], ((t / APP_K_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&k_full[ks], APP_TILE_BYTES);
             tma_load_2d(smem_k + ks * APP_TILE_BYTES, &tmap_k, &k_full[ks], p.k_col0 + un.head * ATT_D, un.kv_row0 + j * APP_BLOCK_KV);
           }
           __syncwarp();
-          mbar_wait(&v_empty[vs], ((t / APP_V_STAGES) & 1) ^ 1);
+          APP_WAIT_BG(&v_empty[vs], ((t / APP_V_STAGES) & 1) ^ 1);
           if (elect_one_sync()) {
             mbar_arrive_expect_tx(&v_full[vs], APP_TILE_BYTES);
             tma_load_2d(smem_v + vs * APP_TILE_BYTES, &tmap_v, &v_full[vs], p.v_col0 + un.head * ATT_D, un.kv_row0 + j * APP_BLOCK_KV);
@@ -384,7 +397,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               mbar_wait(&k_full[ks], (t / APP_K_STAGES) & 1);
             }
             APP_TRACE(2, t, 3 * x);
-            if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // S_X(t-1) has been read by the softmax and the helper warps
+            if (t > 0) mbar_wait(&s_free[x], (t - 1) & 1);   // warpgroup X has S_X(t-1) in registers
             tc_fence_after();
             APP_TRACE(2, t, 3 * x + 1);
             if (elect_one_sync()) {
@@ -448,23 +461,24 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                      x_full, ld, use);
       }
     } else {
-      // ===================== helper: row maxima of every S tile, output of every finished unit =====================
+      // ===================== output warps: write every finished unit out =====================
       const int quad = warp & 3;
       const int row = quad * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-      constexpr float kLog2e = 1.4426950408889634f;
       // Output of unit k: O_X out of TMEM in 16-column chunks, + the extra key's value row, normalised, stored; then the
-      // accumulator goes back to the PV issuer. Runs two tiles after the unit's last one (the unit's last PV has
-      // completed by then, so nothing here waits), between two row-maximum jobs.
+      // accumulator goes back to the PV issuer.
       auto unit_output = [&](int k) {
         const Unit un = unit_of(k);
         const uint4* vx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256 + 128);
 #pragma unroll 1
         for (int x = 0; x < 2; ++x) {
-          mbar_wait(&l_full[x * 4 + quad], k & 1);
+          if (quad == 0 && x == 0) APP_TRACE(3, k, 6);
+          APP_WAIT_BG(&l_full[(k & 1) * 8 + x * 4 + quad], (k >> 1) & 1);
           const float2 lw = lw_smem[(x * 2 + (k & 1)) * 128 + row];
-          mbar_wait(&o_ready[x], k & 1);
+          if (quad == 0 && x == 0) APP_TRACE(3, k, 7);
+          APP_WAIT_BG(&o_ready[x], k & 1);
           tc_fence_after();
+          if (quad == 0 && x == 0) APP_TRACE(2, k, 6);
           const float inv = 1.f / lw.x;
           const int q_idx = un.qp * APP_UNIT_Q + x * APP_TILE_Q + row;   // body index of this thread's query row
           const bool live = q_idx < p.q_len;
@@ -497,54 +511,50 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&o_free[x]);   // the next unit's first PV_X may overwrite O_X now
+          if (quad == 0 && x == 0) APP_TRACE(2, k, 7);
         }
       };
-      int t = 0;
-      for (int k = 0; k < n_my; ++k) {
-        for (int j = 0; j < kv_tiles; ++j, ++t) {
-          const int valid = j == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV;
+      // The extra key's score of every query row of unit k (q_row . k_extra on the CUDA cores, both rows from shared
+      // memory), published to the softmax warp of the same quadrant a whole unit ahead: on the softmax warps it sat
+      // between two units (~1000 clk per unit with the wait for the Q tile, trace p5).
+      auto extra_scores = [&](int k) {
+        const int qs = k % APP_Q_STAGES;
+        APP_WAIT_BG(&q_full[qs], (k / APP_Q_STAGES) & 1);
+        const uint4* kx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256);
 #pragma unroll 1
-          for (int x = 0; x < 2; ++x) {
-            mbar_wait(&s_full[x], t & 1);
-            tc_fence_after();
-            const uint32_t tmem_s = tmem_base + lane_base + APP_COL_S + x * APP_BLOCK_KV;
-            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tmem_s + 32 * c, r);
-              tmem_ld_wait();
-              if (valid < 32 * c + 32) {
+        for (int x = 0; x < 2; ++x) {
+          const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
+          float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (32 * c + i >= valid) r[i] = 0xff800000u;   // keys past the end of the sequence
-              }
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) m4[e] = fmax3(m4[e], __uint_as_float(r[i + 2 * e]), __uint_as_float(r[i + 2 * e + 1]));
-              }
-            }
-            m_smem[x * 128 + row] = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kLog2e;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(&m_full[x * 4 + quad]);
-              mbar_arrive(&s_free[x]);
-            }
+          for (int c = 0; c < 8; ++c) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
+            const uint4 kv = kx[c];
+            acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
+            acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
+            acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
+            acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
           }
-          // the unit that ended two tiles ago (its last PV has executed by now; see the deadlock note at APP_XR_STAGES)
-          if (t >= 2 && (t - 2) % kv_tiles == kv_tiles - 1) unit_output((t - 2) / kv_tiles);
+          es_smem[(x * 2 + (k & 1)) * 128 + row] = (acc0 + acc1) * 1.4426950408889634f;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&e_full[(k & 1) * 8 + x * 4 + quad]);
         }
+        if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the stage's Q tiles
+      };
+#if VFM_APP_SCORES_ON_OUTPUT
+      if (p.extra) extra_scores(0);
+      for (int k = 0; k < n_my; ++k) {
+        if (p.extra && k + 1 < n_my) extra_scores(k + 1);
+        unit_output(k);
       }
-      for (int tt = total_tiles; tt < total_tiles + 2; ++tt)
-        if (tt >= 2 && (tt - 2) % kv_tiles == kv_tiles - 1 && (tt - 2) / kv_tiles < n_my) unit_output((tt - 2) / kv_tiles);
+#else
+      for (int k = 0; k < n_my; ++k) unit_output(k);
+#endif
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(VFM_APP_SOFTMAX_REGS));
     // ===================== softmax: warpgroup X = A (warps 0..3) or B (warps 4..7) =====================
     // Per key tile t (one query row per thread, its 128 scores in registers s[]):
-    //   reference check   m_ref moves (and O_X is rescaled) only when the tile max (from the helper) exceeds it by > 2^24
+    //   reference check   m_ref moves (and O_X is rescaled) only when the tile max exceeds it by > 2^24
     //   token             named barrier: the MUFU pipe is ours
     //   MUFU pass         64 FFMA2 + 128 MUFU.EX2, in place in s[]; nothing else, so the pipe runs at 8 clk / instruction
     //   token release
@@ -563,8 +573,6 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr float kRescaleThreshold = 24.0f;   // log2 units (see attention_sm100.cuh)
     constexpr int kPoly = VFM_APP_POLY;
     const uint32_t sched_mask = static_cast<uint32_t>(p.sched_mask);
-    uint64_t* my_m_full = &m_full[x * 4 + quad];
-    const float* my_m = m_smem + x * 128 + row;
 #if VFM_APP_HANDOFF == 2
     const int bar_mine = 1 + 2 * quad + x, bar_other = 1 + 2 * quad + (x ^ 1);
     constexpr int kBarThreads = 64;
@@ -574,15 +582,26 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #endif
 
     uint32_t s[128];
-    auto mask_tail = [&]() {   // keys past the end of the sequence (tail tile) count as -inf
+    // row max (times log2e) of the tile in s[]; keys past the end of the sequence (tail tile) are masked to -inf first
+    auto row_max = [&](int valid) {
+      if (valid < APP_BLOCK_KV) {
 #pragma unroll
-      for (int i = 0; i < 128; ++i)
-        if (i >= tail_valid) s[i] = 0xff800000u;
+        for (int i = 0; i < 128; ++i)
+          if (i >= valid) s[i] = 0xff800000u;
+      }
+      float m8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) m8[c] = fmaxf(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
+#pragma unroll
+      for (int i = 16; i < 128; i += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m8[c] = fmax3(m8[c], __uint_as_float(s[i + 2 * c]), __uint_as_float(s[i + 2 * c + 1]));
+      }
+      return fmaxf(fmax3(m8[0], m8[1], m8[2]), fmaxf(fmax3(m8[3], m8[4], m8[5]), fmaxf(m8[6], m8[7]))) * kLog2e;
     };
 
     // ---- prologue: the first tile of this CTA's stream
-    mbar_wait(my_m_full, 0);
-    float m_next = *my_m;
+    mbar_wait(&s_full[x], 0);
     tc_fence_after();
     tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
     tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -592,7 +611,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_free[x]);
-    if (kv_tiles == 1 && tail_valid < APP_BLOCK_KV) mask_tail();
+    float m_next = row_max(kv_tiles == 1 ? tail_valid : APP_BLOCK_KV);
 #if VFM_APP_HANDOFF
     // MUFU passes alternate A(t), B(t), A(t+1), ...: a warp enters its pass through a named barrier (its own bar.sync +
     // the bar.arrive of its partner at the end of ITS pass). B opens the first A pass here. Without the token the two
@@ -603,31 +622,38 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #endif
     int t = 0;
     for (int k = 0; k < n_my; ++k) {
-      const int qs = k % APP_Q_STAGES;
       float m_ref = -INFINITY, w_extra = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;   // row sum = l0 + l1 + l2 + l3
       if (p.extra) {
-        // the extra key: s = q_row . k_extra on the CUDA cores (both rows from shared memory); it starts the running
-        // softmax with weight 1
-        mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
-        const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
-        const uint4* kx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256);
-        float acc0 = 0.f, acc1 = 0.f;
+        // the extra key starts the running softmax with weight 1; its score comes from the output warp of this quadrant
+        if (quad == 0) APP_TRACE(x, t, 2);
+#if VFM_APP_SCORES_ON_OUTPUT
+        mbar_wait(&e_full[(k & 1) * 8 + x * 4 + quad], (k >> 1) & 1);
+        m_ref = es_smem[(x * 2 + (k & 1)) * 128 + row];
+#else
+        {
+          const int qs = k % APP_Q_STAGES;
+          mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
+          const uint8_t* qrow = smem_q + (2 * qs + x) * APP_TILE_BYTES + row * 128;
+          const uint4* kx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256);
+          float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
-          const uint4 kv = kx[c];
-          acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
-          acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
-          acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
-          acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 qv = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
+            const uint4 kv = kx[c];
+            acc0 = fmaf(bf16lo(qv.x), bf16lo(kv.x), acc0); acc1 = fmaf(bf16hi(qv.x), bf16hi(kv.x), acc1);
+            acc0 = fmaf(bf16lo(qv.y), bf16lo(kv.y), acc0); acc1 = fmaf(bf16hi(qv.y), bf16hi(kv.y), acc1);
+            acc0 = fmaf(bf16lo(qv.z), bf16lo(kv.z), acc0); acc1 = fmaf(bf16hi(qv.z), bf16hi(kv.z), acc1);
+            acc0 = fmaf(bf16lo(qv.w), bf16lo(kv.w), acc0); acc1 = fmaf(bf16hi(qv.w), bf16hi(kv.w), acc1);
+          }
+          m_ref = (acc0 + acc1) * kLog2e;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the stage's Q tile
         }
-        m_ref = (acc0 + acc1) * kLog2e;
+#endif
         w_extra = 1.f;
 #if VFM_APP_ALUPACK != 2
         l0 = 1.f;
 #endif
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&q_empty[qs]);   // this warp no longer reads the stage's Q tile
       }
 
       for (int j = 0; j < kv_tiles; ++j, ++t) {
@@ -684,11 +710,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           named_bar_arrive(bar_other, kBarThreads);   // the pipe goes to the partner
 #endif
           if (quad == 0) APP_TRACE(x, t, 7);
+          if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
           if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
-          if (more) {
-            mbar_wait(my_m_full, (t + 1) & 1);   // S_X(t+1) is in TMEM and its row maxima are published
-            m_next = *my_m;
-          }
           tc_fence_after();
           if (quad == 0) APP_TRACE(x, t, 1);
 #pragma unroll
@@ -711,20 +734,23 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (more) tmem_ld32(tmem_s + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));   // into the registers just consumed
           }
           if (quad == 0) APP_TRACE(x, t, 5);
-          tmem_ld_wait();
           tmem_st_wait();
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&p_full[x]);
             if (more) mbar_arrive(&s_free[x]);   // S_X(t+2) may overwrite the score columns now
           }
-          if (more && tail_valid < APP_BLOCK_KV && (j + 1 == kv_tiles ? kv_tiles == 1 : j + 2 == kv_tiles)) mask_tail();
+          if (more) {   // the row max of tile t+1 is what stands between this warp and its next token request
+            const int jn = j + 1 == kv_tiles ? 0 : j + 1;
+            m_next = row_max(jn == kv_tiles - 1 ? tail_valid : APP_BLOCK_KV);
+          }
           if (quad == 0) APP_TRACE(x, t, 6);
         }
       }
 
-      // ---- the unit's row sums go to the helper warp of this quadrant, which writes the unit out
+      // ---- the unit's row sums go to the output warp of this quadrant, which writes the unit out
 #if VFM_APP_ALUPACK == 2
       const float l_total = ((l0 + l1) + (l2 + l3)) * (1.f / (1.f + kTruncEps)) + w_extra;
 #else
@@ -732,7 +758,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #endif
       lw_smem[(x * 2 + (k & 1)) * 128 + row] = make_float2(l_total, w_extra);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&l_full[x * 4 + quad]);
+      if (lane == 0) mbar_arrive(&l_full[(k & 1) * 8 + x * 4 + quad]);
     }
   }
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(WIN_THREADS, 2)
 attention_win_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                      const __grid_constant__ CUtensorMap tmap_q16, const __grid_constant__ CUtensorMap tmap_kv16, const WinParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (an integer round trip makes every access generic)
   uint8_t* sQ0 = smem;                      // SWIZZLE_128B tiles first (1024-byte aligned)
   uint8_t* sK0 = sQ0 + WIN_Q64;
   uint8_t* sV0 = sK0 + WIN_K64;
