@@ -64,7 +64,7 @@ class DGIoUMetric:
 
     def __init__(self, dataset_keys=[], mean_used_keys=[], ignore_index: int = 255, iou_metrics=("mIoU",), nan_to_num=None,
                  beta: int = 1, collect_device: str = "cpu", output_dir: Optional[str] = None, format_only: bool = False,
-                 prefix: Optional[str] = None, **kwargs):
+                 prefix: Optional[str] = None, keep_predictions: bool = False, **kwargs):
         if list(iou_metrics) != ["mIoU"]:
             raise NotImplementedError("only iou_metrics=['mIoU'] (what every reference config uses) is implemented")
         self.output_dir = output_dir
@@ -76,6 +76,11 @@ class DGIoUMetric:
         self.ignore_index = ignore_index
         self.results: List[list] = []
         self._dataset_meta: Optional[dict] = None
+        # keep_predictions: hold the uint8 label maps and gather them to rank 0 in dataset order in evaluate()
+        # (mmengine collect_results behind tools/test.py --out); `predictions` is filled on rank 0 only
+        self.keep_predictions = keep_predictions
+        self._pred_maps: List[torch.Tensor] = []
+        self.predictions: Optional[List[torch.Tensor]] = None
 
     @property
     def dataset_meta(self):
@@ -94,6 +99,8 @@ class DGIoUMetric:
             pred = data_sample["pred_sem_seg"]["data"].squeeze()
             if self.output_dir is not None:      # dg_metrics.py:60-72: colourised PNG of the prediction
                 self._save_png(pred, data_sample)
+            if self.keep_predictions:
+                self._pred_maps.append(pred.to(torch.uint8))
             if self.format_only:                 # test sets without ground truth (:46-47)
                 continue
             label = data_sample["gt_sem_seg"]["data"].squeeze().to(pred.device)
@@ -153,10 +160,22 @@ class DGIoUMetric:
 
     def evaluate(self, size: Optional[int] = None) -> Dict[str, float]:
         """Evaluator entry: all-reduce the per-key confusion matrices across ranks (int64 sum over NCCL),
-        compute on every rank, clear. Replaces mmengine collect_results + broadcast_object_list."""
+        compute on every rank, clear. Replaces mmengine collect_results + broadcast_object_list.
+
+        `size` = len(dataset), as mmengine passes it: the round-up sampler hands the last ranks wrapped-around
+        duplicates when len(dataset) % world_size != 0 and `collect_results(..., size)` drops them; here every rank
+        drops its own trailing duplicates before the all-reduce (collect.num_real_samples), so the multi-GPU metrics
+        equal the single-GPU ones."""
         import torch.distributed as dist
+        from .collect import gather_label_maps, num_real_samples
         results = self.results
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.keep_predictions:
+            self.predictions = gather_label_maps(self._pred_maps, size)
+            self._pred_maps = []
+        if multi and size is not None and not self.format_only:
+            results = results[:num_real_samples(size, dist.get_rank(), dist.get_world_size(), len(results))]
+        if multi:
             nc = len(self.dataset_meta["classes"])
             keys = list(self.dataset_keys) + ["unknown"]
             dev = results[0][1].device if results else torch.device("cuda", torch.cuda.current_device())
