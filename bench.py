@@ -2,6 +2,7 @@
 """bench.py — 1024x2048 images/s of DINOv2-L slide inference (BASELINE.json config 2) on N B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--images-per-step B] [--impl b200|reference]
+                    [--config 2|3|4|5] [--min-seconds S] [--gather-labels] [--gpu-comparator]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one pass of the hot path over B synthetic 1024x2048 uint8 images per GPU:
@@ -16,6 +17,11 @@ Prints ONE JSON line (rank 0):
   roofline  dominant kernel family: algorithmic FLOP per launch / CUDA-event time per launch, measured live over a
             repeat of the timed steps with per-launch events (vfm_prof_*), against MEASURED_PEAKS.json
   cpu_baseline  the oracle port (oracle/torch_ref.py, fp32) timed on this box's host cores on a bounded sample
+--config picks the BASELINE.json configuration (default 2 = the headline; 3 = dg_lora_dinov2_ms_masked coarse-to-fine, 4 = EVA02-L
+slide inference, 5 = SAM ViT-H at 1024 crops); every config prints the same line under torchrun at 1/2/4/8 GPUs.
+--min-seconds raises K until the timed region covers S seconds (the JSON reports the K actually timed); --gather-labels adds
+the NCCL gather of the step's label maps to rank 0 inside the timed region; --gpu-comparator adds the key gpu_comparator
+(tools/gpu_comparator.py: the same modules in PyTorch eager bf16 with cuBLASLt + cuDNN SDPA on the same GPU).
 --impl reference times that CPU path alone (the reference is pure Python on packages absent from this
 image, so the oracle port stands in; it cannot read /root/reference at run time).
 """
@@ -53,6 +59,35 @@ FLOP_PER_CROP = {
     "gemm_cls_nchw": 2 * 16384 * 256 * 19,
 }
 FLOP_PER_IMAGE = CROPS_PER_IMAGE * sum(FLOP_PER_CROP.values())
+
+
+def config_table(cfg_id: int, crops_per_pass: int):
+    """BASELINE.json configs -> (metric name, workload text, model config, state dict fn, crop, stride)."""
+    from vfmseg_b200 import synthetic
+    if cfg_id == 2:
+        cfg = synthetic.model_config(stride=(STRIDE, STRIDE), crop_size=(CROP, CROP))
+        out = ("images_per_s_1024x2048_slide_dinov2L",
+               "DINOv2 ViT-L/16 LoRA-merged + LinearHead slide inference, 1024x2048 images, crop 512, stride 341 (18 windows), 19 classes; label map + int64 confusion matrix per image",
+               cfg, synthetic.synthetic_state_dict, CROP, STRIDE)
+    elif cfg_id == 3:
+        cfg = synthetic.ms_model_config()
+        out = ("images_per_s_1024x2048_ms_masked_dinov2L",
+               "dg_lora_dinov2_ms_masked (MsVFMEncoderDecoder ms_slide_inference, configs/_base_/models/lora_dinov2_ms_masked.py:79-86): whole image at 512x1024 + confidence-gated refinement of 512 windows (stride 320, 21 windows) by VFMHead/MaskTransformerDecoder, shipped gate (threadshod 0.968, conf 0.8); ViT-L/16; label map + int64 confusion matrix per image",
+               cfg, synthetic.synthetic_ms_state_dict, 512, 320)
+    elif cfg_id == 4:
+        cfg = synthetic.eva_model_config()
+        out = ("images_per_s_1024x2048_slide_eva02L",
+               "EVA02-L/16 (RoPE, SwiGLU + sub-LN) LoRA + LinearHead slide inference (configs/_base_/models/lora_eva02_linear.py), 1024x2048, crop 512, stride 320 (21 windows), 19 classes",
+               cfg, synthetic.synthetic_eva_state_dict, 512, 320)
+    elif cfg_id == 5:
+        cfg = synthetic.sam_model_config(img_size=1024, crop_size=(1024, 1024), stride=(682, 682))
+        out = ("images_per_s_1024x2048_slide_samH_crop1024",
+               "SAM ViT-H/16 (14x14 windowed + 4 global blocks, decomposed rel-pos bias) LoRA + LinearHead slide inference, 1024x2048, crop 1024, stride 682 (3 windows of 4096 tokens), 19 classes",
+               cfg, synthetic.synthetic_sam_state_dict, 1024, 682)
+    else:
+        raise SystemExit(f"--config {cfg_id}: BASELINE.json has configs 2..5 on the GPU (1 is the reference's CPU case, see --impl reference)")
+    out[2]["max_crops_per_pass"] = crops_per_pass
+    return out
 
 
 def peaks():
@@ -110,28 +145,61 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_crop_seconds(n_timed: int = 3):
-    """Times the oracle port (fp32, all host threads) on single 512x512 crops of the same workload."""
+def cpu_reference_crop_seconds(n_timed: int = 3, config: int = 2):
+    """Times the oracle port (fp32, all host threads) on single windows of the chosen config's workload: backbone + head of
+    one crop (configs 2 / 3: DINOv2 ViT-L at 512; 4: EVA02-L at 512; 5: SAM ViT-H at 1024). Returns (seconds per window,
+    cores, description)."""
     from oracle import torch_ref
     from vfmseg_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = synthetic.model_config()
-    sd = synthetic.synthetic_state_dict(cfg, seed=0)
-    bb, hd = torch_ref.split_state_dict(sd)
-    oc = dict(depth=24, num_heads=16, patch=16, out_indices=(7, 11, 15, 23), lora_scale=1.0, groups=32)
-    img = synthetic.synthetic_images(1, CROP, CROP * (n_timed + 1), seed=1234)
+    crop = 1024 if config == 5 else CROP
+    img = synthetic.synthetic_images(1, crop, crop * (n_timed + 1), seed=1234)
     x = torch_ref.preprocess(img, MEAN, STD, True)
+    if config in (2, 3):
+        cfg = synthetic.model_config()
+        sd = synthetic.synthetic_state_dict(cfg, seed=0)
+        bb, hd = torch_ref.split_state_dict(sd)
+        oc = dict(depth=24, num_heads=16, patch=16, out_indices=(7, 11, 15, 23), lora_scale=1.0, groups=32)
+        fwd = lambda xi: torch_ref.encode_decode(xi, (bb, hd), oc)
+        what = "oracle/torch_ref.py DINOv2 ViT-L/16 + LinearHead, 512 window" + ("; the coarse pass and the refinement decoder of config 3 are not in the sample" if config == 3 else "")
+    elif config == 4:
+        cfg = synthetic.eva_model_config()
+        sd = synthetic.synthetic_eva_state_dict(cfg, seed=0)
+        bbc = cfg["backbone"]["backbone"]
+        pre = "backbone.model.base_model.model."
+        bb = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        hd = {k[len("decode_head."):]: v for k, v in sd.items() if k.startswith("decode_head.")}
+        lc = cfg["backbone"]["Lora_config"]
+        def fwd(xi):
+            feats = torch_ref.eva_forward(xi, bb, depth=bbc["depth"], num_heads=bbc["num_heads"], out_indices=tuple(bbc["out_indices"]),
+                                          lora_scale=lc["lora_alpha"] / lc["r"])
+            return torch_ref.linear_head_forward(feats, hd)
+        what = "oracle/torch_ref.py EVA02-L/16 + LinearHead, 512 window"
+    else:
+        cfg = synthetic.sam_model_config(img_size=1024, crop_size=(1024, 1024), stride=(682, 682))
+        sd = synthetic.synthetic_sam_state_dict(cfg, seed=0)
+        bbc = cfg["backbone"]["backbone"]
+        pre = "backbone.model.base_model.model."
+        bb = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        hd = {k[len("decode_head."):]: v for k, v in sd.items() if k.startswith("decode_head.")}
+        lc = cfg["backbone"]["Lora_config"]
+        def fwd(xi):
+            feats = torch_ref.sam_forward(xi, bb, depth=bbc["depth"], num_heads=bbc["num_heads"], window_size=bbc["window_size"],
+                                          global_attn_indexes=tuple(bbc["global_attn_indexes"]), out_indices=tuple(bbc["out_indices"]),
+                                          lora_scale=lc["lora_alpha"] / lc["r"])
+            return torch_ref.linear_head_forward(feats, hd)
+        what = "oracle/torch_ref.py SAM ViT-H/16 + LinearHead, 1024 window"
     times = []
     with torch.no_grad():
         for i in range(n_timed + 1):
-            xi = x[:, :, :, i * CROP:(i + 1) * CROP].contiguous()
+            xi = x[:, :, :, i * crop:(i + 1) * crop].contiguous()
             t0 = time.perf_counter()
-            torch_ref.encode_decode(xi, (bb, hd), oc)
+            fwd(xi)
             dt = time.perf_counter() - t0
             if i > 0:
                 times.append(dt)
-    return times, cores
+    return times, cores, what
 
 
 def run_reference_arm(args):
@@ -140,18 +208,21 @@ def run_reference_arm(args):
         return 0
     steps, warm = args.steps, args.warmup
     # a step = a bounded sample of the workload: one 512x512 crop of the 18 that make an image
-    n = min(max(steps, 1), 4)
-    times, cores = cpu_reference_crop_seconds(n_timed=n)
+    n = min(max(steps, 1), 4 if args.config != 5 else 1)
+    metric, workload, _cfg, _sd_fn, crop_px, stride_px = config_table(args.config, 36)
+    from oracle import torch_ref as _tr
+    n_windows = len(_tr.slide_boxes(H_IMG, W_IMG, (crop_px, crop_px), (stride_px, stride_px)))
+    times, cores, what = cpu_reference_crop_seconds(n_timed=n, config=args.config)
     t_crop = statistics.mean(times)
-    ips = 1.0 / (CROPS_PER_IMAGE * t_crop)
+    ips = 1.0 / (n_windows * t_crop)
     line = {
-        "metric": "images_per_s_1024x2048_slide_dinov2L", "value": ips, "unit": "images/s", "impl": "reference",
+        "metric": metric, "value": ips, "unit": "images/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": t_crop * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DINOv2 ViT-L/16 LoRA + LinearHead slide inference, 1024x2048, crop 512, stride 341, 19 classes",
-                   "step": "one 512x512 crop forward (1/18 of an image); images/s = 1 / (18 * s_per_crop)"},
+        "config": {"workload": workload, "baseline_config": args.config,
+                   "step": f"one window forward (1/{n_windows} of an image); images/s = 1 / ({n_windows} * s_per_window)"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} single-crop forwards (backbone + head) after 1 warm-up, fp32, torch {torch.__version__} CPU"},
+                         "sample": f"{n} single-window forwards ({what}) after 1 warm-up, fp32, torch {torch.__version__} CPU"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,12 +248,12 @@ def run_b200_arm(args):
     sampler = ClockSampler(local) if rank == 0 else None   # started early: nvidia-smi takes ~1 s to emit its first line
 
     B, K, W = args.images_per_step, args.steps, args.warmup
-    cfg = synthetic.model_config(stride=(STRIDE, STRIDE), crop_size=(CROP, CROP))
-    cfg["max_crops_per_pass"] = args.crops_per_pass
+    metric, workload, cfg, sd_fn, crop_px, stride_px = config_table(args.config, args.crops_per_pass)
     model = vfmseg_b200.MODELS.build(cfg)
-    model.load_state_dict(synthetic.synthetic_state_dict(cfg, seed=0), strict=False)
+    model.load_state_dict(sd_fn(cfg, seed=0), strict=False)
     model = model.to(dev).eval()
     eng = model.engine()
+    n_windows = len(__import__("vfmseg_b200.engine", fromlist=["slide_boxes"]).slide_boxes(H_IMG, W_IMG, (crop_px, crop_px), (stride_px, stride_px)))
 
     # distinct images every step (pool of 4 batches) so no step re-reads the previous step's pixels
     n_pool = 4
@@ -192,9 +263,17 @@ def run_b200_arm(args):
     gt_dev = [t.to(dev) for t in gt_host]
     cm = torch.zeros(NUM_CLASSES + 1, NUM_CLASSES, dtype=torch.int64, device=dev)
 
+    gather_list = [torch.empty(B, H_IMG, W_IMG, dtype=torch.uint8, device=dev) for _ in range(world)] if (args.gather_labels and world > 1 and rank == 0) else None
+
+    def gather_maps(labels):
+        """north_star's "gather of prediction maps": the step's uint8 label maps to rank 0 over NCCL (tools/test.py --out)."""
+        if args.gather_labels and world > 1:
+            dist.gather(labels, gather_list, dst=0)
+
     def step_resident(i):
         labels, _ = model.predict_labels(pool_dev[i % n_pool])
         eng.confusion(cm, labels, gt_dev[i % n_pool])
+        gather_maps(labels)
         return labels
 
     def barrier():
@@ -220,6 +299,12 @@ def run_b200_arm(args):
     for i in range(W):
         step_resident(i)
     torch.cuda.synchronize()
+    if args.min_seconds > 0:   # raise K (same on every rank) until the timed region covers --min-seconds
+        ms_probe = timed(step_resident, 2) / 2
+        k_need = torch.tensor([int(args.min_seconds * 1e3 / max(ms_probe, 1e-3)) + 1], device=dev)
+        if world > 1:
+            dist.all_reduce(k_need, op=dist.ReduceOp.MAX)
+        K = max(K, int(k_need.item()))
     cm.zero_()
     l0 = lib.vfm_launch_count()
     t_wall0 = time.time()
@@ -236,25 +321,48 @@ def run_b200_arm(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- e2e: host uint8 images in, host labels + confusion matrix out, through the public segmentor call
-    in_dev = torch.empty_like(pool_dev[0])
-    gt_in = torch.empty_like(gt_dev[0])
-    lab_host = torch.empty(B, H_IMG, W_IMG, dtype=torch.uint8).pin_memory()
-    cm_host = torch.empty(NUM_CLASSES + 1, NUM_CLASSES, dtype=torch.int64).pin_memory()
+    # ---- e2e: host uint8 images in, host labels + confusion matrix out, through the public segmentor call.
+    # vfmseg_b200.host_pipeline.HostPipeline double-buffers the copies on side streams (upload of step i+1 and download of
+    # step i-1 overlap the compute of step i); every byte still moves inside the timed region and the host result of
+    # every step is synchronised on before its slot is reused.
+    from vfmseg_b200.host_pipeline import HostPipeline
+    pipe = HostPipeline(model, pool_host[0], gt_host[0], NUM_CLASSES)
+    cm_host = pipe.cm_host[0]
+    e2e_sink = [0]
 
     def step_e2e(i):
-        in_dev.copy_(pool_host[i % n_pool], non_blocking=True)
-        gt_in.copy_(gt_host[i % n_pool], non_blocking=True)
-        labels, _ = model.predict_labels(in_dev)
-        eng.confusion(cm, labels, gt_in)
-        lab_host.copy_(labels, non_blocking=True)
-        cm_host.copy_(cm, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller consumes the host result every step
+        nxt = (i + 1) % n_pool
+        out = pipe.submit(pool_host[i % n_pool], gt_host[i % n_pool], pool_host[nxt], gt_host[nxt])
+        if out is not None:
+            e2e_sink[0] += int(out[0][0, 0, 0])       # the caller touches the host result of every step
+        gather_maps_host = None  # (label maps already on the host: a multi-GPU --out run gathers them with collect.gather_label_maps)
 
-    for i in range(min(W, 2)):
-        step_e2e(i)
-    cm.zero_()
-    ms_e2e = timed(step_e2e, K)
+    def e2e_run(steps):
+        for i in range(steps):
+            step_e2e(i)
+        pipe.drain()
+        torch.cuda.current_stream().synchronize()
+
+    e2e_run(min(W, 2))
+    pipe.cm.zero_()
+
+    def timed_e2e(steps):
+        barrier()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        s_.record()
+        e2e_run(steps)
+        if world > 1:
+            dist.all_reduce(pipe.cm, op=dist.ReduceOp.SUM)
+        e_.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = torch.tensor([max(s_.elapsed_time(e_), 0.0)], device=dev)   # current-stream events bracket the side-stream work (drain() syncs it)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    ms_e2e = timed_e2e(K)
     h2d = B * 3 * H_IMG * W_IMG + B * H_IMG * W_IMG
     d2h = B * H_IMG * W_IMG + cm_host.numel() * 8
 
@@ -275,52 +383,64 @@ def run_b200_arm(args):
     if rank == 0:
         pk = peaks()
         total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
-        crops_per_run = K * B * CROPS_PER_IMAGE
+        crops_per_run = K * B * n_windows
+        # per-family algorithmic FLOPs: the full table for config 2; for the EVA02 config the attention core has the same
+        # shape (1025 tokens, 16 heads x 64) — the other configs report time shares only
+        flop_per_crop = FLOP_PER_CROP if args.config == 2 else ({"attention_fwd": FLOP_PER_CROP["attention_fwd"]} if args.config == 4 else {})
+        flop_per_image = FLOP_PER_IMAGE if args.config == 2 else None
         fam = {}
         for name, (cnt, ms) in prof.items():
             d = {"launches": cnt, "ms_total": round(ms, 4), "share": round(ms / total_prof_ms, 4)}
-            if name in FLOP_PER_CROP:
-                d["tflops"] = round(FLOP_PER_CROP[name] * crops_per_run / ms / 1e9, 1)
+            if name in flop_per_crop:
+                d["tflops"] = round(flop_per_crop[name] * crops_per_run / ms / 1e9, 1)
             fam[name] = d
         dense = {k: v for k, v in fam.items() if "tflops" in v}
-        top = max(dense, key=lambda k: dense[k]["ms_total"])
+        top = max(dense, key=lambda k: dense[k]["ms_total"]) if dense else max(fam, key=lambda k: fam[k]["ms_total"])
         cnt, ms = prof[top]
-        achieved = FLOP_PER_CROP[top] * crops_per_run / ms / 1e9
+        achieved = flop_per_crop[top] * crops_per_run / ms / 1e9 if top in flop_per_crop else None
         peak = pk["bf16_sustained"]   # kernels are timed inside a long step -> sustained figure
         traffic = None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (same launch shape only)
-            t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(top)
+            t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(top) if args.config == 2 else None
             if t and t["crops_per_launch"] == min(args.crops_per_pass, B * CROPS_PER_IMAGE):
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         except Exception:
             traffic = None
-        roofline = {"bound": "tensor", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
-                    "launch_ms": round(ms / cnt, 5), "flop_per_launch": FLOP_PER_CROP[top] * crops_per_run / cnt,
+        roofline = {"bound": "tensor", "kernel": top, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "peak_source": pk["source"] + " (bf16_tflops_sustained)",
+                    "launch_ms": round(ms / cnt, 5), "flop_per_launch": flop_per_crop[top] * crops_per_run / cnt if top in flop_per_crop else None,
                     "families": fam,
-                    "whole_step": {"tflops": round(FLOP_PER_IMAGE * B * K / ms_total / 1e9, 1),
-                                   "frac_of_sustained": round(FLOP_PER_IMAGE * B * K / ms_total / 1e9 / peak, 4),
-                                   "frac_of_burst": round(FLOP_PER_IMAGE * B * K / ms_total / 1e9 / pk["bf16_burst"], 4)}}
+                    "whole_step": None if flop_per_image is None else
+                                  {"tflops": round(flop_per_image * B * K / ms_total / 1e9, 1),
+                                   "frac_of_sustained": round(flop_per_image * B * K / ms_total / 1e9 / peak, 4),
+                                   "frac_of_burst": round(flop_per_image * B * K / ms_total / 1e9 / pk["bf16_burst"], 4)}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_reference_crop_seconds(n_timed=3)
+            times, cores, what = cpu_reference_crop_seconds(n_timed=3 if args.config != 5 else 1, config=args.config)
             t_crop = statistics.mean(times)
-            cpu = {"value": 1.0 / (CROPS_PER_IMAGE * t_crop), "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": f"3 single-crop forwards of 18 per image (oracle/torch_ref.py fp32, {t_crop:.2f} s/crop), 1 warm-up"}
+            cpu = {"value": 1.0 / (n_windows * t_crop), "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(times)} single-window forwards of {n_windows} per image ({what}, fp32, {t_crop:.2f} s/window), 1 warm-up"}
+        comparator = None
+        if args.gpu_comparator and world == 1 and args.config == 2:
+            sys.path.insert(0, str(ROOT / "tools"))
+            import gpu_comparator
+            comparator = gpu_comparator.run(images=B, steps=max(3, min(K, 10)), dev=dev)
         value = world * B * K / (ms_total / 1e3)
         e2e_v = world * B * K / (ms_e2e / 1e3)
         non_ign = int((torch.cat([g.view(-1) for g in gt_dev]) != 255).sum())
         line = {
-            "metric": "images_per_s_1024x2048_slide_dinov2L", "value": round(value, 3), "unit": "images/s", "n_gpus": world,
+            "metric": metric, "value": round(value, 3), "unit": "images/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "DINOv2 ViT-L/16 LoRA-merged + LinearHead slide inference, 1024x2048 images, crop 512, stride 341 (18 windows), 19 classes; label map + int64 confusion matrix per image",
-                       "images_per_step_per_gpu": B, "crops_per_pass": args.crops_per_pass, "parallelism": f"images sharded over {world} GPU(s), one int64[20x19] NCCL all-reduce",
+            "config": {"workload": workload, "baseline_config": args.config,
+                       "images_per_step_per_gpu": B, "crops_per_pass": args.crops_per_pass,
+                       "parallelism": f"images sharded over {world} GPU(s), one int64[20x19] NCCL all-reduce" +
+                                      (" + NCCL gather of the uint8 label maps to rank 0 every step" if args.gather_labels and world > 1 else ""),
                        "l2": "working set per step (0.6 GB bf16 weights + ~0.6 GB activations per image) exceeds the 126 MB L2; 4 distinct image batches rotate"},
             "e2e": {"value": round(e2e_v, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e / K, 4), "api": "LoraBackboneEncoderDecoder.predict_labels(uint8 images) + confusion matrix, pinned host in/out"},
+                    "ms_per_step": round(ms_e2e / K, 4), "api": f"{type(model).__name__}.predict_labels(uint8 images) + confusion matrix through vfmseg_b200.host_pipeline.HostPipeline: pinned host in/out, copies double-buffered on side streams inside the timed region"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "flop_per_image": FLOP_PER_IMAGE,
+            "flop_per_image": flop_per_image, "timed_seconds": round(ms_total / 1e3, 3), "gpu_comparator": comparator,
             "check": {"confusion_total": int(cm_value.sum()), "expected_if_all_pool_batches_seen": None},
         }
         emit(line)
@@ -355,9 +475,13 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)   # ~2.8 s timed region on config 2 (0.6 s was too short for the clock sampler)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json config (default 2 = the headline)")
+    ap.add_argument("--min-seconds", type=float, default=0.0, help="raise the step count until the timed region covers this many seconds")
+    ap.add_argument("--gather-labels", action="store_true", help="gather the uint8 label maps to rank 0 over NCCL every step (N > 1)")
+    ap.add_argument("--gpu-comparator", action="store_true", help="also time tools/gpu_comparator.py (PyTorch eager bf16, cuBLASLt + cuDNN SDPA)")
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--images-per-step", type=int, default=2)
+    ap.add_argument("--images-per-step", type=int, default=0, help="images per GPU and step (default 2; 1 for config 5)")
     ap.add_argument("--crops-per-pass", type=int, default=36)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -365,6 +489,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.quick:
         args.warmup = 3
+    if args.images_per_step <= 0:
+        args.images_per_step = 1 if args.config == 5 else 2
     if args.impl == "reference":
         return run_reference_arm(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -9,6 +9,10 @@ Files
   tiny_whole.npz : same model, whole_inference on a non-square 64x96 input (bicubic pos-embed path).
   vitl_crop.npz  : config 1 — DINOv2 ViT-L/16 + LoRA + LinearHead, one 512x512 crop, fp32 CPU:
                    low-res logits subsampled [:, ::2, ::2] and per-tap statistics.
+  vitl_crop_probe.npz / vitl_full_probe.npz : the "trained-network-like" recipe (synthetic.region_images + a classifier fitted by
+                   oracle/probe.py): fitted conv_seg, the reference's slide_inference labels for the WHOLE image and its
+                   logits subsampled; vitl_full_probe is BASELINE config 2 at full size (one 1024x2048 image, 18 windows,
+                   ViT-L). The >= 99.9 % raw label-agreement bar of north_star is asserted against these.
 Inputs and weights are NOT stored: they are regenerated from seeds (torch CPU generators).
 """
 from __future__ import annotations
@@ -92,6 +96,47 @@ def vitl_crop():
     stats = np.array([[f.mean().item(), f.std().item(), f.abs().max().item()] for f in feats], dtype=np.float64)
     np.savez_compressed(GOLDEN / "vitl_crop.npz", lowres_sub=low[0, :, ::2, ::2].numpy(), tap_stats=stats,
                         lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8))
+
+
+def _oracle_cfg(cfg):
+    bb, lc = cfg["backbone"], cfg["Lora_config"]
+    return dict(depth=bb["depth"], num_heads=bb["num_heads"], patch=bb["patch_size"], out_indices=tuple(bb["out_indices"]),
+                lora_scale=lc["lora_alpha"] / lc["r"], groups=cfg["decode_head"]["norm_cfg"]["num_groups"])
+
+
+def _probe_golden(name, cfg, H, W, cell, crop, stride, sub_logits, img_seed=11):
+    """Fit the probe on the oracle's merged features, then run the REFERENCE's slide_inference with it."""
+    from oracle import probe
+    sd = synthetic.synthetic_state_dict(cfg, seed=0)
+    img, planted = synthetic.region_images(1, H, W, seed=img_seed, cell=cell)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    t0 = time.time()
+    feats = probe.merged_features(x, sd, _oracle_cfg(cfg), crop, stride)
+    w, b = probe.fit_probe(feats, planted)
+    del feats
+    sd = synthetic.with_probe_classifier(sd, w, b)
+    model = build_reference(cfg, sd)
+    with torch.no_grad():
+        logits = model.inference(x, [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)])
+        with torch.autocast("cpu", dtype=torch.bfloat16):   # how far a bf16 run of the reference itself lands from its fp32 labels
+            lo = torch_ref.slide_inference(x, torch_ref.split_state_dict(sd), _oracle_cfg(cfg), crop=crop, stride=stride).float()
+    labels = logits.argmax(1)
+    agree_planted = (labels == planted.long()).float().mean().item()
+    agree_bf16 = (labels == lo.argmax(1)).float().mean().item()
+    print(f"{name}: {time.time() - t0:.0f}s; {probe.margin_report(logits)}; labels == planted {agree_planted:.4f}; "
+          f"reference fp32 vs oracle under bf16 autocast: label agreement {agree_bf16:.5f}")
+    np.savez_compressed(GOLDEN / f"{name}.npz", conv_seg_weight=w.numpy(), conv_seg_bias=b.numpy(),
+                        labels=labels[0].numpy().astype(np.uint8), logits_sub=logits[0, :, ::sub_logits, ::sub_logits].numpy().astype(np.float16),
+                        sub=np.int64(sub_logits), img_seed=np.int64(img_seed), cell=np.int64(cell),
+                        agree_bf16_autocast=np.float64(agree_bf16), agree_planted=np.float64(agree_planted))
+
+
+def vitl_crop_probe():   # one 512 x 512 window of the real architecture (smoke(), single-crop tests)
+    _probe_golden("vitl_crop_probe", synthetic.model_config(), 512, 512, 128, (512, 512), (341, 341), 4)
+
+
+def vitl_full_probe():
+    _probe_golden("vitl_full_probe", synthetic.model_config(), 1024, 2048, 256, (512, 512), (341, 341), 8)
 
 
 def build_reference_ms(cfg, sd):
@@ -198,6 +243,6 @@ def tiny_sam():
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva", "tiny_sam"]
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva", "tiny_sam", "vitl_crop_probe", "vitl_full_probe"]
     for w in which:
         globals()[w]()

@@ -1,0 +1,58 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. A "trained" classifier for the synthetic weights: the head's final 1x1 conv
+(`conv_seg`, rein/models/heads/linear_head.py:70 -> mmseg BaseDecodeHead.cls_seg [3P]) fitted by ridge regression so that
+the merged slide-inference logits reproduce the planted label map of `synthetic.region_images`.
+
+Why (SURVEY.md §7 "Tolerance vs random-init weights"): north_star asks for >= 99.9 % per-pixel label agreement.
+19 logits out of a random classifier are near-iid, the reference's own top-2 margin is below the bf16 logit error on
+~0.5 % of the pixels, and there the argmax is a coin flip for ANY bf16 implementation. A trained network is confident
+away from class boundaries; the probe gives the synthetic network exactly that property without touching the backbone or
+the rest of the head (whose numerics are what the test exercises).
+
+Slide merging (bilinear resize of every window's logits, zero-padded sum, division by the window count) is linear, and
+so is `conv_seg`, so the merged logits are W @ F + b with F the merged 256-channel features: F comes from one oracle run
+with `conv_seg` replaced by the identity.
+"""
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import torch
+
+from . import torch_ref
+
+
+def merged_features(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: dict, crop: Sequence[int], stride: Sequence[int]) -> torch.Tensor:
+    """fp32 [B, ch, H, W]: slide_inference with the classifier replaced by the identity."""
+    bb, hd = torch_ref.split_state_dict(sd)
+    ch = hd["conv_seg.weight"].shape[1]
+    hd = dict(hd)
+    hd["conv_seg.weight"] = torch.eye(ch).view(ch, ch, 1, 1)
+    hd["conv_seg.bias"] = torch.zeros(ch)
+    with torch.no_grad():
+        return torch_ref.slide_inference(x, (bb, hd), cfg, crop=crop, stride=stride)
+
+
+def fit_probe(feats: torch.Tensor, planted: torch.Tensor, num_classes: int = 19, sub: int = 7, target: float = 8.0,
+              ridge: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Ridge regression of `target` x one-hot(planted) on the features of every `sub`-th pixel. The ridge strength is a
+    conditioning trade-off measured on the ViT-L crop (fp32 reference vs the same modules under bf16 CPU autocast): a weak
+    ridge (1e-3) fits the planted map best (97.8 %) but its large cancelling weights amplify the bf16 error of the FEATURES
+    until only 92 % of the logits stay inside the 2e-2 band; ridge 1.0 keeps 99.94 % inside and the labels still agree on
+    99.92 % of the pixels (planted accuracy 86 %).
+    feats [B, ch, H, W] fp32, planted [B, H, W] integer -> (weight [nc, ch], bias [nc]) fp32."""
+    B, ch = feats.shape[:2]
+    X = feats.permute(0, 2, 3, 1).reshape(-1, ch)[::sub]
+    y = planted.reshape(-1)[::sub].long()
+    T = torch.nn.functional.one_hot(y, num_classes).double() * target
+    Xa = torch.cat([X, torch.ones(X.shape[0], 1)], 1).double()
+    lam = ridge * Xa.pow(2).mean() * Xa.shape[0]
+    sol = torch.linalg.solve(Xa.t() @ Xa + lam * torch.eye(ch + 1, dtype=torch.double), Xa.t() @ T)
+    return sol[:ch].t().float().contiguous(), sol[ch].float().contiguous()
+
+
+def margin_report(logits: torch.Tensor) -> str:
+    rms = logits.pow(2).mean().sqrt().item()
+    top2 = logits.topk(2, dim=1).values
+    m = (top2[:, 0] - top2[:, 1]) / rms
+    return (f"rms {rms:.3f}; top-2 margin < 0.01 / 0.02 / 0.05 rms on {(m < 0.01).float().mean().item():.5f} / "
+            f"{(m < 0.02).float().mean().item():.5f} / {(m < 0.05).float().mean().item():.5f} of the pixels")

@@ -217,6 +217,110 @@ def test_vitl_full_image_properties():
     assert torch.equal(low_single[0], low[7])
 
 
+def _probe_model(golden_name):
+    """ViT-L config with the classifier fitted by oracle/probe.py (stored in the golden) and the region image it was
+    fitted on — the "trained-network-like" recipe (synthetic.region_images)."""
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / golden_name)
+    cfg = synthetic.model_config()
+    sd = synthetic.with_probe_classifier(synthetic.synthetic_state_dict(cfg, seed=0), g["conv_seg_weight"], g["conv_seg_bias"])
+    import vfmseg_b200
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "num_batches_tracked" not in m]
+    return model.cuda().eval(), g
+
+
+def _check_probe(labels, logits, g, what):
+    """north_star's bars on the reference's own slide_inference output (golden): RAW per-pixel label agreement >= 99.9 %
+    over the whole image, logits within bf16 tolerance on the stored sub-grid."""
+    sub = int(g["sub"])
+    ref_sub = torch.from_numpy(g["logits_sub"].astype(np.float32))
+    _check_logits(logits[0, :, ::sub, ::sub], ref_sub, f"{what}: logits (every {sub}th pixel) vs reference golden")
+    raw = (labels[0].cpu().numpy() == g["labels"]).mean()
+    print(f"{what}: RAW label agreement with the reference {raw:.6f} over {g['labels'].size} pixels "
+          f"(the reference's own fp32-vs-bf16-autocast agreement on this input: {float(g['agree_bf16_autocast']):.5f})")
+    assert raw >= 0.999, f"{what}: raw label agreement {raw:.6f} < 0.999"
+
+
+def test_vitl_crop_probe_raw_label_agreement():
+    """One 512 x 512 window of the real architecture, trained-like classifier: raw agreement >= 99.9 %."""
+    from vfmseg_b200 import synthetic
+    model, g = _probe_model("vitl_crop_probe.npz")
+    img, _ = synthetic.region_images(1, 512, 512, seed=int(g["img_seed"]), cell=int(g["cell"]))
+    labels, logits = model.predict_labels(img.cuda(), want_logits=True)
+    _check_probe(labels, logits, g, "ViT-L crop, probe classifier")
+
+
+def test_vitl_full_size_config2_vs_reference_golden():
+    """BASELINE config 2 at FULL size against the reference's own slide_inference (golden generated by
+    oracle/make_golden.py:vitl_full_probe from the reference modules): one 1024 x 2048 image, 18 windows of 512 at
+    stride 341, ViT-L/16 + LoRA + LinearHead, fp32 CPU. Raw label agreement >= 99.9 % over all 2 M pixels."""
+    from vfmseg_b200 import synthetic
+    model, g = _probe_model("vitl_full_probe.npz")
+    img, _ = synthetic.region_images(1, 1024, 2048, seed=int(g["img_seed"]), cell=int(g["cell"]))
+    labels, logits = model.predict_labels(img.cuda(), want_logits=True)
+    assert labels.shape == (1, 1024, 2048)
+    _check_probe(labels, logits, g, "config 2 full size, probe classifier")
+
+
+def test_postprocess_result_resize_to_ori_shape():
+    """mmseg postprocess_result for the reference's cross-domain test pipelines: BDD100K 1280x720 is fed as 1820x1024
+    (configs/_base_/datasets/bdd100k_1024x1024.py:15) and the merged logits are resized back to ori_shape before the
+    argmax. (a) the fused resize+argmax op vs torch on full-size fp32 logits; (b) padding strip + flip + resize through
+    the segmentor's postprocess_result vs the same steps in torch."""
+    import torch.nn.functional as F
+    import vfmseg_b200
+    from vfmseg_b200 import ops, synthetic
+    from vfmseg_b200.structures import SegDataSample
+    g = torch.Generator(device="cpu").manual_seed(5)
+    coarse = torch.randn(1, 19, 64, 114, generator=g)
+    logits = (F.interpolate(coarse, size=(1024, 1820), mode="bicubic", align_corners=False) * 3 +
+              torch.randn(1, 19, 1024, 1820, generator=g) * 0.05).cuda().contiguous()
+    lab, res = ops.resize_argmax(logits, (720, 1280))
+    ref = F.interpolate(logits, size=(720, 1280), mode="bilinear", align_corners=False)
+    assert res.shape == ref.shape and (res - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    agree = (lab.long() == ref.argmax(1)).float().mean().item()
+    print(f"resize_argmax 1024x1820 -> 720x1280: max |err| {(res - ref).abs().max().item():.3g}, label agreement {agree:.6f}")
+    assert agree >= 0.999
+    # (b) through the registered segmentor
+    model = vfmseg_b200.MODELS.build(dict(synthetic.tiny_config()))
+    small = logits[:, :, :200, :300].contiguous()
+    metas = [dict(ori_shape=(120, 176), img_shape=(200, 300), padding_size=[4, 12, 0, 8], flip=True, flip_direction="horizontal")]
+    out = model.postprocess_result(small, [SegDataSample(metainfo=metas[0])])
+    want = F.interpolate(small[:, :, 0:192, 4:288].flip(dims=(3,)), size=(120, 176), mode="bilinear", align_corners=False)[0]
+    got = out[0].seg_logits.data
+    assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    assert out[0].pred_sem_seg.data.shape == (1, 120, 176)
+    assert (out[0].pred_sem_seg.data[0] == want.argmax(0)).float().mean().item() >= 0.999
+    # identity metas keep the merge kernel's labels
+    same = model.postprocess_result(small, None)
+    assert torch.equal(same[0].pred_sem_seg.data[0], small[0].argmax(0))
+
+
+def test_slide_inference_bdd_size_1820_fast_merge():
+    """W = 1820 is not a multiple of the merge tile width (64): the tiled merge kernel runs with edge tiles partly idle and
+    must equal the torch pad/add/divide restatement."""
+    import torch.nn.functional as F
+    from vfmseg_b200 import ops
+    from vfmseg_b200.engine import slide_boxes
+    H, W = 1024, 1820
+    boxes = slide_boxes(H, W, (512, 512), (341, 341))
+    g = torch.Generator(device="cpu").manual_seed(6)
+    low = torch.randn(len(boxes), 19, 128, 128, generator=g).cuda()
+    bx = torch.tensor(boxes, dtype=torch.int32, device="cuda")
+    labels, logits = ops.slide_merge_argmax(low, bx, 1, (512, 512), (H, W), want_logits=True)
+    preds = torch.zeros(1, 19, H, W, device="cuda")
+    count = torch.zeros(1, 1, H, W, device="cuda")
+    for k, (y1, x1) in enumerate(boxes):
+        up = F.interpolate(low[k:k + 1], size=(512, 512), mode="bilinear", align_corners=False)
+        preds += F.pad(up, (x1, W - x1 - 512, y1, H - y1 - 512))
+        count[:, :, y1:y1 + 512, x1:x1 + 512] += 1
+    ref = preds / count
+    assert (logits - ref).abs().max().item() <= 1e-4
+    assert (labels.long() == ref.argmax(1)).float().mean().item() >= 0.9999
+
+
 def test_metric_bit_exact_vs_reference_golden():
     import vfmseg_b200
     from vfmseg_b200 import synthetic

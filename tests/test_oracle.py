@@ -262,3 +262,26 @@ def test_tta_flip_oracle_against_live_reference(flip):
         got_m = torch_ref.tta_flip_combine(lambda im: torch_ref.slide_inference(im, sd, ocfg, crop=(64, 64), stride=(32, 32)),
                                            torch.flip(x, [3]), True)
         torch.testing.assert_close(torch.flip(got_m, [3]), got, rtol=0, atol=1e-6)
+
+
+def test_probe_golden_pins_the_oracle_at_real_dimensions():
+    """vitl_crop_probe.npz comes from the REFERENCE's modules (oracle/make_golden.py); the oracle restatement with the same
+    fitted classifier must reproduce its labels (fp32 vs fp32: differences only from summation order) — this pins the
+    oracle at ViT-L dimensions, not just on the tiny model — and the golden must have the trained-like margins the
+    >= 99.9 % label bar relies on."""
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / "vitl_crop_probe.npz")
+    cfg = synthetic.model_config()
+    sd = synthetic.with_probe_classifier(synthetic.synthetic_state_dict(cfg, seed=0), g["conv_seg_weight"], g["conv_seg_bias"])
+    img, planted = synthetic.region_images(1, 512, 512, seed=int(g["img_seed"]), cell=int(g["cell"]))
+    x = torch_ref.preprocess(img, [123.675, 116.28, 103.53], [58.395, 57.12, 57.375], True)
+    bb, lc = cfg["backbone"], cfg["Lora_config"]
+    oc = dict(depth=bb["depth"], num_heads=bb["num_heads"], patch=16, out_indices=tuple(bb["out_indices"]),
+              lora_scale=lc["lora_alpha"] / lc["r"], groups=32)
+    with torch.no_grad():
+        ref = torch_ref.slide_inference(x, torch_ref.split_state_dict(sd), oc, crop=(512, 512), stride=(341, 341))
+    assert (ref[0].argmax(0).numpy() == g["labels"]).mean() >= 0.9999
+    sub = int(g["sub"])
+    gl = torch.from_numpy(g["logits_sub"].astype(np.float32))
+    assert (ref[0, :, ::sub, ::sub] - gl).abs().max().item() <= 2e-3 * gl.abs().max().item() + 2e-3   # fp16 storage
+    assert float(g["agree_planted"]) > 0.95 and float(g["agree_bf16_autocast"]) > 0.999

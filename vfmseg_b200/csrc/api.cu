@@ -816,9 +816,9 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
     LaunchScope scope("slide_merge_argmax", S(stream));
     const bool strips = (W % 4) == 0 && nc <= 19 && ((reinterpret_cast<uintptr_t>(labels) & 3) == 0) &&
                         (!logits_out || (reinterpret_cast<uintptr_t>(logits_out) & 15) == 0);
-    const bool tiles = strips && (W % MERGE_TW) == 0 && (H % MERGE_TH) == 0 && crop_h == 4 * lh && crop_w == 4 * lw && n_img <= 65535;
-    if (tiles) {    // low-res footprints staged through shared memory, one CTA per 64 x 16 output tile
-      const dim3 grid(W / MERGE_TW, H / MERGE_TH, n_img);
+    const bool tiles = strips && crop_h == 4 * lh && crop_w == 4 * lw && n_img <= 65535;
+    if (tiles) {    // low-res footprints staged through shared memory, one CTA per 64 x 16 output tile (edge tiles partly idle)
+      const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
       slide_merge_tile_kernel<19><<<grid, 256, 0, S(stream)>>>(lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
                                                               lh, lw, H, W, labels, logits_out);
     } else if (strips) {   // four pixels per thread sharing their bilinear taps

@@ -185,7 +185,9 @@ slide_merge_argmax4_kernel(const float* __restrict__ lowres, const int2* __restr
 // at most 6 rows x 18 columns per class — into shared memory with all loads in flight, then every thread resamples its
 // strip of four pixels from there. The per-pixel gather kernels above spend their time in chains of L2-latency loads
 // (0.65 ms per image against ~4 us of traffic); this one reads each low-res value once per tile.
-// Requires W % 64 == 0, H % 16 == 0 and an exact x4 upsampling (crop = 4 x low-res), which is what LinearHead produces.
+// Requires W % 4 == 0 and an exact x4 upsampling (crop = 4 x low-res), which is what LinearHead produces; tiles that hang
+// over the right / bottom edge (e.g. the 1820 x 1024 BDD100K test size, configs/_base_/datasets/bdd100k_1024x1024.py:15)
+// run with their outside strips idle.
 constexpr int MERGE_TW = 64, MERGE_TH = 16, MERGE_FR = 6, MERGE_FC = 20;   // tile, footprint rows / padded columns
 template <int NC_MAX>
 __global__ void __launch_bounds__(256)
@@ -196,6 +198,7 @@ slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict
   const int tx0 = blockIdx.x * MERGE_TW, ty0 = blockIdx.y * MERGE_TH, b = blockIdx.z;
   const int t = threadIdx.x;
   const int xs = tx0 + (t & 15) * 4, y = ty0 + (t >> 4);
+  const bool in_img = xs < W && y < H;   // W % 4 == 0: a strip is inside or outside as a whole
   const size_t plane = static_cast<size_t>(lh) * lw;
   float acc[4][NC_MAX];
 #pragma unroll
@@ -222,7 +225,7 @@ slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict
     }
     __syncthreads();
     const int cy = y - by;
-    if (cy < 0 || cy >= crop_h) continue;   // (no barrier below this point in the iteration)
+    if (!in_img || cy < 0 || cy >= crop_h) continue;   // (no barrier below this point in the iteration)
     const float sy = src(cy);
     const int y0 = static_cast<int>(sy);
     const int yp = (y0 < lh - 1) ? MERGE_FC : 0;
@@ -247,6 +250,7 @@ slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict
       }
     }
   }
+  if (!in_img) return;
   const size_t pix = static_cast<size_t>(y) * W + xs;
   uint32_t lab = 0;
 #pragma unroll

@@ -160,21 +160,48 @@ class LoraBackboneEncoderDecoder(nn.Module):
             labels, logits, _ = eng.whole(x, want_logits=want_logits)
         return labels, logits
 
-    def predict(self, inputs: torch.Tensor, data_samples: Optional[Sequence[SegDataSample]] = None) -> List[SegDataSample]:
-        """mmseg BaseSegmentor.predict + postprocess_result for un-padded, un-resized inputs
-        (ori_shape == img_shape, which is what the reference's Cityscapes test pipeline produces)."""
-        labels, logits = self.predict_labels(inputs, want_logits=True)
-        B, H, W = labels.shape
+    def postprocess_result(self, seg_logits: torch.Tensor, data_samples: Optional[Sequence[SegDataSample]] = None,
+                           labels: Optional[torch.Tensor] = None) -> List[SegDataSample]:
+        """mmseg BaseSegmentor.postprocess_result for C > 1: per sample strip `img_padding_size` /
+        `padding_size` (left, right, top, bottom), undo a test-time flip, resize the logits to `ori_shape` (bilinear,
+        align_corners of the head) and arg-max. The resize + argmax is one kernel (ops.resize_argmax); samples whose
+        `ori_shape` equals the network size — Cityscapes — keep the label map the merge kernel already produced.
+        The reference's cross-domain test pipelines need the resize: BDD100K 1280x720 is fed as 1820x1024
+        (configs/_base_/datasets/bdd100k_1024x1024.py:15), Mapillary likewise."""
+        from .. import ops
+        B, C, H, W = seg_logits.shape
         if data_samples is None:
             data_samples = [SegDataSample(metainfo=dict(ori_shape=(H, W), img_shape=(H, W))) for _ in range(B)]
+        if self.align_corners:
+            raise NotImplementedError("postprocess_result: align_corners=True heads are not part of the reference configs")
         for i, s in enumerate(data_samples):
-            meta = getattr(s, "metainfo", {})
-            ori = tuple(meta.get("ori_shape", (H, W)))[:2]
-            pad = meta.get("padding_size", [0, 0, 0, 0])
-            if ori != (H, W) or any(pad):
-                raise NotImplementedError("predict(): padded / resized test inputs are outside the slide-inference path")
-            s.set_data({"seg_logits": PixelData(data=logits[i]), "pred_sem_seg": PixelData(data=labels[i:i + 1].long())})
+            meta = getattr(s, "metainfo", {}) or {}
+            pad = meta.get("img_padding_size", meta.get("padding_size", [0, 0, 0, 0]))
+            left, right, top, bottom = [int(v) for v in pad]
+            ori = tuple(int(v) for v in tuple(meta.get("ori_shape", (H, W)))[:2])
+            flip = meta.get("flip", None)
+            if not (left or right or top or bottom or flip) and ori == (H, W):
+                lg = seg_logits[i]
+                lab = labels[i:i + 1] if labels is not None else lg.argmax(0, keepdim=True)
+            else:
+                lg = seg_logits[i:i + 1, :, top:H - bottom, left:W - right]
+                if flip:
+                    direction = meta.get("flip_direction", None)
+                    assert direction in ("horizontal", "vertical")
+                    lg = lg.flip(dims=(3,)) if direction == "horizontal" else lg.flip(dims=(2,))
+                if tuple(lg.shape[2:]) == ori:
+                    lg = lg[0]
+                    lab = lg.argmax(0, keepdim=True)
+                else:
+                    lab, lg = ops.resize_argmax(lg, ori)
+                    lg = lg[0]
+            s.set_data({"seg_logits": PixelData(data=lg), "pred_sem_seg": PixelData(data=lab.long())})
         return list(data_samples)
+
+    def predict(self, inputs: torch.Tensor, data_samples: Optional[Sequence[SegDataSample]] = None) -> List[SegDataSample]:
+        """mmseg BaseSegmentor.predict: inference at the network size, then postprocess_result per sample."""
+        labels, logits = self.predict_labels(inputs, want_logits=True)
+        return self.postprocess_result(logits, data_samples, labels=labels)
 
     def forward(self, inputs, data_samples=None, mode="predict"):
         if mode == "predict":

@@ -194,6 +194,14 @@ def resize_bilinear(low, size):
     return logits
 
 
+def resize_argmax(logits, size):
+    """mmseg postprocess_result's `resize(seg_logits, size=ori_shape, bilinear, align_corners=False)` + argmax in one
+    kernel: fp32 [B,nc,h,w] -> (uint8 labels [B,H,W], fp32 logits [B,nc,H,W]); any scale, up or down."""
+    B = logits.shape[0]
+    boxes = torch.zeros(1, 2, dtype=torch.int32, device=logits.device)
+    return slide_merge_argmax(logits.contiguous(), boxes, B, tuple(size), tuple(size), want_logits=True)
+
+
 # ------------------------------------------------------------------ coarse-to-fine path (config 3)
 def image_resize_norm(img, size, norm: _C.VfmPixelNorm | None = None):
     """Bilinear (align_corners=False) resize of [B,3,H,W] uint8 (normalised on the fly) or fp32 input -> fp32 [B,3,h,w]."""

@@ -136,6 +136,34 @@ def synthetic_images(n: int, H: int, W: int, seed: int = 1234) -> torch.Tensor:
     return img.clamp_(0, 255).round_().to(torch.uint8)
 
 
+def region_images(n: int, H: int, W: int, seed: int = 11, cell: int = 128, num_classes: int = 19):
+    """The "trained-network-like" input recipe: uint8 BGR [n,3,H,W] images made of cell x cell blocks, each block one of
+    `num_classes` palette colours (+-8 levels of per-pixel noise), and the planted uint8 label map [n,H,W] (block -> palette
+    index). Together with a classifier fitted on the features of exactly these images (oracle/probe.py; the fitted
+    `conv_seg` travels in tests/golden/*_probe.npz) the head's logits get what a trained network's have: one class well
+    ahead inside every region, near-ties only along region boundaries. With the plain random classifier the top-2 margin is
+    below the bf16 logit error on ~0.5 % of the pixels whatever the input is (19 near-iid logits), and no implementation in
+    bf16 — the reference itself under CPU autocast included — can agree with the fp32 argmax on 99.9 % of them."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    palette = torch.randint(0, 256, (num_classes, 3), generator=g).float()
+    hs, ws = -(-H // cell), -(-W // cell)
+    lab = torch.randint(0, num_classes, (n, hs, ws), generator=g)
+    img = palette[lab].permute(0, 3, 1, 2)
+    img = img.repeat_interleave(cell, 2).repeat_interleave(cell, 3)[:, :, :H, :W]
+    img = img + (torch.rand(n, 3, H, W, generator=g) - 0.5) * 16.0
+    planted = lab.repeat_interleave(cell, 1).repeat_interleave(cell, 2)[:, :H, :W].contiguous()
+    return img.clamp_(0, 255).round_().to(torch.uint8), planted.to(torch.uint8)
+
+
+def with_probe_classifier(sd: Dict[str, torch.Tensor], weight, bias, prefix: str = "decode_head.") -> Dict[str, torch.Tensor]:
+    """Copy of `sd` with the head's 1x1 classifier replaced by a fitted probe (weight [nc, ch], bias [nc])."""
+    out = dict(sd)
+    w = torch.as_tensor(weight, dtype=torch.float32)
+    out[prefix + "conv_seg.weight"] = w.reshape(w.shape[0], w.shape[1], 1, 1).clone()
+    out[prefix + "conv_seg.bias"] = torch.as_tensor(bias, dtype=torch.float32).clone()
+    return out
+
+
 def synthetic_labels(n: int, H: int, W: int, num_classes: int = 19, seed: int = 4321, ignore_frac: float = 0.05) -> torch.Tensor:
     """uint8 [n,H,W]: piecewise-constant class map (16x16 blocks) with ~5 % ignore (255) pixels."""
     g = torch.Generator(device="cpu").manual_seed(seed)
