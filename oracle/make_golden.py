@@ -240,9 +240,62 @@ def tiny_sam():
     print("tiny_sam", logits.shape, logits.std(), [float(f.std()) for f in feats])
 
 
+def _real_crop_golden(name, cfg, sd, builder, crop):
+    """One real-dimension window through the reference's backbone + LinearHead: low-res logits [:, ::2, ::2] and argmax."""
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "backbone.pth")
+        torch.save(synthetic.ms_backbone_checkpoint_from(sd), ck)
+        model = builder(cfg, ck)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "rope" not in m and "num_batches_tracked" not in m], (missing, unexpected)
+    model.eval()
+    img = synthetic.synthetic_images(1, crop, crop, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    t0 = time.time()
+    with torch.no_grad():
+        low = model.decode_head(model.extract_feat(x))
+    print(f"{name}: reference forward {time.time() - t0:.1f}s", tuple(low.shape), float(low.std()))
+    np.savez_compressed(GOLDEN / f"{name}.npz", lowres_sub=low[0, :, ::2, ::2].numpy().astype(np.float16),
+                        lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8))
+
+
+def eva_crop():   # BASELINE config 4 at real dimensions: EVA02-L/16, one 512 x 512 window
+    cfg = synthetic.eva_model_config()
+    _real_crop_golden("eva_crop", cfg, synthetic.synthetic_eva_state_dict(cfg, seed=0), ref_shim.build_reference_eva_segmentor, 512)
+
+
+def sam_crop():   # BASELINE config 5 at real dimensions: SAM ViT-H/16, one 1024 x 1024 window (4096 tokens, 25 padded 14 x 14 windows)
+    cfg = synthetic.sam_model_config(img_size=1024, crop_size=(1024, 1024), stride=(682, 682))
+    _real_crop_golden("sam_crop", cfg, synthetic.synthetic_sam_state_dict(cfg, seed=0), ref_shim.build_reference_sam_segmentor, 1024)
+
+
+def ms_crop():
+    """BASELINE config 3 at real dimensions: the VFMHead refinement of ONE 512 x 512 window of a 1024 x 2048 image — coarse
+    whole-image pass at 512 x 1024, context = the window's slice of the up-sampled coarse logits, ViT-L features of the
+    window, VFMHead.forward with the decoder's mask off: refined low-res logits [19, 32, 32] + the coarse logits."""
+    import torch.nn.functional as F
+    cfg = synthetic.ms_model_config()
+    sd = synthetic.synthetic_ms_state_dict(cfg, seed=0)
+    model = build_reference_ms(cfg, sd)
+    img = synthetic.synthetic_images(1, 1024, 2048, seed=1234)
+    x = torch_ref.preprocess(img, MEAN, STD, True)
+    metas = [dict(ori_shape=x.shape[2:], img_shape=x.shape[2:], pad_shape=x.shape[2:], padding_size=[0] * 4)]
+    t0 = time.time()
+    with torch.no_grad():
+        model.aux_decoder.transformer_decoder.mask_enable = False
+        lr = F.interpolate(x, size=(512, 1024), mode="bilinear", align_corners=False)
+        seg = model.whole_inference(lr, metas)                      # [1, 19, 1024, 2048]
+        y1, x1 = 320, 640                                           # window (1, 2) of the stride-320 grid
+        feats = model.extract_feat(x[:, :, y1:y1 + 512, x1:x1 + 512])
+        head_out = model.aux_decoder(feats, seg[:, :, y1:y1 + 512, x1:x1 + 512])
+    print(f"ms_crop: {time.time() - t0:.1f}s", tuple(head_out.shape), float(head_out.std()))
+    np.savez_compressed(GOLDEN / "ms_crop.npz", head_out=head_out[0].numpy().astype(np.float32), window=np.array([y1, x1]),
+                        coarse_sub=seg[0, :, ::16, ::16].numpy().astype(np.float16))
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva", "tiny_sam", "vitl_crop_probe", "vitl_full_probe"]
+    which = sys.argv[1:] or ["tiny_slide", "tiny_whole", "vitl_crop", "tiny_ms", "tiny_eva", "tiny_sam", "vitl_crop_probe", "vitl_full_probe", "eva_crop", "sam_crop", "ms_crop"]
     for w in which:
         globals()[w]()

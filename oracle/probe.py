@@ -33,13 +33,16 @@ def merged_features(x: torch.Tensor, sd: Dict[str, torch.Tensor], cfg: dict, cro
 
 
 def fit_probe(feats: torch.Tensor, planted: torch.Tensor, num_classes: int = 19, sub: int = 7, target: float = 8.0,
-              ridge: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Ridge regression of `target` x one-hot(planted) on the features of every `sub`-th pixel. The ridge strength is a
-    conditioning trade-off measured on the ViT-L crop (fp32 reference vs the same modules under bf16 CPU autocast): a weak
-    ridge (1e-3) fits the planted map best (97.8 %) but its large cancelling weights amplify the bf16 error of the FEATURES
-    until only 92 % of the logits stay inside the 2e-2 band; ridge 1.0 keeps 99.94 % inside and the labels still agree on
-    99.92 % of the pixels (planted accuracy 86 %).
-    feats [B, ch, H, W] fp32, planted [B, H, W] integer -> (weight [nc, ch], bias [nc]) fp32."""
+              ridge: float = 0.1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Ridge regression of `target` x one-hot(planted) on the features of every `sub`-th pixel.
+    feats [B, ch, H, W] fp32, planted [B, H, W] integer -> (weight [nc, ch], bias [nc]) fp32.
+    The ridge strength trades margins against conditioning (measured on the ViT-L crop, fp32 reference vs the same modules
+    under bf16 CPU autocast; label agreement / logits inside the 2e-2 band / planted accuracy):
+        1e-3: 99.93 % / 91.8 % / 97.8 %     0.1: 99.97 % / 97.9 % / 94.0 %     1.0: 99.92 % / 99.94 % / 86.3 %
+    A fitted classifier has larger, partly cancelling weights than the random one (mean |w| 0.33 against 0.10), so the same
+    bf16 error of the FEATURES is a larger share of the logit rms; the logit band is asserted on the random-classifier
+    goldens (same features), the label bar on these. 0.1 gives the best label agreement at full size (1.0 drops the
+    reference's own fp32-vs-autocast agreement to 99.75 % there)."""
     B, ch = feats.shape[:2]
     X = feats.permute(0, 2, 3, 1).reshape(-1, ch)[::sub]
     y = planted.reshape(-1)[::sub].long()

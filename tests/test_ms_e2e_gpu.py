@@ -19,6 +19,12 @@ pytestmark = pytest.mark.gpu
 # pixels the reference decides by more than the logit tolerance (measured 100 %), raw agreement >= 98.5 % (measured
 # 98.9-99.2 %: random weights leave 16-23 % of the pixels with a top-2 margin inside the tolerance).
 MS_FRAC = 0.95
+# Round 2: the error is a property of the reference's head, not of this implementation — tests/test_oracle.py::
+# test_ms_head_amplifies_bf16_input_error_beyond_the_logit_band measures, on this very input, that the fp32 oracle head fed
+# with a bf16-autocast backbone keeps only ~97 % of its outputs inside the band (the head doubles the relative error of its
+# coarse-logit input) and that the reference's modules under end-to-end bf16 autocast keep ~89 % (1.9-2.0 % rms). The
+# asserts below therefore also compare against that yardstick, computed live: at least as many logits in the band and no
+# larger rms error than the reference itself at bf16.
 
 
 def _rel_rms(got, ref):
@@ -93,6 +99,40 @@ def test_vfm_head_module_vs_reference_golden():
     assert out.shape == (1, 19, 4, 4)
     _check_logits(out, torch.from_numpy(g["head_out"]), "VFMHead.forward vs reference golden", frac=0.90)
     assert _rel_rms(out, torch.from_numpy(g["head_out"])) <= 0.02
+    # yardstick: the reference's modules under bf16 autocast on the same input (see the note at MS_FRAC)
+    from test_oracle import _ms_head_conditioning
+    y = _ms_head_conditioning()
+    ref = torch.from_numpy(g["head_out"]).float()
+    got = out.float().cpu()
+    rms = ref.pow(2).mean().sqrt()
+    ours = ((got - ref).abs() <= 2e-2 * ref.abs() + 2e-2 * rms).float().mean().item()
+    print(f"VFMHead: within band {ours:.4f} / rel rms {_rel_rms(out, ref):.4f}; reference under bf16 autocast {y['all_bf16'][0]:.4f} / "
+          f"{y['all_bf16'][1]:.4f}; exact head on bf16 inputs {y['inputs_only'][0]:.4f} / {y['inputs_only'][1]:.4f}")
+    assert ours >= y["all_bf16"][0] and _rel_rms(out, ref) <= y["all_bf16"][1]
+
+
+def test_ms_real_dimension_window_vs_reference_golden():
+    """BASELINE config 3 at REAL dimensions: coarse pass of a 1024 x 2048 image at 512 x 1024 and the VFMHead refinement of
+    one 512 x 512 window (ViT-L features, 3-block MaskTransformerDecoder, 256 channels); golden = the reference's own
+    Ms_VFM_encoder_decoder.py / VFMHead.py / Transformer.py modules in fp32 (oracle/make_golden.py:ms_crop). Bars as for the
+    tiny model (see the note at MS_FRAC): the head amplifies the bf16 error of its coarse-logit input."""
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / "ms_crop.npz")
+    cfg = synthetic.ms_model_config()
+    model, _ = _build_ms(cfg)
+    img = synthetic.synthetic_images(1, 1024, 2048, seed=1234).cuda()
+    model.test_cfg.conf = 1.5                     # refine every window
+    labels, logits, info = model._ms(img, True, "image")
+    assert info["n_refined"] == 21 and info["refined"].shape == (21, 19, 32, 32)
+    y1, x1 = [int(v) for v in g["window"]]
+    from vfmseg_b200.engine import slide_boxes
+    k = slide_boxes(1024, 2048, (512, 512), (320, 320)).index((y1, x1))
+    ref = torch.from_numpy(g["head_out"])
+    got = info["refined"][k]
+    _check_logits(got, ref, "config 3 real dimensions: refined window vs reference golden", frac=0.90)
+    assert _rel_rms(got, ref) <= 0.025
+    up = torch.nn.functional.interpolate(info["low0"], size=(1024, 2048), mode="bilinear", align_corners=False)
+    _check_logits(up[0, :, ::16, ::16], torch.from_numpy(g["coarse_sub"].astype(np.float32)), "config 3 real dimensions: coarse logits vs reference golden")
 
 
 def test_ms_batch_and_modes_vs_oracle():

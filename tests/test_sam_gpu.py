@@ -106,6 +106,22 @@ def test_tiny_sam_vs_reference_golden():
         model.extract_feat(torch.zeros(1, 3, 256, 320).cuda())
 
 
+def test_sam_real_dimension_crop_vs_reference_golden():
+    """BASELINE config 5 at REAL dimensions: SAM ViT-H/16 (1280 wide, 32 blocks, 16 heads x 80; 28 windowed blocks over 25
+    padded 14 x 14 windows, 4 global blocks over 4096 tokens with decomposed rel-pos bias) + LinearHead, one 1024 x 1024
+    window; golden = the reference's own sam_vit.py + linear_head.py in fp32 (oracle/make_golden.py:sam_crop)."""
+    from vfmseg_b200 import synthetic
+    g = np.load(GOLDEN / "sam_crop.npz")
+    cfg = synthetic.sam_model_config(img_size=1024, crop_size=(1024, 1024), stride=(682, 682))
+    model, _ = _build_sam(cfg)
+    img = synthetic.synthetic_images(1, 1024, 1024, seed=1234).cuda()
+    low = model.engine().crops_lowres(img, torch.tensor([[0, 0, 0, 0]], dtype=torch.int32, device="cuda"), (1024, 1024))
+    assert low.shape == (1, 19, 256, 256)
+    ref = torch.from_numpy(g["lowres_sub"].astype(np.float32))
+    _check_logits(low[0, :, ::2, ::2], ref, "SAM ViT-H 1024 crop low-res logits vs reference golden")
+    _check_labels(low[0].argmax(0)[::2, ::2], ref, "SAM ViT-H 1024 crop low-res labels vs reference golden")
+
+
 def test_full_size_sam_runs():
     """BASELINE config 5 shapes at the shipped crop (SAM ViT-H/16: 1280 wide, 32 blocks, 16 heads x 80, 1024x2048 image,
     crop 512 / stride 320 as configs/_base_/models/lora_sam_linear.py:49-54): finite logits, batching invariance."""

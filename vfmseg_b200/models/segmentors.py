@@ -39,6 +39,11 @@ class SegDataPreProcessor(nn.Module):
         inputs = data["inputs"]
         if isinstance(inputs, (list, tuple)):
             inputs = torch.stack(list(inputs), dim=0)
+        if inputs.dtype != torch.uint8:
+            # mmseg normalises whatever dtype arrives; here mean / std / channel flip live in the patch-gather kernel and are
+            # applied to uint8 pixels only, so a float image would silently skip them
+            raise TypeError(f"SegDataPreProcessor expects uint8 images (got {inputs.dtype}); already-normalised fp32 tensors go to "
+                            "predict() / inference() directly")
         return dict(inputs=inputs.to(self._dummy.device, non_blocking=True).contiguous(), data_samples=data.get("data_samples"))
 
 
@@ -92,12 +97,35 @@ class LoraBackboneEncoderDecoder(nn.Module):
     def invalidate(self):
         self._engine = None
 
+    def _weights_version(self) -> int:
+        """Changes whenever any parameter or buffer is written in place (load_state_dict on a SUBMODULE, optimizer steps,
+        manual edits): the packed bf16 copies inside the cached engine must not outlive the weights they were made from."""
+        v = 0
+        for t in self.parameters():
+            v += t._version
+        for t in self.buffers():
+            v += t._version
+        return v
+
     def _apply(self, fn, *a, **k):
         self._engine = None
         return super()._apply(fn, *a, **k)
 
     def engine(self) -> SlideEngine:
+        ver = self._weights_version()
+        if self._engine is not None and getattr(self, "_engine_version", None) != ver:
+            self._engine = None
+            for m in self.modules():          # per-module packed caches (backbone.packed(), decode_head.packed(), ...)
+                if m is not self and hasattr(m, "invalidate"):
+                    m.invalidate()
         if self._engine is None:
+            n_taps = len(getattr(self.inner_backbone, "out_indices", [])) or None
+            in_index = getattr(self.decode_head, "in_index", None)
+            if in_index is not None and n_taps is not None and list(in_index) != list(range(n_taps)):
+                # the fused path feeds the backbone taps to the fusion conv in out_indices order; mmseg's
+                # BaseDecodeHead._transform_inputs would select / permute them by in_index (ADVICE r1)
+                raise NotImplementedError(f"decode_head.in_index={list(in_index)} must be {list(range(n_taps))} for the fused slide path")
+            self._engine_version = ver
             bb = self.inner_backbone
             dev = next(bb.parameters()).device
             if dev.type != "cuda":
