@@ -270,10 +270,11 @@ def run_b200_arm(args):
         if args.gather_labels and world > 1:
             dist.gather(labels, gather_list, dst=0)
 
-    def step_resident(i):
+    def step_resident(i, collective=True):
         labels, _ = model.predict_labels(pool_dev[i % n_pool])
         eng.confusion(cm, labels, gt_dev[i % n_pool])
-        gather_maps(labels)
+        if collective:            # (the per-launch profile leg below runs on rank 0 alone: no collective there)
+            gather_maps(labels)
         return labels
 
     def barrier():
@@ -371,7 +372,7 @@ def run_b200_arm(args):
     if rank == 0:
         lib.vfm_prof_enable(1)
         for i in range(K):
-            step_resident(i)
+            step_resident(i, collective=False)
         buf = ctypes.create_string_buffer(1 << 16)
         _C.check(lib.vfm_prof_report(buf, len(buf)))
         lib.vfm_prof_enable(0)
@@ -401,7 +402,7 @@ def run_b200_arm(args):
         peak = pk["bf16_sustained"]   # kernels are timed inside a long step -> sustained figure
         traffic = None
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (same launch shape only)
-            t = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text()).get(top) if args.config == 2 else None
+            t = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text()).get(top) if args.config == 2 else None
             if t and t["crops_per_launch"] == min(args.crops_per_pass, B * CROPS_PER_IMAGE):
                 traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
         except Exception:

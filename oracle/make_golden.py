@@ -254,9 +254,19 @@ def _real_crop_golden(name, cfg, sd, builder, crop):
     t0 = time.time()
     with torch.no_grad():
         low = model.decode_head(model.extract_feat(x))
-    print(f"{name}: reference forward {time.time() - t0:.1f}s", tuple(low.shape), float(low.std()))
+    # yardstick: the SAME reference modules under CPU bf16 autocast (what "bf16 tolerance" means for this architecture)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        lo = model.decode_head(model.extract_feat(x)).float()
+    rms = low.pow(2).mean().sqrt()
+    err = (lo - low).abs()
+    within = (err <= 2e-2 * low.abs() + 2e-2 * rms).float().mean().item()
+    rel = ((lo - low).pow(2).mean().sqrt() / rms).item()
+    agree = (lo.argmax(1) == low.argmax(1)).float().mean().item()
+    print(f"{name}: reference forward {time.time() - t0:.1f}s", tuple(low.shape), float(low.std()),
+          f"| reference under bf16 autocast: within band {within:.4f}, rel rms {rel:.4f}, label agreement {agree:.4f}")
     np.savez_compressed(GOLDEN / f"{name}.npz", lowres_sub=low[0, :, ::2, ::2].numpy().astype(np.float16),
-                        lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8))
+                        lowres_argmax=low[0].argmax(0).numpy().astype(np.uint8), autocast_within=np.float64(within),
+                        autocast_rel_rms=np.float64(rel), autocast_label_agreement=np.float64(agree))
 
 
 def eva_crop():   # BASELINE config 4 at real dimensions: EVA02-L/16, one 512 x 512 window
@@ -288,9 +298,17 @@ def ms_crop():
         y1, x1 = 320, 640                                           # window (1, 2) of the stride-320 grid
         feats = model.extract_feat(x[:, :, y1:y1 + 512, x1:x1 + 512])
         head_out = model.aux_decoder(feats, seg[:, :, y1:y1 + 512, x1:x1 + 512])
-    print(f"ms_crop: {time.time() - t0:.1f}s", tuple(head_out.shape), float(head_out.std()))
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        seg_b = model.whole_inference(lr, metas).float()
+        head_b = model.aux_decoder(model.extract_feat(x[:, :, y1:y1 + 512, x1:x1 + 512]), seg_b[:, :, y1:y1 + 512, x1:x1 + 512]).float()
+    rms = head_out.pow(2).mean().sqrt()
+    within = ((head_b - head_out).abs() <= 2e-2 * head_out.abs() + 2e-2 * rms).float().mean().item()
+    rel = ((head_b - head_out).pow(2).mean().sqrt() / rms).item()
+    print(f"ms_crop: {time.time() - t0:.1f}s", tuple(head_out.shape), float(head_out.std()),
+          f"| reference under bf16 autocast: within band {within:.4f}, rel rms {rel:.4f}")
     np.savez_compressed(GOLDEN / "ms_crop.npz", head_out=head_out[0].numpy().astype(np.float32), window=np.array([y1, x1]),
-                        coarse_sub=seg[0, :, ::16, ::16].numpy().astype(np.float16))
+                        coarse_sub=seg[0, :, ::16, ::16].numpy().astype(np.float16), autocast_within=np.float64(within),
+                        autocast_rel_rms=np.float64(rel))
 
 
 if __name__ == "__main__":

@@ -109,8 +109,14 @@ def test_eva_real_dimension_crop_vs_reference_golden():
     low = model.engine().crops_lowres(img, torch.tensor([[0, 0, 0, 0]], dtype=torch.int32, device="cuda"), (512, 512))
     assert low.shape == (1, 19, 128, 128)
     ref = torch.from_numpy(g["lowres_sub"].astype(np.float32))
-    _check_logits(low[0, :, ::2, ::2], ref, "EVA02-L crop low-res logits vs reference golden")
-    _check_labels(low[0].argmax(0)[::2, ::2], ref, "EVA02-L crop low-res labels vs reference golden")
+    # EVA02 has no LayerScale (init_values=None): every branch enters the residual stream at full weight and the bf16 error
+    # of 24 blocks adds up to ~1 % of the logit rms at real depth (the tiny 4-block golden sits at 99.98 % inside the band).
+    # Yardstick stored with the golden: the reference's own modules under CPU bf16 autocast keep 95.8 % inside the band
+    # (rel rms 1.47 %); asserted: at least that, and >= 97.5 % (measured 98.2 %).
+    _check_logits(low[0, :, ::2, ::2], ref, "EVA02-L crop low-res logits vs reference golden", frac=max(0.975, float(g["autocast_within"])))
+    got = low[0, :, ::2, ::2].float().cpu()
+    assert ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= float(g["autocast_rel_rms"])
+    _check_labels(low[0].argmax(0)[::2, ::2], ref, "EVA02-L crop low-res labels vs reference golden", raw_min=float(g["autocast_label_agreement"]), top2_min=0.999)
 
 
 def test_gemm_bias_rope_matches_gemm_then_rope():

@@ -123,14 +123,16 @@ def test_ms_real_dimension_window_vs_reference_golden():
     img = synthetic.synthetic_images(1, 1024, 2048, seed=1234).cuda()
     model.test_cfg.conf = 1.5                     # refine every window
     labels, logits, info = model._ms(img, True, "image")
-    assert info["n_refined"] == 21 and info["refined"].shape == (21, 19, 32, 32)
-    y1, x1 = [int(v) for v in g["window"]]
     from vfmseg_b200.engine import slide_boxes
-    k = slide_boxes(1024, 2048, (512, 512), (320, 320)).index((y1, x1))
+    boxes = slide_boxes(1024, 2048, (512, 512), (320, 320))
+    assert info["n_refined"] == len(boxes) == 18 and info["refined"].shape == (18, 19, 32, 32)
+    y1, x1 = [int(v) for v in g["window"]]
+    k = boxes.index((y1, x1))
     ref = torch.from_numpy(g["head_out"])
     got = info["refined"][k]
-    _check_logits(got, ref, "config 3 real dimensions: refined window vs reference golden", frac=0.90)
-    assert _rel_rms(got, ref) <= 0.025
+    # yardstick stored with the golden: the reference's own modules under CPU bf16 autocast keep 92.9 % inside the band (rel rms 1.70 %)
+    _check_logits(got, ref, "config 3 real dimensions: refined window vs reference golden", frac=max(0.90, float(g["autocast_within"])))
+    assert _rel_rms(got, ref) <= float(g["autocast_rel_rms"])
     up = torch.nn.functional.interpolate(info["low0"], size=(1024, 2048), mode="bilinear", align_corners=False)
     _check_logits(up[0, :, ::16, ::16], torch.from_numpy(g["coarse_sub"].astype(np.float32)), "config 3 real dimensions: coarse logits vs reference golden")
 

@@ -118,8 +118,12 @@ def test_sam_real_dimension_crop_vs_reference_golden():
     low = model.engine().crops_lowres(img, torch.tensor([[0, 0, 0, 0]], dtype=torch.int32, device="cuda"), (1024, 1024))
     assert low.shape == (1, 19, 256, 256)
     ref = torch.from_numpy(g["lowres_sub"].astype(np.float32))
-    _check_logits(low[0, :, ::2, ::2], ref, "SAM ViT-H 1024 crop low-res logits vs reference golden")
-    _check_labels(low[0].argmax(0)[::2, ::2], ref, "SAM ViT-H 1024 crop low-res labels vs reference golden")
+    # 32 blocks without LayerScale: the reference's own modules under CPU bf16 autocast keep 96.8 % of these logits inside the
+    # band (rel rms 1.36 %, stored with the golden); asserted: at least that, and >= 99 % (measured 99.4 %).
+    _check_logits(low[0, :, ::2, ::2], ref, "SAM ViT-H 1024 crop low-res logits vs reference golden", frac=max(0.99, float(g["autocast_within"])))
+    got = low[0, :, ::2, ::2].float().cpu()
+    assert ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= float(g["autocast_rel_rms"])
+    _check_labels(low[0].argmax(0)[::2, ::2], ref, "SAM ViT-H 1024 crop low-res labels vs reference golden", raw_min=float(g["autocast_label_agreement"]), top2_min=0.999)
 
 
 def test_full_size_sam_runs():
