@@ -466,7 +466,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int row = quad * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
       // Output of unit k: O_X out of TMEM in 16-column chunks, + the extra key's value row, normalised, stored; then the
-      // accumulator goes back to the PV issuer.
+      // accumulator goes back to the PV issuer. (A TMEM load round trip costs ~400 clk here while the MMA pipe streams its
+      // accumulators through TMEM — ~1900 clk for the four dependent rounds of one tile, trace p5 — but two 32-column loads
+      // instead of four of 16 measured slower, 0.275 against 0.263 ms: the 56-register budget of these warps spills.)
       auto unit_output = [&](int k) {
         const Unit un = unit_of(k);
         const uint4* vx = reinterpret_cast<const uint4*>(smem_xr + (k % APP_XR_STAGES) * 256 + 128);
