@@ -94,8 +94,10 @@ int vfm_gemm_f32(const void* A, int lda, const void* W, int ldw, const float* bi
 int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int heads, void* stream);
 /* Same, choosing how a sequence is tiled: mode 0 = automatic, 1 = tensor-core tiles over every token, 2 = token 0 of
  * each sequence (the ViT cls token, dino_v2.py:225) is split off and handled on the CUDA cores so that 1 + 64k
- * tokens need no partial tile; 3 = the serial kernel (one score buffer, four CTAs per SM; an alternative kept for comparison).
- * The result is the same softmax attention in every mode. */
+ * tokens need no partial tile; 3 = the serial kernel (one score buffer, four CTAs per SM; an alternative kept for comparison);
+ * 4 = the ping-pong kernel (256-query units, 128-key tiles, one persistent CTA per SM, attention_pp_sm100.cuh), 5 = the same
+ * with token 0 split off. Mode 0 picks 5 for ViT windows (seq_len = 1 + a multiple of 256, >= 513), whatever n_seq is, and 1
+ * otherwise. The result is the same softmax attention in every mode. */
 int vfm_attention_fwd_ex(const void* qkv, void* out, int n_seq, int seq_len, int heads, int mode, void* stream);
 /* Cross attention: q [n_seq*q_len, >= heads*64] (row pitch q_ld), kv [n_seq*kv_len, 2*heads*64] packed (k | v),
  * out [n_seq*q_len, heads*64] (row pitch out_ld). Replaces the attention core of
