@@ -82,6 +82,9 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #ifndef VFM_APP_SCORES_ON_OUTPUT
 #define VFM_APP_SCORES_ON_OUTPUT 0   // the extra key's scores are computed by the softmax warps at unit start (0) or, a unit
 #endif                               // ahead, by the output warps (1: measured slower, 0.277 against 0.263 ms)
+#ifndef VFM_APP_EARLY_PROBE
+#define VFM_APP_EARLY_PROBE 0   // 1: probe the consumer pass's two barriers (non-blocking test_wait) from the end of the MUFU pass
+#endif                          // (measured slower: 0.266 against 0.260 ms per 36-window launch, same box — the probes lengthen the exclusive pass)
 #ifndef VFM_APP_HANDOFF
 #define VFM_APP_HANDOFF 1   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token):
 #endif                      // 1 = one token per warpgroup pair (256 threads), 2 = one per SM sub-partition (warp pair, 64 threads)
@@ -698,6 +701,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         // instead of the 16 the pipe needs. A fake data dependence on a later exponential (round 1's trick) only
         // moves the wait, and warp-level barriers are scheduled across; real control flow is what ptxas respects.
         const bool more = t + 1 < total_tiles;
+        bool ready = false;   // both barriers of the consumer pass were seen complete from inside the MUFU pass
         if (sched_mask & 1u) {
 #pragma unroll
           for (int i = 0; i < 64; ++i) {
@@ -706,14 +710,26 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             s[2 * i] = __float_as_uint(fast_exp2(x0));
             s[2 * i + 1] = __float_as_uint((kPoly != 0 && (i % (kPoly ? kPoly : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1));
           }
+#if VFM_APP_EARLY_PROBE
+          // A completed mbarrier wait still costs ~100 clk of round trip, twice, at the head of the consumer pass — on the
+          // chain that decides the tile period. Probe both barriers here instead (non-blocking test_wait), where the warp
+          // issues one instruction in eight: the parity operands carry a fake dependence on two of the LAST exponentials
+          // (their sign bit, always 0), so ptxas cannot hoist the probes to the top of the pass, where S(t+1) / PV(t-1)
+          // have not completed yet. A miss falls back to the blocking waits below.
+          const bool ok_s = !more || mbar_test_wait(&s_full[x], sign_gate(static_cast<uint32_t>((t + 1) & 1), s[118]));
+          const bool ok_p = t == 0 || mbar_test_wait(&p_free[x], sign_gate(static_cast<uint32_t>((t - 1) & 1), s[119]));
+          ready = ok_s && ok_p;
+#endif
         }
         if (sched_mask & 2u) {
 #if VFM_APP_HANDOFF
           named_bar_arrive(bar_other, kBarThreads);   // the pipe goes to the partner
 #endif
           if (quad == 0) APP_TRACE(x, t, 7);
-          if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
-          if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
+          if (!ready) {
+            if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
+            if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
+          }
           tc_fence_after();
           if (quad == 0) APP_TRACE(x, t, 1);
 #pragma unroll
