@@ -50,8 +50,7 @@ MEAN, STD = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
 # algorithmic FLOPs (2*M*N*K), SURVEY.md §8d
 FLOP_PER_CROP = {
     "gemm_bias_bf16": 24 * 2 * TOKENS * 1024 * 3072 + 2 * 1024 * 4096 * 1024,          # qkv x24 + head fusion conv
-    "gemm_bias_ls_residual": 24 * 2 * TOKENS * 1024 * 1024 + 20 * 2 * TOKENS * 1024 * 4096,  # proj x24 + fc2 x20 (TMA reduce-add)
-    "gemm_bias_ls_residual_tap": 4 * 2 * TOKENS * 1024 * 4096,                                # fc2 of blocks 7/11/15/23 (+ feature tap)
+    "gemm_bias_ls_residual": 24 * 2 * TOKENS * 1024 * 1024 + 24 * 2 * TOKENS * 1024 * 4096,  # proj x24 + fc2 x24 (TMA reduce-add; the taps are written by the next LayerNorm pass)
     "gemm_bias_gelu_bf16": 24 * 2 * TOKENS * 4096 * 1024,                                # fc1
     "attention_fwd": 24 * 4 * 16 * TOKENS * TOKENS * 64,                                  # QK^T + PV
     "gemm_patch_embed": 2 * 1024 * 768 * 1024,
@@ -59,6 +58,25 @@ FLOP_PER_CROP = {
     "gemm_cls_nchw": 2 * 16384 * 256 * 19,
 }
 FLOP_PER_IMAGE = CROPS_PER_IMAGE * sum(FLOP_PER_CROP.values())
+
+def flop_table(fold_bits: int):
+    """FLOP_PER_CROP under the launch names of the folded-LayerNorm schedule of vfm_vit_forward (VFM_LN_FOLD, default 3):
+    bit 0 = norm1 folded (20 of 24 fc2 GEMMs emit bf16(x) + row statistics, 20 qkv GEMMs apply them; norm1 of blocks 0, 8, 12,
+    16 stays a kernel), bit 1 = norm2 folded (24 proj GEMMs emit, 24 fc1 GEMMs apply)."""
+    QKV, PROJ, FC1 = 2 * TOKENS * 1024 * 3072, 2 * TOKENS * 1024 * 1024, 2 * TOKENS * 4096 * 1024
+    FC2, FUSION = FC1, 2 * 1024 * 4096 * 1024
+    n1 = 20 if fold_bits & 1 else 0
+    n2 = 24 if fold_bits & 2 else 0
+    t = dict(FLOP_PER_CROP)
+    t.update({
+        "gemm_bias_bf16": (24 - n1) * QKV + FUSION, "gemm_lnfold_bf16": n1 * QKV,
+        "gemm_bias_gelu_bf16": (24 - n2) * FC1, "gemm_lnfold_gelu_bf16": n2 * FC1,
+        "gemm_bias_ls_residual": (24 - n2) * PROJ + (24 - n1) * FC2,
+        "gemm_bias_ls_residual_stats": n2 * PROJ, "gemm_bias_ls_residual_stats_k": n1 * FC2,
+    })
+    t = {k: v for k, v in t.items() if v}
+    assert sum(t.values()) == sum(FLOP_PER_CROP.values())
+    return t
 
 
 def config_table(cfg_id: int, crops_per_pass: int):
@@ -387,7 +405,8 @@ def run_b200_arm(args):
         crops_per_run = K * B * n_windows
         # per-family algorithmic FLOPs: the full table for config 2; for the EVA02 config the attention core has the same
         # shape (1025 tokens, 16 heads x 64) — the other configs report time shares only
-        flop_per_crop = FLOP_PER_CROP if args.config == 2 else ({"attention_fwd": FLOP_PER_CROP["attention_fwd"]} if args.config == 4 else {})
+        table2 = flop_table(int(os.environ.get("VFM_LN_FOLD", "3")))
+        flop_per_crop = table2 if args.config == 2 else ({"attention_fwd": FLOP_PER_CROP["attention_fwd"]} if args.config == 4 else {})
         flop_per_image = FLOP_PER_IMAGE if args.config == 2 else None
         fam = {}
         for name, (cnt, ms) in prof.items():

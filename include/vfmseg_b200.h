@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VFM_ABI_VERSION 1
+#define VFM_ABI_VERSION 2   /* 2: VfmBlockParams grew the folded-LayerNorm weight sets */
 
 enum {
   VFM_OK = 0,
@@ -67,6 +67,27 @@ int vfm_gemm_bias_gelu_bf16(const void* A, int lda, const void* W, int ldw, cons
 int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, const float* bias,
                               const float* gamma, float* x, int ldx, void* tap, int tap_ld,
                               int tap_col0, int tokens_per_crop, int M, int N, int K, void* stream);
+
+/* The same residual update (x bit-identical to vfm_gemm_bias_ls_residual) that also prepares the LayerNorm which always
+ * follows it (dino_layers/block.py:89-90,112-113): xb[M,N] = bf16(x_new) and stats[row][N/128] = (sum, sum of squares) of
+ * x_new over each 128-column slot (fp32 pairs; written once per slot, no atomics). N % 256 == 0. */
+int vfm_gemm_bias_ls_residual_stats(const void* A, int lda, const void* W, int ldw, const float* bias,
+                                    const float* gamma, float* x, int ldx, void* xb, int ldxb, float* stats,
+                                    int M, int N, int K, void* stream);
+
+/* out = bf16(act(Linear(LayerNorm(x)))) with the norm folded away: A = bf16(x) [M,K] and stats [M][K/128] from
+ * vfm_gemm_bias_ls_residual_stats, Wf = bf16(ln_w * W), bias_f = b + W ln_b, colsum[n] = sum_k Wf[n,k];
+ * out = act(rstd_r * (acc - mean_r * colsum) + bias_f), act = exact-erf GELU when gelu != 0. K % 256 == 0.
+ * Replaces norm1 -> attn.qkv and norm2 -> mlp.fc1 -> GELU (dino_layers/block.py:89-90, attention.py:51, mlp.py:35-36). */
+int vfm_gemm_lnfold_bf16(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                         const float* stats, float eps, int gelu, void* out, int ldo, int M, int N, int K,
+                         void* stream);
+
+/* vfm_gemm_lnfold_bf16 (no activation) followed by the rotary embedding of vfm_gemm_bias_rope_bf16: norm1 -> attn.qkv ->
+ * RoPE of EVA02 (rein/models/backbones/eva_02.py:337-369) with the LayerNorm folded into the weights. */
+int vfm_gemm_lnfold_rope_bf16(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                              const float* stats, float eps, void* out, int ldo, int M, int N, int K,
+                              const float* cos_t, const float* sin_t, int rope_cols, int tokens_per_seq, void* stream);
 
 /* x[crop*(patches+1) + 1 + p, :] = acc + bias + pos[1 + p, :] for GEMM row = crop*patches + p.
  * Replaces PatchEmbed.proj (conv k=s=16) + pos-embed add, patch_embed.py:75-77, dino_v2.py:219-226. */
@@ -176,6 +197,12 @@ typedef struct {
   const void* fc1_w;  const float* fc1_b;
   const void* fc2_w;  const float* fc2_b;
   const float* ls2;
+  /* Optional (all three of a set, or null): the Linear that follows a LayerNorm with the norm folded in —
+   * wf = bf16(ln_w[k] * W[n, k]), bf = b + W ln_b (fp32), cs[n] = sum_k wf[n, k] (fp32, of the rounded weights).
+   * When present (and embed_dim % 256 == 0) vfm_vit_forward skips the LayerNorm pass: the preceding residual GEMM emits
+   * bf16(x) and the row statistics (vfm_gemm_bias_ls_residual_stats), this GEMM applies them (vfm_gemm_lnfold_bf16). */
+  const void* qkv_wf; const float* qkv_bf; const float* qkv_cs;   /* norm1 -> attn.qkv */
+  const void* fc1_wf; const float* fc1_bf; const float* fc1_cs;   /* norm2 -> mlp.fc1 */
 } VfmBlockParams;
 
 typedef struct {

@@ -112,9 +112,9 @@ def test_abi_header_and_binding_agree_and_library_exports_every_symbol():
     lib = _C.load()           # built by __graft_entry__.build(); dlopen works without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vfm_abi_version() == 1
+    assert lib.vfm_abi_version() == 2
     assert lib.vfm_launch_count() >= 0
-    assert ctypes.sizeof(_C.VfmBlockParams) == 14 * 8
+    assert ctypes.sizeof(_C.VfmBlockParams) == 20 * 8
     # argument validation happens before any CUDA call
     assert lib.vfm_layernorm(None, None, None, None, 0, 1024, 1e-6, None) == -1
     assert b"layernorm" in lib.vfm_last_error()
@@ -345,3 +345,33 @@ def test_round1_advice_guards():
     m2 = vfmseg_b200.MODELS.build(bad)
     with pytest.raises(NotImplementedError):
         m2.engine()
+
+
+def test_fold_layernorm_algebra():
+    """ops.fold_layernorm: rstd * (bf16(x) @ wf^T - mean * colsum) + bias_f reproduces Linear(LayerNorm(x)) (what
+    EpiTmaBf16LN computes from the statistics EpiTmaResidualStats emits), to bf16-operand accuracy, on the CPU."""
+    import torch
+    import torch.nn.functional as F
+    from vfmseg_b200.ops import fold_layernorm
+    g = torch.Generator().manual_seed(7)
+    M, C, N = 64, 256, 96
+    x = torch.randn(M, C, generator=g) * 1.5 + 0.4
+    x[:, 3] += 8.0
+    ln_w = 1 + 0.2 * torch.randn(C, generator=g)
+    ln_b = 0.1 * torch.randn(C, generator=g)
+    w = torch.randn(N, C, generator=g) * C ** -0.5
+    b = 0.1 * torch.randn(N, generator=g)
+    wf, bf, cs = fold_layernorm(w, b, ln_w, ln_b)
+    assert wf.dtype == torch.bfloat16 and bf.dtype == torch.float32 and cs.dtype == torch.float32
+    xs = x.view(M, C // 128, 128)
+    s, q = xs.sum(-1).sum(-1), (xs * xs).sum(-1).sum(-1)   # slot sums added in slot order, as the epilogue does
+    mean = s / C
+    rstd = torch.rsqrt(q / C - mean * mean + 1e-6)
+    acc = x.to(torch.bfloat16).float() @ wf.float().t()
+    got = rstd[:, None] * (acc - mean[:, None] * cs[None, :]) + bf[None, :]
+    ref = F.linear(F.layer_norm(x, (C,), ln_w, ln_b, 1e-6), w, b)
+    # the yardstick: the unfolded kernel pair rounds LayerNorm(x) and W to bf16
+    old = F.layer_norm(x, (C,), ln_w, ln_b, 1e-6).to(torch.bfloat16).float() @ w.to(torch.bfloat16).float().t() + b
+    e_new = (got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()
+    e_old = (old - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()
+    assert e_new < 5e-3 and e_new < 1.5 * e_old + 1e-4, (float(e_new), float(e_old))

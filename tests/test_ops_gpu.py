@@ -76,6 +76,55 @@ def test_gemm_residual_with_tap(ops):
     assert torch.equal(x, x2)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (2050, 1024, 1024), (1025, 1024, 4096), (36900, 1024, 1024), (37, 512, 64)])
+def test_gemm_residual_stats(ops, M, N, K):
+    """Residual GEMM that also emits bf16(x) and the LayerNorm statistics: x bit-identical to the reduce-add epilogue."""
+    a = _rand(M, K, seed=41, dtype=torch.bfloat16)
+    w = _rand(N, K, scale=K ** -0.5, seed=42, dtype=torch.bfloat16)
+    b = _rand(N, seed=43)
+    g = _rand(N, seed=44) * 0.3
+    x0 = _rand(M, N, seed=45) * 2 + 0.25
+    x_ref = ops.gemm_bias_ls_residual_(x0.clone(), a, w, b, g)
+    x = x0.clone()
+    xb, stats = ops.gemm_bias_ls_residual_stats_(x, a, w, b, g)
+    assert torch.equal(x, x_ref), f"x differs from the reduce-add path: max {(x - x_ref).abs().max().item():.3g}"
+    assert torch.equal(xb, x.to(torch.bfloat16)), "xb != bf16(x)"
+    xs = x.double().view(M, N // 128, 128)
+    _close(stats[..., 0], xs.sum(-1).float(), 1e-5, 1e-3, "slot sums")
+    _close(stats[..., 1], (xs * xs).sum(-1).float(), 1e-5, 1e-3, "slot sums of squares")
+    _close(x, x0 + g * (a.float() @ w.float().t() + b), 2e-3, 2e-3, "residual value")
+
+
+@pytest.mark.parametrize("M,C,N,gelu", [(300, 256, 768, False), (2050, 1024, 3072, False), (2050, 1024, 4096, True), (36900, 1024, 256, True)])
+def test_gemm_lnfold(ops, M, C, N, gelu):
+    """Linear(LayerNorm(x)) with the norm folded into the weights and applied by the epilogue from the emitted statistics,
+    against torch fp32 LayerNorm -> Linear (-> GELU) and against the unfolded kernel pair."""
+    K0 = 512
+    a = _rand(M, K0, seed=51, dtype=torch.bfloat16)
+    w0 = _rand(C, K0, scale=K0 ** -0.5, seed=52, dtype=torch.bfloat16)
+    x = _rand(M, C, seed=53) * 1.5 + 0.3
+    x[:, 7] += 6.0   # an outlier channel, as ViT residual streams have
+    xb, stats = ops.gemm_bias_ls_residual_stats_(x, a, w0, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda") * 0.5)
+    ln_w = 1 + 0.2 * _rand(C, seed=54)
+    ln_b = 0.1 * _rand(C, seed=55)
+    w = _rand(N, C, scale=C ** -0.5, seed=56)
+    b = _rand(N, seed=57) * 0.1
+    wf, bf, cs = ops.fold_layernorm(w, b, ln_w, ln_b)
+    got = ops.gemm_lnfold_bf16(xb, stats, wf, bf, cs, 1e-6, gelu=gelu).float()
+    ref = F.linear(F.layer_norm(x, (C,), ln_w, ln_b, 1e-6), w, b)
+    if gelu:
+        ref = F.gelu(ref)
+    xn = ops.layernorm(x, ln_w, ln_b, 1e-6)
+    wb = w.to(torch.bfloat16)
+    old = (ops.gemm_bias_gelu_bf16(xn, wb, b) if gelu else ops.gemm_bias_bf16(xn, wb, b)).float()
+    rms = ref.pow(2).mean().sqrt().item()
+    e_new = (got - ref).pow(2).mean().sqrt().item() / rms
+    e_old = (old - ref).pow(2).mean().sqrt().item() / rms
+    assert e_new < 6e-3, f"folded LayerNorm GEMM: rms error {e_new:.3g} of the output rms"
+    assert e_new < 1.5 * e_old + 1e-4, f"folded path ({e_new:.3g}) is less accurate than LayerNorm kernel + GEMM ({e_old:.3g})"
+    _close(got, ref, 3e-2, 3e-2 * rms, "gemm_lnfold_bf16")
+
+
 def test_patch_gather_and_embed(ops):
     B, H, W, C = 2, 96, 128, 256
     img = _rand(B, 3, H, W, seed=12)

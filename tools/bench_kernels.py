@@ -93,6 +93,18 @@ def main():
     rec("gemm fc1  [M,1024]x[4096,1024] +gelu", ms, best, 2.0 * M * H * C)
     ms, best = timeit(lambda: ops.gemm_bias_ls_residual_(x, a4, w2, bp, g), args.iters, flush=flush, label="gemm fc2  [M,4096]x[1024,4096] +residual")
     rec("gemm fc2  [M,4096]x[1024,4096] +residual", ms, best, 2.0 * M * H * C)
+    # folded-LayerNorm schedule: residual GEMMs that also emit bf16(x) + row statistics, and the GEMMs that consume them
+    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_stats_(x, a, wproj, bp, g), args.iters, flush=flush, label="gemm proj +residual +stats")
+    rec("gemm proj +residual +stats", ms, best, 2.0 * M * C * C)
+    ms, best = timeit(lambda: ops.gemm_bias_ls_residual_stats_(x, a4, w2, bp, g), args.iters, flush=flush, label="gemm fc2  +residual +stats")
+    rec("gemm fc2  +residual +stats", ms, best, 2.0 * M * H * C)
+    if not ONLY or "lnfold" in ONLY or "stats" in ONLY:
+        xb, st = ops.gemm_bias_ls_residual_stats_(x, a, wproj, bp, g)
+        cq, c1 = f32(3 * C), f32(H)
+        ms, best = timeit(lambda: ops.gemm_lnfold_bf16(xb, st, wqkv, bq, cq, 1e-6), args.iters, flush=flush, label="gemm qkv  lnfold")
+        rec("gemm qkv  lnfold", ms, best, 2.0 * M * 3 * C * C)
+        ms, best = timeit(lambda: ops.gemm_lnfold_bf16(xb, st, w1, b1, c1, 1e-6, gelu=True), args.iters, flush=flush, label="gemm fc1  lnfold +gelu")
+        rec("gemm fc1  lnfold +gelu", ms, best, 2.0 * M * H * C)
     qkv = bf(M, 3 * C)
     ms, best = timeit(lambda: ops.attention_fwd(qkv, args.crops, T, heads), args.iters, flush=flush, label="attention 16 heads S=1025 d=64")
     rec("attention 16 heads S=1025 d=64", ms, best, 4.0 * args.crops * heads * T * T * 64)

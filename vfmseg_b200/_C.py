@@ -24,7 +24,8 @@ class VfmPixelNorm(C.Structure):
 class VfmBlockParams(C.Structure):
     _fields_ = [(n, _p) for n in (
         "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",
-        "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+        "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2",
+        "qkv_wf", "qkv_bf", "qkv_cs", "fc1_wf", "fc1_bf", "fc1_cs")]
 
 
 class VfmVitParams(C.Structure):
@@ -56,6 +57,9 @@ SIGNATURES = {
     "vfm_gemm_bias_rope_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "vfm_gemm_bias_gelu_bf16": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_bias_ls_residual": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "vfm_gemm_bias_ls_residual_stats": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p]),
+    "vfm_gemm_lnfold_bf16": (_i, [_p, _i, _p, _i, _p, _p, _p, _f, _i, _p, _i, _i, _i, _i, _p]),
+    "vfm_gemm_lnfold_rope_bf16": (_i, [_p, _i, _p, _i, _p, _p, _p, _f, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "vfm_gemm_patch_embed": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "vfm_gemm_convt2x2_gelu": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "vfm_gemm_cls_nchw": (_i, [_p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p]),
@@ -124,8 +128,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table diverge
         fn.restype = res
         fn.argtypes = args
-    if lib.vfm_abi_version() != 1:
-        raise VfmError(f"ABI version mismatch: library {lib.vfm_abi_version()}, binding 1")
+    if lib.vfm_abi_version() != 2:
+        raise VfmError(f"ABI version mismatch: library {lib.vfm_abi_version()}, binding 2")
     _lib = lib
     return lib
 

@@ -171,7 +171,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   if (!A || !W) return fail(VFM_ERR_INVALID, "%s: null operand", name);
   if (M <= 0 || N <= 0 || K <= 0 || (N % 32) != 0 || (K % 8) != 0)
     return fail(VFM_ERR_INVALID, "%s: need M,N,K > 0, N %% 32 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", name, M, N, K);
-  using Cfg = GemmCfg<BLOCK_N, CTA_GROUP>;
+  using Cfg = GemmCfg<BLOCK_N, CTA_GROUP, epi_warp_bytes<Epi>::value>;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, lda, GEMM_BLOCK_M);
   if (rc) return rc;
@@ -184,8 +184,11 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
     } else {
       if ((rc = make_tmap_ex(&tout, od.ptr, M, N, od.ld, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
     }
-  } else if constexpr (Epi::kMode == EPI_TMA_RED_F32) {
+  } else if constexpr (Epi::kMode == EPI_TMA_RED_F32 || Epi::kMode == EPI_TMA_RES_STATS) {
     if ((rc = make_tmap_ex(&tout, od.ptr, od.rows > 0 ? od.rows : M, N, od.ld, 32, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4))) return rc;
+  }
+  if constexpr (Epi::kMode == EPI_TMA_RES_STATS) {
+    if (N % BLOCK_N) return fail(VFM_ERR_INVALID, "%s: N must be a multiple of %d", name, BLOCK_N);
   }
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, CTA_GROUP, Epi>;
   static bool attr_done = false;  // per template instantiation
@@ -339,6 +342,52 @@ int vfm_gemm_bias_ls_residual(const void* A, int lda, const void* W, int ldw, co
   }
   EpiResidual e{x, ldx, bias, gamma, BF(tap), tap_ld, tap_col0, FastDiv(tokens_per_crop > 0 ? tokens_per_crop : 1)};
   return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_tap");
+}
+
+int vfm_gemm_bias_ls_residual_stats(const void* A, int lda, const void* W, int ldw, const float* bias, const float* gamma,
+                                    float* x, int ldx, void* xb, int ldxb, float* stats, int M, int N, int K, void* stream) {
+  if (!x || !bias || !gamma || !xb || !stats || (ldx % 4) || (ldxb % 8) || (N % 256) ||
+      (reinterpret_cast<uintptr_t>(stats) & 15))
+    return fail(VFM_ERR_INVALID, "gemm_bias_ls_residual_stats: bad x/xb/stats/bias/gamma, or N %% 256 != 0");
+  // staging shape (gemm_sm100.cuh, EpiTmaResidualStats): serial single box when the main loop is long enough to hide it
+  // (K >= 2048: mlp.fc2), deep otherwise; VFM_RS_MODE=1 / 2 forces deep / serial (experiments)
+  static const int rs_mode = [] { const char* e = getenv("VFM_RS_MODE"); return e ? atoi(e) : 0; }();
+  const bool deep = rs_mode == 1 || (rs_mode == 0 && K < 2048);
+  static const int l2pf = [] { const char* e = getenv("VFM_RS_L2PF"); return e ? atoi(e) : 0; }();   // L2 prefetch of the next tile's old x: measured slower (x read from DRAM twice: +165 MB per fc2 launch)
+  int rc;
+  if (deep) {
+    EpiTmaResidualStats<true> e{bias, gamma, reinterpret_cast<float2*>(stats), N / 128, l2pf, {}};
+    if ((rc = make_tmap_ex(&e.tmap_xb, xb, M, N, ldxb, 32, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2))) return rc;
+    return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_stats", OutDesc{x, ldx});
+  }
+  EpiTmaResidualStats<false> e{bias, gamma, reinterpret_cast<float2*>(stats), N / 128, l2pf, {}};
+  if ((rc = make_tmap_sw(&e.tmap_xb, xb, M, N, ldxb, 32, 32))) return rc;
+  return launch_gemm<256, 2>(A, lda, W, ldw, M, N, K, e, S(stream), "gemm_bias_ls_residual_stats_k", OutDesc{x, ldx});
+}
+
+int vfm_gemm_lnfold_bf16(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                         const float* stats, float eps, int gelu, void* out, int ldo, int M, int N, int K, void* stream) {
+  if (!out || !bias_f || !colsum || !stats || (ldo % 8) || (K % 256) || (reinterpret_cast<uintptr_t>(stats) & 15))
+    return fail(VFM_ERR_INVALID, "gemm_lnfold_bf16: bad out/bias/colsum/stats/ldo, or K %% 256 != 0");
+  const float2* st = reinterpret_cast<const float2*>(stats);
+  if (gelu) {
+    EpiTmaBf16LN<true> e{bias_f, colsum, st, K / 128, M, 1.f / static_cast<float>(K), eps};
+    return launch_gemm<256, 2>(A, lda, Wf, ldw, M, N, K, e, S(stream), "gemm_lnfold_gelu_bf16", OutDesc{out, ldo});
+  }
+  EpiTmaBf16LN<false> e{bias_f, colsum, st, K / 128, M, 1.f / static_cast<float>(K), eps};
+  return launch_gemm<256, 2>(A, lda, Wf, ldw, M, N, K, e, S(stream), "gemm_lnfold_bf16", OutDesc{out, ldo});
+}
+
+int vfm_gemm_lnfold_rope_bf16(const void* A, int lda, const void* Wf, int ldw, const float* bias_f, const float* colsum,
+                              const float* stats, float eps, void* out, int ldo, int M, int N, int K, const float* cos_t,
+                              const float* sin_t, int rope_cols, int tokens_per_seq, void* stream) {
+  if (!out || !bias_f || !colsum || !stats || (ldo % 8) || (K % 256) || (reinterpret_cast<uintptr_t>(stats) & 15) || !cos_t || !sin_t ||
+      tokens_per_seq < 2 || rope_cols < 0 || (rope_cols % 64) || rope_cols > N ||
+      ((reinterpret_cast<uintptr_t>(cos_t) | reinterpret_cast<uintptr_t>(sin_t)) & 15))
+    return fail(VFM_ERR_INVALID, "gemm_lnfold_rope_bf16: bad args (K %% 256 == 0, rope_cols %% 64 == 0, 16-byte aligned tables / stats)");
+  EpiTmaBf16LNRope e{{bias_f, colsum, reinterpret_cast<const float2*>(stats), K / 128, M, 1.f / static_cast<float>(K), eps},
+                     cos_t, sin_t, rope_cols, FastDiv(tokens_per_seq)};
+  return launch_gemm<256, 2>(A, lda, Wf, ldw, M, N, K, e, S(stream), "gemm_lnfold_rope_bf16", OutDesc{out, ldo});
 }
 
 int vfm_gemm_patch_embed_ex(const void* A, int lda, const void* W, int ldw, const float* bias, const float* pos, float* x,
@@ -1047,7 +1096,8 @@ size_t vfm_vit_workspace_bytes(const VfmVitParams* p, int n_crops, int gh, int g
   size_t hid = M * p->mlp_hidden * 2;
   const size_t patches = static_cast<size_t>(n_crops) * gh * gw * 768 * 2;
   if (patches > hid) hid = patches;
-  return align_up(M * C * 4, 256) + 2 * align_up(M * C * 2, 256) + align_up(M * 3 * C * 2, 256) + align_up(hid, 256);
+  return align_up(M * C * 4, 256) + 2 * align_up(M * C * 2, 256) + align_up(M * 3 * C * 2, 256) + align_up(hid, 256) +
+         align_up(M * (C / 128 + 1) * 8, 256);   // LayerNorm statistics: (sum, sum of squares) per row and 128-column slot
 }
 
 int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w,
@@ -1067,6 +1117,18 @@ int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const Vfm
   void* att = ws;                                     ws += align_up(static_cast<size_t>(M) * C * 2, 256);
   void* qkv = ws;                                     ws += align_up(static_cast<size_t>(M) * 3 * C * 2, 256);
   void* hid = ws;
+  {
+    size_t hb = static_cast<size_t>(M) * Hd * 2;
+    const size_t pb = static_cast<size_t>(n_crops) * P * 768 * 2;
+    if (pb > hb) hb = pb;
+    ws += align_up(hb, 256);
+  }
+  float* stats = reinterpret_cast<float*>(ws);
+  // LayerNorm folding (EpiTmaResidualStats -> EpiTmaBf16LN): a residual GEMM whose successor is a plain LayerNorm + Linear
+  // also writes bf16(x) into xn and the row statistics; the successor runs on the folded weights. Not folded: norm1 of
+  // block 0 (x comes from the patch embedding) and the norm1 passes that also emit a feature tap.
+  static const int fold_env = [] { const char* e = getenv("VFM_LN_FOLD"); return e ? atoi(e) : 3; }();   // bit 0: norm1 (fc2 -> qkv), bit 1: norm2 (proj -> fc1)
+  const bool fold_ok1 = (fold_env & 1) && (C % 256) == 0, fold_ok2 = (fold_env & 2) && (C % 256) == 0;
   int rc;
   // tokens: patch gather -> patch-embed GEMM (+bias +pos) ; cls rows
   if ((rc = vfm_patch_gather(img, is_u8, nrm, img_h, img_w, crops, n_crops, gh, gw, hid, stream))) return rc;
@@ -1084,13 +1146,37 @@ int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const Vfm
       tap_col0 = next_tap * C;
       ++next_tap;
     }
-    if ((rc = vfm_layernorm_tap(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, tap, p->n_taps * C, tap_col0, T, stream))) return rc;
-    if ((rc = vfm_gemm_bias_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, 3 * C, M, 3 * C, C, stream))) return rc;
+    // norm1 + qkv
+    const bool fold1 = fold_ok1 && l > 0 && tap == nullptr && b.qkv_wf && b.qkv_bf && b.qkv_cs;
+    if (fold1) {
+      if ((rc = vfm_gemm_lnfold_bf16(xn, C, b.qkv_wf, C, b.qkv_bf, b.qkv_cs, stats, p->ln_eps, 0, qkv, 3 * C, M, 3 * C, C, stream))) return rc;
+    } else {
+      if ((rc = vfm_layernorm_tap(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, tap, p->n_taps * C, tap_col0, T, stream))) return rc;
+      if ((rc = vfm_gemm_bias_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, 3 * C, M, 3 * C, C, stream))) return rc;
+    }
     if ((rc = vfm_attention_fwd(qkv, att, n_crops, T, p->heads, stream))) return rc;
-    if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, b.ls1, x, C, nullptr, 0, 0, T, M, C, C, stream))) return rc;
-    if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
-    if ((rc = vfm_gemm_bias_gelu_bf16(xn, C, b.fc1_w, C, b.fc1_b, hid, Hd, M, Hd, C, stream))) return rc;
-    if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, nullptr, 0, 0, T, M, C, Hd, stream))) return rc;
+    // proj (+ residual) -> norm2 + fc1 (+ GELU)
+    const bool fold2 = fold_ok2 && b.fc1_wf && b.fc1_bf && b.fc1_cs;
+    if (fold2) {
+      if ((rc = vfm_gemm_bias_ls_residual_stats(att, C, b.proj_w, C, b.proj_b, b.ls1, x, C, xn, C, stats, M, C, C, stream))) return rc;
+      if ((rc = vfm_gemm_lnfold_bf16(xn, C, b.fc1_wf, C, b.fc1_bf, b.fc1_cs, stats, p->ln_eps, 1, hid, Hd, M, Hd, C, stream))) return rc;
+    } else {
+      if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, b.ls1, x, C, nullptr, 0, 0, T, M, C, C, stream))) return rc;
+      if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
+      if ((rc = vfm_gemm_bias_gelu_bf16(xn, C, b.fc1_w, C, b.fc1_b, hid, Hd, M, Hd, C, stream))) return rc;
+    }
+    // fc2 (+ residual); it prepares the next block's norm1 when that one is folded
+    bool next_fold = false;
+    if (fold_ok1 && l + 1 < p->depth) {
+      const VfmBlockParams& nb = p->blocks[l + 1];
+      const bool next_tap_here = next_tap < p->n_taps && p->tap_blocks[next_tap] == l;
+      next_fold = !next_tap_here && nb.qkv_wf && nb.qkv_bf && nb.qkv_cs;
+    }
+    if (next_fold) {
+      if ((rc = vfm_gemm_bias_ls_residual_stats(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, xn, C, stats, M, C, Hd, stream))) return rc;
+    } else {
+      if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.fc2_w, Hd, b.fc2_b, b.ls2, x, C, nullptr, 0, 0, T, M, C, Hd, stream))) return rc;
+    }
   }
   if (next_tap < p->n_taps && p->tap_blocks[next_tap] == p->depth - 1) {
     if ((rc = vfm_layernorm_tap(x, nullptr, nullptr, nullptr, M, C, p->ln_eps, taps, p->n_taps * C, next_tap * C, T, stream))) return rc;

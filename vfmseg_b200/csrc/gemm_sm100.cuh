@@ -50,20 +50,23 @@ constexpr int GEMM_EPI_WARPS = 8;
 // row-per-thread writes and for both column-per-lane read patterns, and exactly the 4 KB of one TMA box
 __device__ __forceinline__ int stg_idx(int r, int c) { return r * 32 + (c ^ r); }
 
-enum EpiMode { EPI_F32 = 0, EPI_BF16X2 = 1, EPI_DIRECT = 2, EPI_TMA_BF16 = 3, EPI_TMA_RED_F32 = 4 };
+enum EpiMode { EPI_F32 = 0, EPI_BF16X2 = 1, EPI_DIRECT = 2, EPI_TMA_BF16 = 3, EPI_TMA_RED_F32 = 4, EPI_TMA_RES_STATS = 5 };
 
-template <int BLOCK_N, int CTA_GROUP>
+template <int BLOCK_N, int CTA_GROUP, int EPI_WARP_BYTES = 4096>
 struct GemmCfg {
   static constexpr int kBRows = BLOCK_N / CTA_GROUP;                  // W rows staged per CTA
   static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int kBBytes = kBRows * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * 4096;   // per warp: 32x32 fp32 transpose tile or one 4 KB TMA box
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiStageBytes;
+  static constexpr int kEpiWarpBytes = EPI_WARP_BYTES;           // per warp: 32x32 fp32 transpose tile or one 4 KB TMA box (12 KB: EPI_TMA_RES_STATS)
+  static constexpr int kEpiStageBytes = GEMM_EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kEpiStageBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;   // 2 accumulator stages
   static constexpr int kEpiSplit = (BLOCK_N >= 64) ? 2 : 1;                  // column halves
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + kBarBytes;
+  static_assert((2 * kStages + 6 + 2 * GEMM_EPI_WARPS) * 8 <= kBarBytes, "barrier block too small");
 };
 
 // ------------------------------------------------------------------ epilogues
@@ -111,6 +114,17 @@ template <class E> struct epi_needs_row<E, std::enable_if_t<E::kNeedsRow>> : std
 // instead of reduce-adding it at row_base
 template <class E, class = void> struct epi_plain_store : std::false_type {};
 template <class E> struct epi_plain_store<E, std::enable_if_t<E::kPlainStore>> : std::true_type {};
+
+// epilogues that need more than one 4 KB box of staging per warp declare kStageBytesPerWarp
+template <class E, class = void> struct epi_warp_bytes : std::integral_constant<int, 4096> {};
+template <class E> struct epi_warp_bytes<E, std::enable_if_t<(E::kStageBytesPerWarp > 0)>> : std::integral_constant<int, E::kStageBytesPerWarp> {};
+
+template <class E, class = void> struct epi_has_row_ctx : std::false_type {};
+template <class E> struct epi_has_row_ctx<E, std::enable_if_t<E::kHasRowCtx>> : std::true_type {};
+template <class E, bool = epi_has_row_ctx<E>::value> struct epi_row_ctx { struct type {}; };
+template <class E> struct epi_row_ctx<E, true> { using type = typename E::RowCtx; };
+template <class E, class = void> struct epi_deep : std::false_type {};
+template <class E> struct epi_deep<E, std::enable_if_t<E::kDeepStaging>> : std::true_type {};
 
 template <bool kGelu>
 struct EpiTmaBf16 {             // out = bf16(act(acc + bias)); act = exact-erf GELU (fc1) or identity (qkv, fusion conv)
@@ -198,6 +212,97 @@ struct EpiTmaResidual {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0) + i);
       v[4 * i] = __fmul_rn(g.x, v[4 * i] + b.x); v[4 * i + 1] = __fmul_rn(g.y, v[4 * i + 1] + b.y);
       v[4 * i + 2] = __fmul_rn(g.z, v[4 * i + 2] + b.z); v[4 * i + 3] = __fmul_rn(g.w, v[4 * i + 3] + b.w);
+    }
+  }
+};
+
+// The residual update that also prepares the NEXT LayerNorm (block.py:89-114: x = x + ls(f(norm(x))) is always followed
+// by another norm of the new x): x_new = x + gamma * (acc + bias) is formed in the SM (old x arrives through the TMA
+// engine, one 32 x 32 box a chunk ahead, its L2 prefetch a tile ahead), and leaves three ways:
+//   x      fp32, plain TMA store (same bits as the reduce-add of EpiTmaResidual: one fp32 add, round to nearest);
+//   xb     bf16(x_new), TMA store — the A operand of the next GEMM, whose weights carry the LayerNorm's gamma and whose
+//          epilogue (EpiTmaBf16LN) applies mean / rstd per row: the layernorm_kernel pass (read 4 B + write 2 B per
+//          element) disappears, at the price of this 2 B write and of reading x in the SM instead of in L2;
+//   stats  (sum, sum of squares) of every row over the 128 columns this warp owns -> stats[row][n_slots] with
+//          slot = column / 128, written once, summed in slot order by the consumer (no atomics: bit-reproducible).
+// Two staging shapes. kDeep: 12 KB per epilogue warp (two fp32 boxes, the next chunk's old x in flight while this one is
+// processed, + a bf16 box of two chunks) — leaves the main loop a 4-stage ring. !kDeep: ONE 4 KB box per warp, everything
+// serial (load -> modify in place -> store fp32 -> same buffer: store bf16 -> next load; ~2.5 k clk per chunk) — the main
+// loop keeps its 6 stages; for the K = 4096 GEMM (mlp.fc2: 36 k clk of MMA per tile) the epilogue has that time to spare,
+// and measured with the 4-stage ring that GEMM lost 28 % (0.250 against 0.195 ms: three stages in flight do not cover
+// the L2 latency of the operand stream).
+template <bool kDeep>
+struct EpiTmaResidualStats {
+  static constexpr int kMode = EPI_TMA_RES_STATS;
+  static constexpr bool kDeepStaging = kDeep;
+  static constexpr int kStageBytesPerWarp = kDeep ? 12288 : 4096;
+  const float* bias; const float* gamma; float2* stats; int n_slots; int l2_prefetch;
+  alignas(64) CUtensorMap tmap_xb;   // bf16 [M, N]; kDeep: box {64 cols, 32 rows} SWIZZLE_128B, else {32 cols, 32 rows} SWIZZLE_64B
+};
+
+// out = bf16(act(rstd_r * (acc - mean_r * colsum) + bias)): Linear(LayerNorm(x)) with the norm folded away
+// (dino_layers/block.py:89-90,112-113 norm1 -> attn.qkv, norm2 -> mlp.fc1). A = bf16(x) un-normalised, W' = bf16(ln_w * W)
+// (folded along K on the host), colsum[n] = sum_k W'[n, k] (of the ROUNDED weights, so the mean term cancels what the
+// tensor core summed), bias = b + W ln_b (fp32). mean / rstd come from the (sum, sum of squares) slots EpiTmaResidualStats
+// wrote for the row, added in slot order; biased variance and eps as torch.nn.LayerNorm.
+template <bool kGelu>
+struct EpiTmaBf16LN {
+  static constexpr int kMode = EPI_TMA_BF16;
+  static constexpr bool kStore4D = false;
+  static constexpr bool kNeedsRow = true;
+  static constexpr bool kHasRowCtx = true;   // mean / rstd of the row are computed once per tile, not once per 32-column chunk
+  const float* bias; const float* colsum; const float2* stats; int n_slots; int M; float inv_n; float eps;
+  struct RowCtx { float rstd, nm; };
+  __device__ __forceinline__ RowCtx row_ctx(int row) const {
+    const float2* sp = stats + static_cast<size_t>(row < M ? row : M - 1) * n_slots;
+    float sum = 0.f, sq = 0.f;
+    for (int i = 0; i < n_slots; i += 2) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(sp + i));
+      sum += t.x; sq += t.y; sum += t.z; sq += t.w;
+    }
+    const float mean = sum * inv_n;
+    return {rsqrtf(fmaxf(sq * inv_n - mean * mean, 0.f) + eps), -mean};
+  }
+  __device__ __forceinline__ void apply_ctx(const RowCtx& rc, int row, int col0, float (&v)[32]) const {
+    const float rstd = rc.rstd, nm = rc.nm;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + i);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(colsum + col0) + i);
+      v[4 * i] = fmaf(rstd, fmaf(nm, c.x, v[4 * i]), b.x); v[4 * i + 1] = fmaf(rstd, fmaf(nm, c.y, v[4 * i + 1]), b.y);
+      v[4 * i + 2] = fmaf(rstd, fmaf(nm, c.z, v[4 * i + 2]), b.z); v[4 * i + 3] = fmaf(rstd, fmaf(nm, c.w, v[4 * i + 3]), b.w);
+      if constexpr (kGelu) {
+        v[4 * i] = gelu_erf(v[4 * i]); v[4 * i + 1] = gelu_erf(v[4 * i + 1]);
+        v[4 * i + 2] = gelu_erf(v[4 * i + 2]); v[4 * i + 3] = gelu_erf(v[4 * i + 3]);
+      }
+    }
+  }
+};
+
+// EpiTmaBf16LN followed by EpiTmaBf16Rope's rotation: norm1 -> attn.qkv + 2-D RoPE of EVA02 (eva_02.py:337-369) with the
+// LayerNorm folded into the weights.
+struct EpiTmaBf16LNRope {
+  static constexpr int kMode = EPI_TMA_BF16;
+  static constexpr bool kStore4D = false;
+  static constexpr bool kNeedsRow = true;
+  static constexpr bool kHasRowCtx = true;
+  EpiTmaBf16LN<false> ln; const float* cos_t; const float* sin_t; int rope_cols; FastDiv tokens_per_seq;
+  using RowCtx = EpiTmaBf16LN<false>::RowCtx;
+  __device__ __forceinline__ RowCtx row_ctx(int row) const { return ln.row_ctx(row); }
+  __device__ __forceinline__ void apply_ctx(const RowCtx& rc, int row, int col0, float (&v)[32]) const {
+    ln.apply_ctx(rc, row, col0, v);
+    if (col0 >= rope_cols) return;   // warp-uniform: the v third
+    int seq, tok;
+    tokens_per_seq.divmod(row, seq, tok);
+    if (tok == 0) return;
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + static_cast<size_t>(tok - 1) * 64 + (col0 & 63));
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + static_cast<size_t>(tok - 1) * 64 + (col0 & 63));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 c = __ldg(cp + i), sn = __ldg(sp + i);
+      const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+      v[4 * i] = x0 * c.x - x1 * sn.x; v[4 * i + 1] = x1 * c.y + x0 * sn.y;
+      v[4 * i + 2] = x2 * c.z - x3 * sn.z; v[4 * i + 3] = x3 * c.w + x2 * sn.w;
     }
   }
 };
@@ -331,8 +436,8 @@ struct EpiF32 {
 template <int BLOCK_N, int CTA_GROUP, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, int M, int N, int K, Epi epi) {
-  using Cfg = GemmCfg<BLOCK_N, CTA_GROUP>;
+                    const __grid_constant__ CUtensorMap tmap_out, int M, int N, int K, const __grid_constant__ Epi epi) {
+  using Cfg = GemmCfg<BLOCK_N, CTA_GROUP, epi_warp_bytes<Epi>::value>;
   constexpr int kStages = Cfg::kStages;
   constexpr int TILE_M = GEMM_BLOCK_M * CTA_GROUP;
   extern __shared__ uint8_t smem_raw[];
@@ -347,6 +452,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = bars + 2 * kStages;    // [2]        MMA -> epilogue (each CTA has its own)
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA (leader's copy is the live one)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_ld = bars + 2 * kStages + 6;   // [8 epilogue warps][2]  TMA -> epilogue warp (EPI_TMA_RES_STATS: old residual boxes)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -367,6 +473,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // full: one arrival (the leader producer's expect_tx); the peer CTA contributes only transaction bytes
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * Cfg::kEpiSplit * CTA_GROUP); }
+    if constexpr (Epi::kMode == EPI_TMA_RES_STATS) {
+      for (int s = 0; s < 2 * GEMM_EPI_WARPS; ++s) mbar_init(&epi_ld[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols, CTA_GROUP>(tmem_slot);
@@ -439,13 +548,209 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 4) >> 2;
     if (half < Cfg::kEpiSplit) {
       constexpr int kColsPerSplit = BLOCK_N / Cfg::kEpiSplit;
-      float* stg = epi_stage + (warp - 4) * 1024;   // 4096 B per warp
+      float* stg = epi_stage + (warp - 4) * (Cfg::kEpiWarpBytes / 4);   // 4096 B per warp (12288: EPI_TMA_RES_STATS)
       int acc = 0; uint32_t acc_phase = 0;
 #ifdef VFM_EPI_TIMING
       unsigned long long dbg[5] = {0, 0, 0, 0, 0};
 #endif
+      if constexpr (Epi::kMode == EPI_TMA_RES_STATS && !epi_deep<Epi>::value) {
+        // ---- residual + LayerNorm statistics, serial single-box staging (see EpiTmaResidualStats<false>)
+        constexpr int kChunks = kColsPerSplit / 32;
+        uint8_t* buf = reinterpret_cast<uint8_t*>(stg);
+        uint64_t* ldb = epi_ld + (warp - 4) * 2;
+        const int sw = lane & 7;             // SWIZZLE_128B (fp32 box, 128-byte rows): 16-byte chunk index ^= row % 8
+        const int sw64 = (lane >> 1) & 3;    // SWIZZLE_64B (bf16 box, 64-byte rows): 16-byte chunk index ^= (row / 2) % 4
+        auto tile_rc = [&](int tile, int& row, int& col) {
+          const int mb = tile / n_tiles, nb = tile - mb * n_tiles;
+          row = mb * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M + quad * 32;
+          col = nb * BLOCK_N + half * kColsPerSplit;
+        };
+        auto issue_load = [&](int col, int row) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(ldb, 4096);
+            tma_load_2d(buf, &tmap_out, ldb, col, row);
+          }
+          __syncwarp();
+        };
+        uint32_t q = 0;
+        if (first_tile < num_tiles) {
+          int r0, c0;
+          tile_rc(first_tile, r0, c0);
+          issue_load(c0, r0);
+        }
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+          int row_base, colw;
+          tile_rc(tile, row_base, colw);
+          const int next_tile = tile + tile_step;
+          int nrow = 0, ncol = 0;
+          if (next_tile < num_tiles) {   // the next tile's old x: into L2 now
+            tile_rc(next_tile, nrow, ncol);
+            if (epi.l2_prefetch && lane < kChunks) tma_prefetch_l2_2d(&tmap_out, ncol + 32 * lane, nrow);
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerSplit;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c, ++q) {
+            uint32_t r[32];
+            tmem_ld32(taddr + 32 * c, r);
+            mbar_wait(ldb, q & 1u);
+            tmem_ld_wait();
+            const int col0 = colw + 32 * c;
+            uint8_t* rowp = buf + lane * 128;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = *reinterpret_cast<const float4*>(rowp + ((j ^ sw) << 4));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(epi.gamma + col0) + j);
+              v[4 * j] = __fadd_rn(o.x, __fmul_rn(g.x, __uint_as_float(r[4 * j]) + b.x));
+              v[4 * j + 1] = __fadd_rn(o.y, __fmul_rn(g.y, __uint_as_float(r[4 * j + 1]) + b.y));
+              v[4 * j + 2] = __fadd_rn(o.z, __fmul_rn(g.z, __uint_as_float(r[4 * j + 2]) + b.z));
+              v[4 * j + 3] = __fadd_rn(o.w, __fmul_rn(g.w, __uint_as_float(r[4 * j + 3]) + b.w));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one_sync()) { tma_store_2d(&tmap_out, buf, col0, row_base); tma_store_commit(); }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s4[i & 3] += v[i]; q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]); }
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            tma_store_wait_read<0>();   // the fp32 box has left: the same buffer takes the bf16 box
+            __syncwarp();
+            uint8_t* rowb = buf + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(rowb + ((j ^ sw64) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one_sync()) { tma_store_2d(&epi.tmap_xb, buf, col0, row_base); tma_store_commit(); }
+            __syncwarp();
+            tma_store_wait_read<0>();
+            __syncwarp();
+            if (c + 1 < kChunks) issue_load(col0 + 32, row_base);
+            else if (next_tile < num_tiles) issue_load(ncol, nrow);
+          }
+          if (row_base + lane < M)
+            epi.stats[static_cast<size_t>(row_base + lane) * epi.n_slots + colw / kColsPerSplit] =
+                make_float2((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        tma_store_wait<0>();
+      } else if constexpr (Epi::kMode == EPI_TMA_RES_STATS) {
+        // ---- residual + LayerNorm statistics (see EpiTmaResidualStats). Per warp: bx[2] = fp32 boxes (old x in, new x out,
+        // in place), bb = bf16 box (two 32-column chunks side by side). q counts the chunks of this warp's stream:
+        // buffer q & 1, barrier parity (q >> 1) & 1.
+        static_assert(kColsPerSplit % 64 == 0, "EPI_TMA_RES_STATS: 64-column bf16 boxes");
+        constexpr int kChunks = kColsPerSplit / 32;
+        uint8_t* bx = reinterpret_cast<uint8_t*>(stg);
+        uint8_t* bb = bx + 8192;
+        uint64_t* ldb = epi_ld + (warp - 4) * 2;
+        const int sw = lane & 7;   // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+        auto tile_rc = [&](int tile, int& row, int& col) {
+          const int mb = tile / n_tiles, nb = tile - mb * n_tiles;
+          row = mb * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M + quad * 32;
+          col = nb * BLOCK_N + half * kColsPerSplit;
+        };
+        auto issue_load = [&](uint32_t qq, int col, int row) {
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&ldb[qq & 1u], 4096);
+            tma_load_2d(bx + (qq & 1u) * 4096, &tmap_out, &ldb[qq & 1u], col, row);
+          }
+          __syncwarp();
+        };
+        uint32_t q = 0;
+        if (first_tile < num_tiles) {
+          int r0, c0;
+          tile_rc(first_tile, r0, c0);
+          issue_load(0, c0, r0);
+        }
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+          int row_base, colw;
+          tile_rc(tile, row_base, colw);
+          const int next_tile = tile + tile_step;
+          int nrow = 0, ncol = 0;
+          if (next_tile < num_tiles) {   // the next tile's old x: into L2 now (a whole tile ahead of its first use)
+            tile_rc(next_tile, nrow, ncol);
+            if (epi.l2_prefetch && lane < kChunks) tma_prefetch_l2_2d(&tmap_out, ncol + 32 * lane, nrow);
+          }
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerSplit;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // four interleaved partial sums (fixed order)
+#pragma unroll 1
+          for (int c = 0; c < kChunks; ++c, ++q) {
+            uint32_t r[32];
+            tmem_ld32(taddr + 32 * c, r);
+            mbar_wait(&ldb[q & 1u], (q >> 1) & 1u);
+            tmem_ld_wait();
+            const int col0 = colw + 32 * c;
+            uint8_t* rowp = bx + (q & 1u) * 4096 + lane * 128;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = *reinterpret_cast<const float4*>(rowp + ((j ^ sw) << 4));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + j);
+              const float4 g = __ldg(reinterpret_cast<const float4*>(epi.gamma + col0) + j);
+              v[4 * j] = __fadd_rn(o.x, __fmul_rn(g.x, __uint_as_float(r[4 * j]) + b.x));
+              v[4 * j + 1] = __fadd_rn(o.y, __fmul_rn(g.y, __uint_as_float(r[4 * j + 1]) + b.y));
+              v[4 * j + 2] = __fadd_rn(o.z, __fmul_rn(g.z, __uint_as_float(r[4 * j + 2]) + b.z));
+              v[4 * j + 3] = __fadd_rn(o.w, __fmul_rn(g.w, __uint_as_float(r[4 * j + 3]) + b.w));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s4[i & 3] += v[i]; q4[i & 3] = fmaf(v[i], v[i], q4[i & 3]); }
+            // the other fp32 box (stored a chunk ago) and the bf16 box have been read by the TMA engine
+            tma_store_wait_read<0>();
+            __syncwarp();
+            if (c + 1 < kChunks) issue_load(q + 1, col0 + 32, row_base);
+            else if (next_tile < num_tiles) issue_load(q + 1, ncol, nrow);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            const int hbox = c & 1;   // even chunk -> left 64 B of the bf16 rows, odd chunk -> right 64 B
+            uint8_t* rowb = bb + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(rowb + (((hbox * 4 + j) ^ sw) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one_sync()) {
+              tma_store_2d(&tmap_out, bx + (q & 1u) * 4096, col0, row_base);
+              if (hbox == 1) tma_store_2d(&epi.tmap_xb, bb, col0 - 32, row_base);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
+          if (row_base + lane < M)
+            epi.stats[static_cast<size_t>(row_base + lane) * epi.n_slots + colw / kColsPerSplit] =
+                make_float2((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        tma_store_wait<0>();
+      } else
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M + quad * 32;
+        typename epi_row_ctx<Epi>::type row_ctx{};   // per-row constants (LayerNorm mean / rstd), fetched while the main loop still runs
+        if constexpr (epi_has_row_ctx<Epi>::value) row_ctx = epi.row_ctx(row_base + lane);
         VFM_TICK(t_w0);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
@@ -454,7 +759,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #ifdef VFM_EPI_TIMING
         dbg[4] += 1;
 #endif
-        const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * GEMM_BLOCK_M + quad * 32;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + half * kColsPerSplit;
 #pragma unroll 1
         for (int c = 0; c < kColsPerSplit; c += 32) {
@@ -470,7 +774,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-              if constexpr (epi_needs_row<Epi>::value) epi.apply_row(row_base + lane, col0, v);
+              if constexpr (epi_has_row_ctx<Epi>::value) epi.apply_ctx(row_ctx, row_base + lane, col0, v);
+              else if constexpr (epi_needs_row<Epi>::value) epi.apply_row(row_base + lane, col0, v);
               else epi.apply(col0, v);
               uint8_t* box = reinterpret_cast<uint8_t*>(stg);
               uint8_t* rowp = box + lane * 128;

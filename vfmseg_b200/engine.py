@@ -136,6 +136,14 @@ class PackedVit:
             blk.fc2_w = dev(sd[p + "mlp.fc2.weight"], torch.bfloat16).data_ptr()
             blk.fc2_b = dev(self._bias(sd, p + "mlp.fc2.bias", Cc), torch.float32).data_ptr()
             blk.ls2 = dev(sd[p + "ls2.gamma"], torch.float32).data_ptr() if p + "ls2.gamma" in sd else ones.data_ptr()
+            if Cc % 256 == 0:
+                # LayerNorm folded into the Linear that follows it (include/vfmseg_b200.h, VfmBlockParams): norm1 -> qkv, norm2 -> fc1
+                from .ops import fold_layernorm
+                wf, bf, cs = fold_layernorm(w, b, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+                blk.qkv_wf, blk.qkv_bf, blk.qkv_cs = dev(wf, torch.bfloat16).data_ptr(), dev(bf, torch.float32).data_ptr(), dev(cs, torch.float32).data_ptr()
+                wf, bf, cs = fold_layernorm(sd[p + "mlp.fc1.weight"], self._bias(sd, p + "mlp.fc1.bias", spec.mlp_hidden),
+                                            sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+                blk.fc1_wf, blk.fc1_bf, blk.fc1_cs = dev(wf, torch.bfloat16).data_ptr(), dev(bf, torch.float32).data_ptr(), dev(cs, torch.float32).data_ptr()
         self._keep = keep
 
     @staticmethod

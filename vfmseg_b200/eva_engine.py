@@ -60,6 +60,13 @@ def _bias(sd, key: str):
     return None
 
 
+def _ln_fold_bits() -> int:
+    """VFM_LN_FOLD (same meaning as in vfm_vit_forward): bit 0 = norm1 folded into qkv (statistics from the previous block's
+    last GEMM), bit 1 = norm2 folded into the first MLP GEMM (statistics from attn.proj). Default 3 (both)."""
+    import os
+    return int(os.environ.get("VFM_LN_FOLD", "3"))
+
+
 class PackedEva:
     def __init__(self, sd: Dict[str, torch.Tensor], spec: EvaSpec, lora_scale: float, device):
         self.spec, self.device = spec, device
@@ -103,7 +110,15 @@ class PackedEva:
             b12[:H], b12[Hp:Hp + H] = _bias(sd, p + "mlp.w1"), _bias(sd, p + "mlp.w2")
             w3 = torch.zeros(C, Hp)
             w3[:, :H] = _lora_merged(sd, p + "mlp.w3", lora_scale)
+            fold = {}
+            if C % 256 == 0:   # LayerNorm folded into the Linear behind it (ops.fold_layernorm; vfm_gemm_lnfold_bf16)
+                wf, bfold, cs = ops.fold_layernorm(torch.cat([wq, wk, wv], 0), torch.cat([qb, torch.zeros(C), vb]),
+                                                   sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+                fold["qkv_f"] = (dev(wf, bf), dev(bfold, f32), dev(cs, f32))
+                wf, bfold, cs = ops.fold_layernorm(w12, b12, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+                fold["w12_f"] = (dev(wf, bf), dev(bfold, f32), dev(cs, f32))
             self.blocks.append(dict(
+                **fold,
                 n1=(dev(sd[p + "norm1.weight"], f32), dev(sd[p + "norm1.bias"], f32)),
                 n2=(dev(sd[p + "norm2.weight"], f32), dev(sd[p + "norm2.bias"], f32)),
                 qkv_w=dev(torch.cat([wq, wk, wv], 0), bf), qkv_b=dev(torch.cat([qb, torch.zeros(C), vb]), f32),
@@ -128,16 +143,32 @@ class PackedEva:
         ops.cls_rows_(x, self.cls_token, self.pos, n, T)                              # cls_token + pos_embed[0]
         outs = sorted(s.out_indices)
         taps = torch.empty(n * P, len(outs) * C, dtype=torch.bfloat16, device=x.device)
+        # LayerNorm folding (csrc/gemm_sm100.cuh, EpiTmaResidualStats -> EpiTmaBf16LN): a residual GEMM followed by a plain norm
+        # + Linear also emits bf16(x) and the row statistics; norm1 of block 0 and the norm1 passes that write a tap stay kernels
+        bits = _ln_fold_bits() if "qkv_f" in self.blocks[0] else 0
+        fold1, fold2 = bool(bits & 1), bool(bits & 2)
+        pre = None                                                                    # (bf16(x), stats) from the previous block's w3 GEMM
         for i, b in enumerate(self.blocks):
             tap_i = outs.index(i - 1) if (i - 1) in outs else None                    # tap of the previous block's output
-            h = ops.layernorm_tap(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None,
-                                  (tap_i or 0) * C, T)
-            qkv = ops.gemm_bias_rope_bf16(h, b["qkv_w"], b["qkv_b"], self.rope_cos, self.rope_sin, 2 * C, T)   # :337-369
+            if pre is not None:
+                qkv = ops.gemm_lnfold_rope_bf16(*pre, *b["qkv_f"], s.ln_eps, self.rope_cos, self.rope_sin, 2 * C, T)
+            else:
+                h = ops.layernorm_tap(x, *b["n1"], s.ln_eps, taps if tap_i is not None else None,
+                                      (tap_i or 0) * C, T)
+                qkv = ops.gemm_bias_rope_bf16(h, b["qkv_w"], b["qkv_b"], self.rope_cos, self.rope_sin, 2 * C, T)   # :337-369
             att = ops.attention_fwd(qkv, n, T, s.num_heads)                           # xops.memory_efficient_attention :376
-            ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
-            h = ops.layernorm(x, *b["n2"], s.ln_eps)
-            u = ops.swiglu_layernorm(ops.gemm_bias_bf16(h, b["w12"], b["b12"]), *b["ffn_ln"], s.hidden, s.ln_eps)
-            ops.gemm_bias_ls_residual_(x, u, b["w3"], b["b3"], self.ones)
+            if fold2:
+                xb, st = ops.gemm_bias_ls_residual_stats_(x, att, b["proj_w"], b["proj_b"], self.ones)
+                h12 = ops.gemm_lnfold_bf16(xb, st, *b["w12_f"], s.ln_eps)
+            else:
+                ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
+                h12 = ops.gemm_bias_bf16(ops.layernorm(x, *b["n2"], s.ln_eps), b["w12"], b["b12"])
+            u = ops.swiglu_layernorm(h12, *b["ffn_ln"], s.hidden, s.ln_eps)
+            if fold1 and i + 1 < s.depth and i not in outs:
+                pre = ops.gemm_bias_ls_residual_stats_(x, u, b["w3"], b["b3"], self.ones)
+            else:
+                pre = None
+                ops.gemm_bias_ls_residual_(x, u, b["w3"], b["b3"], self.ones)
         if (s.depth - 1) in outs:
             ops.layernorm_tap(x, None, None, s.ln_eps, taps, outs.index(s.depth - 1) * C, T, want_out=False)
         return taps

@@ -73,6 +73,48 @@ def gemm_bias_ls_residual_(x, a, w, bias, gamma, tap=None, tap_col0=0, tokens_pe
     return x
 
 
+def gemm_bias_ls_residual_stats_(x, a, w, bias, gamma):
+    """x (fp32 [M,N]) += gamma * (a @ w.T + bias) in place (same bits as gemm_bias_ls_residual_); also returns
+    xb = bf16(x) and stats [M, N/128, 2] = (sum, sum of squares) of every row over each 128-column slot."""
+    M, K = a.shape
+    N = w.shape[0]
+    xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    stats = torch.empty(M, N // 128, 2, device=a.device, dtype=torch.float32)
+    _C.call("vfm_gemm_bias_ls_residual_stats", _bf16(a), K, _bf16(w), K, _f32(bias), _f32(gamma), _f32(x), N,
+            _bf16(xb), N, _f32(stats), M, N, K, _stream())
+    return xb, stats
+
+
+def fold_layernorm(w, b, ln_w, ln_b):
+    """Linear(LayerNorm(x)) with the norm folded into the Linear (see vfm_gemm_lnfold_bf16): returns
+    (wf bf16 [N,K] = ln_w * w, bias_f fp32 [N] = b + w @ ln_b, colsum fp32 [N] = row sums of the ROUNDED wf)."""
+    w32, g, beta = w.float(), ln_w.float(), ln_b.float()
+    wf = (w32 * g[None, :]).to(torch.bfloat16)
+    bias_f = (b.float() if b is not None else torch.zeros(w32.shape[0], device=w32.device)) + w32.double().matmul(beta.double()).float()
+    colsum = wf.double().sum(dim=1).float()
+    return wf.contiguous(), bias_f.contiguous(), colsum.contiguous()
+
+
+def gemm_lnfold_bf16(xb, stats, wf, bias_f, colsum, eps, gelu=False):
+    """bf16(act(Linear(LayerNorm(x)))) from xb = bf16(x), the row statistics and the folded weights."""
+    M, K = xb.shape
+    N = wf.shape[0]
+    out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_lnfold_bf16", _bf16(xb), K, _bf16(wf), K, _f32(bias_f), _f32(colsum), _f32(stats), float(eps),
+            int(bool(gelu)), _bf16(out), N, M, N, K, _stream())
+    return out
+
+
+def gemm_lnfold_rope_bf16(xb, stats, wf, bias_f, colsum, eps, cos_t, sin_t, rope_cols, tokens_per_seq):
+    """gemm_lnfold_bf16 + the RoPE epilogue of gemm_bias_rope_bf16 (EVA02 norm1 -> qkv -> rope)."""
+    M, K = xb.shape
+    N = wf.shape[0]
+    out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    _C.call("vfm_gemm_lnfold_rope_bf16", _bf16(xb), K, _bf16(wf), K, _f32(bias_f), _f32(colsum), _f32(stats), float(eps),
+            _bf16(out), N, M, N, K, _f32(cos_t), _f32(sin_t), rope_cols, tokens_per_seq, _stream())
+    return out
+
+
 def gemm_patch_embed(a, w, bias, pos, n_crops, patches):
     M, K = a.shape
     N = w.shape[0]

@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _C, ops
+from .eva_engine import _ln_fold_bits
 
 
 @dataclass
@@ -119,6 +120,10 @@ class PackedSam:
                 proj_w=dev(_lora_merged(sd, p + "attn.proj", lora_scale), bf), proj_b=dev(_bias(sd, p + "attn.proj"), f32),
                 lin1_w=dev(_lora_merged(sd, p + "mlp.lin1", lora_scale), bf), lin1_b=dev(_bias(sd, p + "mlp.lin1"), f32),
                 lin2_w=dev(_lora_merged(sd, p + "mlp.lin2", lora_scale), bf), lin2_b=dev(_bias(sd, p + "mlp.lin2"), f32))
+            if C % 256 == 0:   # norm2 -> mlp.lin1 (+ GELU) with the LayerNorm folded into the weights (ops.fold_layernorm)
+                wf, bfold, cs = ops.fold_layernorm(_lora_merged(sd, p + "mlp.lin1", lora_scale), _bias(sd, p + "mlp.lin1"),
+                                                   sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+                blk["lin1_f"] = (dev(wf, bf), dev(bfold, f32), dev(cs, f32))
             self.blocks.append(blk)
         self._keep = keep
         self._maps: Dict[tuple, tuple] = {}
@@ -187,9 +192,14 @@ class PackedSam:
                     att = ops.attention_global_tc(qkv, self._maps[key], n, P, H, d, gh, gw, scale, g0)
                 else:
                     att = ops.attention_relpos_terms(qkv, n, P, H, d, gh, gw, scale, g0)
-            ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
-            h = ops.layernorm(x, *b["n2"], s.ln_eps)
-            ops.gemm_bias_ls_residual_(x, ops.gemm_bias_gelu_bf16(h, b["lin1_w"], b["lin1_b"]), b["lin2_w"], b["lin2_b"], self.ones)
+            if "lin1_f" in b and (_ln_fold_bits() & 2):
+                # the proj GEMM also emits bf16(x) and the row statistics; lin1 applies norm2 in its epilogue (no LayerNorm pass)
+                xb, st = ops.gemm_bias_ls_residual_stats_(x, att, b["proj_w"], b["proj_b"], self.ones)
+                hid = ops.gemm_lnfold_bf16(xb, st, *b["lin1_f"], s.ln_eps, gelu=True)
+            else:
+                ops.gemm_bias_ls_residual_(x, att, b["proj_w"], b["proj_b"], self.ones)
+                hid = ops.gemm_bias_gelu_bf16(ops.layernorm(x, *b["n2"], s.ln_eps), b["lin1_w"], b["lin1_b"])
+            ops.gemm_bias_ls_residual_(x, hid, b["lin2_w"], b["lin2_b"], self.ones)
         if (s.depth - 1) in outs:
             ops.layernorm_tap_nocls(x, None, None, s.ln_eps, taps, outs.index(s.depth - 1) * C, want_out=False)
         return taps
