@@ -3,6 +3,7 @@ weight folding, C-ABI symbol table, metric reduction. No GPU compute is issued."
 import ctypes
 import os
 import re
+import sys
 from pathlib import Path
 
 import numpy as np
@@ -202,6 +203,64 @@ def test_convert_dinov2_matches_reference_converter():
     ck = {"state_dict": {"decode_head.conv_seg.bias": torch.zeros(19)}}
     convert.merge_backbone_checkpoint(ck, {"cls_token": w["cls_token"]})
     assert set(ck["state_dict"]) == {"decode_head.conv_seg.bias", "backbone.cls_token"}
+
+
+def _load_ref_script(path, name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_convert_sam_and_eva2_match_reference_converters(tmp_path):
+    """convert_sam_state_dict / convert_eva2_state_dict / generate_full_weights vs the reference's scripts (run from the
+    reference tree when present: their functions, or the script itself on a temporary checkpoint)."""
+    import subprocess
+    import torch
+    from vfmseg_b200 import convert
+    g = torch.Generator().manual_seed(1)
+    sam = {f"image_encoder.blocks.{i}.norm1.weight": torch.randn(8, generator=g) for i in range(12)}
+    sam.update({"image_encoder.patch_embed.proj.weight": torch.randn(8, 3, 16, 16, generator=g),
+                "image_encoder.pos_embed": torch.randn(1, 64, 64, 8, generator=g), "mask_decoder.x": torch.zeros(1)})
+    out = convert.convert_sam_state_dict(sam, kernel=16, crop_size=(512, 512))
+    assert "x" not in out and "mask_decoder.x" not in out and out["pos_embed"].shape == (1, 32, 32, 8)
+    assert out["patch_embed.proj.weight"].shape == (8, 3, 16, 16)
+    with pytest.raises(KeyError):
+        convert.convert_sam_state_dict({"image_encoder.pos_embed": torch.zeros(1, 4, 4, 8)})
+    eva = {"model": {"patch_embed.proj.weight": torch.randn(8, 3, 14, 14, generator=g), "pos_embed": torch.randn(1, 1 + 16 * 16, 8, generator=g),
+                     "positional_embedding": torch.randn(1 + 16 * 16, 8, generator=g), "rope.freqs_cos": torch.zeros(4), "blocks.0.attn.rope.freqs_sin": torch.zeros(4),
+                     "cls_token": torch.randn(1, 1, 8, generator=g)}}
+    eo = convert.convert_eva2_state_dict(eva)
+    assert not [k for k in eo if "rope" in k] and eo["pos_embed"].shape == (1, 1025, 8) and eo["positional_embedding"].shape == (1025, 8)
+    assert eo["patch_embed.proj.weight"].shape == (8, 3, 16, 16) and torch.equal(eo["pos_embed"][:, :1], eva["model"]["pos_embed"][:, :1])
+    bb = {"pos_embed": torch.randn(1, 1 + 37 * 37, 1024, generator=g), "patch_embed.proj.weight": torch.randn(4, 3, 14, 14, generator=g)}
+    full = convert.generate_full_weights(bb, {"state_dict": {"decode_head.conv_seg.bias": torch.zeros(19)}})
+    assert full["state_dict"]["backbone.pos_embed"].shape == (1, 1025, 1024) and full["state_dict"]["backbone.patch_embed.proj.weight"].shape == (4, 3, 16, 16)
+    assert torch.equal(full["state_dict"]["backbone.pos_embed"], convert.convert_dinov2_state_dict(bb)["pos_embed"])
+    ref_dir = "/root/reference/tools/convert_models"
+    if os.path.exists(ref_dir):
+        mod = _load_ref_script(f"{ref_dir}/convert_sam.py", "ref_convert_sam")
+        ref = mod.select_component({k: v.clone() for k, v in sam.items()}, "image_encoder.")
+        mod.interpolate_patch_embed_(ref, kernel_conv=16)
+        mod.interpolate_pos_embed_(ref, crop_size=(512, 512), kernel_conv=16)
+        assert set(ref) == set(out)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+        # the EVA02 converter is a script without a main(): run it on a temporary checkpoint
+        src, dst = tmp_path / "eva_in.pt", tmp_path / "eva_out.pt"
+        torch.save(eva, src)
+        subprocess.run([sys.executable, f"{ref_dir}/convert_eva2_512x512.py", str(src), str(dst)], check=True, capture_output=True)
+        ref = torch.load(dst, map_location="cpu")
+        assert set(ref) == set(eo)
+        for k in ref:
+            assert torch.equal(eo[k], ref[k]), k
+        gen = _load_ref_script("/root/reference/tools/generate_full_weights.py", "ref_generate_full_weights")
+        bpath = tmp_path / "bb.pt"
+        torch.save(bb, bpath)
+        rb = gen.load_backbone(str(bpath))
+        for k in rb:
+            assert torch.equal(full["state_dict"]["backbone." + k], rb[k]), k
 
 
 def test_id2color_and_png_export(tmp_path):
