@@ -163,6 +163,12 @@ int sm_count() {
   return n;
 }
 
+// VFM_PDL=0 switches programmatic dependent launch off (every kernel then starts after its predecessor has drained)
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VFM_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 struct OutDesc { const void* ptr = nullptr; int ld = 0; int convt_w = 0; int convt_rows = 0; int rows = 0; };   // destination of the TMA-store epilogues
 
 template <int BLOCK_N, int CTA_GROUP, class Epi>
@@ -210,13 +216,15 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA_GROUP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in sm100_ptx.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   {
     LaunchScope scope(name, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, M, N, K_pad, epi);
@@ -497,7 +505,18 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     const unsigned grid = static_cast<unsigned>(units < n_sm ? units : n_sm);
     {
       LaunchScope scope("attention_fwd", st);   // same family as the round-1 kernel in the per-launch profile (bench.py roofline.families)
-      attention_pp_kernel<<<grid, APP_THREADS, APP_SMEM_BYTES, st>>>(tq, tk, tv, p);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(APP_THREADS);
+      cfg.dynamicSmemBytes = APP_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled() ? 1 : 0;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, attention_pp_kernel, tq, tk, tv, p);
+      if (e != cudaSuccess) return fail(VFM_ERR_CUDA, "launch of attention_pp failed: %s", cudaGetErrorString(e));
     }
     VFM_LAUNCH_CHECK("attention_pp");
     return VFM_OK;

@@ -321,11 +321,13 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     for (int i = 0; i < 16; ++i) { mbar_init(&l_full[i], 1); mbar_init(&e_full[i], 1); }
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   if (warp == 9) tmem_alloc<APP_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // programmatic dependent launch: the qkv rows come from the previous kernel (see sm100_ptx.cuh)
 #ifdef VFM_APP_TRACE
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long ns;

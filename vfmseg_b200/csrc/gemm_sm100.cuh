@@ -478,11 +478,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     fence_barrier_init();
   }
+  pdl_launch_dependents();   // the next kernel on the stream may set itself up on SMs this grid has left
   if (warp == 2) tmem_alloc<Cfg::kTmemCols, CTA_GROUP>(tmem_slot);
   tc_fence_before();
   if constexpr (CTA_GROUP == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                // everything above touched no global data; the operands may come from the previous kernel
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its own W rows) =====================

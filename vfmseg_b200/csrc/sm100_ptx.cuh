@@ -99,6 +99,14 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor on the stream
+// is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) on the SMs the
+// predecessor has already left and then block in pdl_wait() until the predecessor grid has completed and its writes are
+// visible. pdl_launch_dependents() in the predecessor allows that early start (without it the successor starts at grid end).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
