@@ -94,6 +94,11 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #define VFM_APP_SOFTMAX_REGS 200
 #define VFM_APP_SERVICE_REGS 56
 #endif
+#ifndef VFM_APP_OUT32
+#define VFM_APP_OUT32 0   // 1: the output warps read O in two 32-column rounds and hand the accumulator back before their stores; measured with the
+#endif                    // register budget moved their way (softmax 192 / service 64: 586, 184 / 72: 592 TFLOP/s) against 595.5 as shipped — the unit
+#if 0                     // output is not what bounds the kernel
+#endif
 static_assert(256 * VFM_APP_SOFTMAX_REGS + 256 * VFM_APP_SERVICE_REGS <= 512 * 128, "setmaxnreg budget exceeds the CTA's register pool");
 
 #ifdef VFM_APP_TRACE
@@ -491,6 +496,41 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           const bool live = q_idx < p.q_len;
           uint4* dst = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(un.seq * p.q_seq_rows + p.q_row_off + q_idx) * p.out_ld + un.head * ATT_D);
           const uint32_t tmem_o = tmem_base + lane_base + APP_COL_O + x * ATT_D;
+#if VFM_APP_OUT32
+          // two 32-column rounds instead of four of 16 (needs the 64+ register budget of VFM_APP_SERVICE_REGS); the accumulator
+          // goes back to the PV issuer as soon as the second round is in registers, before its global stores
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + c * 32, o);
+            tmem_ld_wait();
+            if (c == ATT_D / 32 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&o_free[x]);
+            }
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]);
+                if (p.extra) {
+                  const uint4 xv = vx[4 * c + i];
+                  v[0] = fmaf(lw.y, bf16lo(xv.x), v[0]); v[1] = fmaf(lw.y, bf16hi(xv.x), v[1]);
+                  v[2] = fmaf(lw.y, bf16lo(xv.y), v[2]); v[3] = fmaf(lw.y, bf16hi(xv.y), v[3]);
+                  v[4] = fmaf(lw.y, bf16lo(xv.z), v[4]); v[5] = fmaf(lw.y, bf16hi(xv.z), v[5]);
+                  v[6] = fmaf(lw.y, bf16lo(xv.w), v[6]); v[7] = fmaf(lw.y, bf16hi(xv.w), v[7]);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= inv;
+                dst[4 * c + i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              }
+            }
+          }
+          if (quad == 0 && x == 0) APP_TRACE(2, k, 7);
+          continue;
+#endif
 #pragma unroll 1
           for (int c = 0; c < ATT_D / 16; ++c) {
             uint32_t o[16];
