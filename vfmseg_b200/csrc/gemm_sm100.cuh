@@ -599,6 +599,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld32(taddr + 32 * c, r);
             mbar_wait(ldb, q & 1u);
             tmem_ld_wait();
+            if (c == kChunks - 1) {   // the tile's last accumulator columns are in registers: the MMA issuer may have the TMEM stage back now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+              }
+            }
             const int col0 = colw + 32 * c;
             uint8_t* rowp = buf + lane * 128;
             float v[32];
@@ -642,11 +649,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (row_base + lane < M)
             epi.stats[static_cast<size_t>(row_base + lane) * epi.n_slots + colw / kColsPerSplit] =
                 make_float2((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]));
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
-          }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         tma_store_wait<0>();
@@ -697,6 +699,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld32(taddr + 32 * c, r);
             mbar_wait(&ldb[q & 1u], (q >> 1) & 1u);
             tmem_ld_wait();
+            if (c == kChunks - 1) {   // the tile's last accumulator columns are in registers: the MMA issuer may have the TMEM stage back now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+              }
+            }
             const int col0 = colw + 32 * c;
             uint8_t* rowp = bx + (q & 1u) * 4096 + lane * 128;
             float v[32];
@@ -739,11 +748,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (row_base + lane < M)
             epi.stats[static_cast<size_t>(row_base + lane) * epi.n_slots + colw / kColsPerSplit] =
                 make_float2((s4[0] + s4[1]) + (s4[2] + s4[3]), (q4[0] + q4[1]) + (q4[2] + q4[3]));
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
-          }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         tma_store_wait<0>();
@@ -768,6 +772,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           VFM_TICK(t0);
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
+          if (c + 32 >= kColsPerSplit) {   // the tile's last accumulator columns are in registers: the MMA issuer may have the TMEM stage back
+            tc_fence_before();             // now, a chunk of epilogue math and stores earlier than at the end of the tile
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+            }
+          }
           VFM_TICK(t1);
           VFM_ACC(1, t0, t1);
           const int col0 = n_blk * BLOCK_N + half * kColsPerSplit + c;
@@ -872,11 +883,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             VFM_TICK(t3);
             VFM_ACC(3, t2, t3);
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (CTA_GROUP == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
