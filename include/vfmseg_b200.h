@@ -117,7 +117,8 @@ int vfm_attention_fwd(const void* qkv, void* out, int n_seq, int seq_len, int he
  * each sequence (the ViT cls token, dino_v2.py:225) is split off and handled on the CUDA cores so that 1 + 64k
  * tokens need no partial tile; 3 = the serial kernel (one score buffer, four CTAs per SM; an alternative kept for comparison);
  * 4 = the ping-pong kernel (256-query units, 128-key tiles, one persistent CTA per SM, attention_pp_sm100.cuh), 5 = the same
- * with token 0 split off. Mode 0 picks 5 for ViT windows (seq_len = 1 + a multiple of 256, >= 513), whatever n_seq is, and 1
+ * with token 0 split off; 6 / 7 = modes 4 / 5 with the softmax warps working per 64-key half (attention_ph_sm100.cuh; an experiment,
+ * measured slower). Mode 0 picks 5 for ViT windows (seq_len = 1 + a multiple of 256, >= 513), whatever n_seq is, and 1
  * otherwise. The result is the same softmax attention in every mode. */
 int vfm_attention_fwd_ex(const void* qkv, void* out, int n_seq, int seq_len, int heads, int mode, void* stream);
 /* Cross attention: q [n_seq*q_len, >= heads*64] (row pitch q_ld), kv [n_seq*kv_len, 2*heads*64] packed (k | v),

@@ -186,14 +186,18 @@ def _attn_ref(qkv, n_seq, S, heads):
     (1, 128, 1, 4), (2, 256, 2, 4), (1, 1024, 2, 4), (3, 1025, 4, 4), (3, 1025, 4, 5), (2, 197, 2, 4), (2, 197, 2, 5),
     (1, 2049, 2, 4), (1, 2049, 2, 5), (2, 17, 2, 4), (2, 17, 2, 5), (2, 2, 1, 5), (1, 385, 3, 5), (2, 641, 2, 4),
     (20, 257, 12, 4), (20, 257, 12, 5), (40, 65, 8, 4), (40, 65, 8, 5), (600, 17, 1, 5), (300, 129, 2, 4), (300, 129, 2, 5),
-    (7, 1025, 16, 5), (36, 1025, 16, 0)])
+    (7, 1025, 16, 5), (36, 1025, 16, 0),
+    # modes 6 / 7: the per-half softmax pipeline over the same units (attention_ph_sm100.cuh; experiment, slower than 4 / 5): half
+    # tiles that are empty or ragged at the end of a sequence, one key tile per unit, several units per CTA, the peaked case below
+    (1, 128, 1, 6), (2, 197, 2, 6), (2, 197, 2, 7), (1, 2049, 2, 7), (2, 17, 2, 7), (2, 2, 1, 7), (3, 300, 4, 6), (2, 641, 2, 6),
+    (20, 257, 12, 6), (40, 65, 8, 6), (40, 65, 8, 7), (300, 129, 2, 7), (7, 1025, 16, 7)])
 def test_attention(ops, n_seq, S, heads, mode):
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=21, dtype=torch.bfloat16)
     out = ops.attention_fwd(qkv, n_seq, S, heads, mode)
     _close(out, _attn_ref(qkv, n_seq, S, heads), 2e-2, 2e-2, f"attention S={S} heads={heads} mode={mode}")
 
 
-@pytest.mark.parametrize("mode", [1, 2, 4, 5])
+@pytest.mark.parametrize("mode", [1, 2, 4, 5, 6, 7])
 def test_attention_peaked(ops, mode):
     # large-magnitude scores: exercises the online-softmax rescaling (and the rescaling of the split-off key's weight)
     n_seq, S, heads = 1, 1025, 2
@@ -209,7 +213,7 @@ def test_attention_modes_agree(ops):
     n_seq, S, heads = 2, 1025, 3
     qkv = _rand(n_seq * S, 3 * heads * 64, seed=31, dtype=torch.bfloat16)
     a = ops.attention_fwd(qkv, n_seq, S, heads, 1).float()
-    for mode in (2, 4, 5):
+    for mode in (2, 4, 5, 6, 7):
         b = ops.attention_fwd(qkv, n_seq, S, heads, mode).float()
         assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item(), mode
 

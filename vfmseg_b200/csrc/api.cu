@@ -15,6 +15,7 @@
 
 #include "attention_sm100.cuh"
 #include "attention_pp_sm100.cuh"
+#include "attention_ph_sm100.cuh"
 #include "sam_ops.cuh"
 #include "attention_win_sm100.cuh"
 #include "attention_glob_sm100.cuh"
@@ -453,11 +454,11 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
                      int kv_total, int heads, int mode, cudaStream_t st) {
   if (!q || !k || !v || !out || n_seq <= 0 || q_total <= 0 || kv_total <= 0 || heads <= 0)
     return fail(VFM_ERR_INVALID, "attention: bad args");
-  if (mode < 0 || mode > 5) return fail(VFM_ERR_INVALID, "attention: mode must be 0..5");
+  if (mode < 0 || mode > 7) return fail(VFM_ERR_INVALID, "attention: mode must be 0..7");
   if ((out_ld % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return fail(VFM_ERR_INVALID, "attention: out must be 16-byte aligned");
   if (mode == 0) {   // experiment knob (tools/): VFM_ATT_MODE=1|2|3 overrides the automatic choice
     static const int forced = [] { const char* e = std::getenv("VFM_ATT_MODE"); return e ? std::atoi(e) : 0; }();
-    if (forced >= 1 && forced <= 5 && !((forced == 2 || forced == 5) && (q_total != kv_total || kv_total < 2))) mode = forced;
+    if (forced >= 1 && forced <= 7 && !((forced == 2 || forced == 5 || forced == 7) && (q_total != kv_total || kv_total < 2))) mode = forced;
   }
   if (mode == 0) {
     // Automatic choice. ViT windows (1 cls token + a multiple of 256 patch tokens, self attention): the ping-pong kernel in
@@ -469,7 +470,9 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     if (q_total == kv_total && body >= 512 && body % APP_UNIT_Q == 0 && kv_total <= APP_MAX_EXTRA_KEYS) mode = 5;
   }
   if (mode >= 4) {
-    // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM; 5 = extra-token split
+    // ping-pong kernel (attention_pp_sm100.cuh): 256-query units, 128-key tiles, one persistent CTA per SM; 5 = extra-token split;
+    // 6 / 7 = the same units with the per-half softmax pipeline (attention_ph_sm100.cuh), 7 = extra-token split
+    const bool per_half = mode >= 6;
     const int ex = mode & 1;
     if (ex && (q_total != kv_total || kv_total < 2)) return fail(VFM_ERR_INVALID, "attention: extra-token mode needs q_total == kv_total >= 2");
     if (ex && kv_total > APP_MAX_EXTRA_KEYS) return fail(VFM_ERR_INVALID, "attention: sequence too long for extra-token mode (%d keys)", kv_total);
@@ -495,6 +498,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
     static bool attr_pp = false;
     if (!attr_pp) {
       VFM_CUDA(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
+      VFM_CUDA(cudaFuncSetAttribute(attention_ph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APP_SMEM_BYTES));
       attr_pp = true;
     }
     const long long units = static_cast<long long>(n_seq) * heads * p.q_tiles;
@@ -515,7 +519,7 @@ static int launch_attention(const void* q, int q_ld, int q_col0, const void* k, 
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr;
       cfg.numAttrs = pdl_enabled() ? 1 : 0;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, attention_pp_kernel, tq, tk, tv, p);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, per_half ? attention_ph_kernel : attention_pp_kernel, tq, tk, tv, p);
       if (e != cudaSuccess) return fail(VFM_ERR_CUDA, "launch of attention_pp failed: %s", cudaGetErrorString(e));
     }
     VFM_LAUNCH_CHECK("attention_pp");

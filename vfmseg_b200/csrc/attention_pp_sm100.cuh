@@ -94,10 +94,14 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #define VFM_APP_SOFTMAX_REGS 200
 #define VFM_APP_SERVICE_REGS 56
 #endif
+// VFM_APP_OUT32 = 1: the output warps read O in two 32-column rounds and hand the accumulator back before their stores. Measured
+// with the register budget moved their way (softmax 192 / service 64: 586, 184 / 72: 592 TFLOP/s) against 595.5 as shipped: the
+// unit output is not what bounds the kernel.
 #ifndef VFM_APP_OUT32
-#define VFM_APP_OUT32 0   // 1: the output warps read O in two 32-column rounds and hand the accumulator back before their stores; measured with the
-#endif                    // register budget moved their way (softmax 192 / service 64: 586, 184 / 72: 592 TFLOP/s) against 595.5 as shipped — the unit
-#if 0                     // output is not what bounds the kernel
+#define VFM_APP_OUT32 0
+#endif
+#ifndef VFM_APP_ELECT_WAIT
+#define VFM_APP_ELECT_WAIT 0   // 1: lane 0 alone polls the consumer pass's two mbarriers, the warp follows through __syncwarp
 #endif
 static_assert(256 * VFM_APP_SOFTMAX_REGS + 256 * VFM_APP_SERVICE_REGS <= 512 * 128, "setmaxnreg budget exceeds the CTA's register pool");
 
@@ -769,8 +773,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #endif
           if (quad == 0) APP_TRACE(x, t, 7);
           if (!ready) {
+#if VFM_APP_ELECT_WAIT
+            if (lane == 0) {   // one lane polls, the warp follows through __syncwarp (32 lanes polling one mbarrier are 32 shared-memory requests)
+              if (more) mbar_wait(&s_full[x], (t + 1) & 1);
+              if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);
+            }
+            __syncwarp();
+#else
             if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
             if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
+#endif
           }
           tc_fence_after();
           if (quad == 0) APP_TRACE(x, t, 1);
