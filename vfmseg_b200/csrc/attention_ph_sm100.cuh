@@ -11,8 +11,8 @@
 //     complete what the PREVIOUS half-iteration issued (tcgen05.wait::st / ::ld are free by now: P(prev) goes to the PV issuer,
 //     the S columns of that half go back to the S issuer, its row maximum is taken) -> pack + tcgen05.st of P(t, h) ->
 //     tcgen05.ld of S(t+1, h) into the registers just consumed.
-// tcgen05.wait::ld waits for ALL outstanding loads, so the wait sits BEFORE the new loads are issued: every load and store has
-// the partner's pass and this warp's next pass to complete. For that the S and PV MMAs are issued per half as well (S: N = 64,
+// tcgen05.wait::ld waits for ALL outstanding loads, so the wait sits BEFORE the new loads are issued: every load has the partner's
+// pass and this warp's next pass to complete (the P store is completed at once: see the note at its tcgen05.wait::st). For that the S and PV MMAs are issued per half as well (S: N = 64,
 // PV: four k-steps), each with its own full / free barrier pair; the S issuer may write half h of S(t+1) as soon as half h of S(t)
 // is in registers, half a tile before the other half.
 #pragma once
@@ -525,7 +525,14 @@ attention_ph_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               tmem_st16(tmem_p + o / 2 + c * 16, pk);
               if (more) tmem_ld32(tmem_s + o + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[o + 32 * c]));   // into the registers just consumed
             }
-            pend_st = true;
+            // The P store is completed here, not deferred like the loads: p_full needs the arrival of all four warps of the
+            // warpgroup, and a warp in the (rare) rescale path above waits for the PV behind it BEFORE the token barrier its three
+            // siblings must pass to reach their deferred arrival — a dead-lock (found by the peaked-score cases of the test matrix).
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[2 * x + h]);
+            pend_st = false;
             pend_ld = more;
             if (quad == 0) APP_TRACE(x, 2 * t + h, 5);
           }

@@ -74,8 +74,11 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #ifndef VFM_APP_BACKOFF
 #define VFM_APP_BACKOFF 0   // 1: the TMA / output warps sleep between polls of their barriers
 #endif
+#ifndef VFM_APP_BACKOFF_NS
+#define VFM_APP_BACKOFF_NS 32
+#endif
 #if VFM_APP_BACKOFF
-#define APP_WAIT_BG mbar_wait_backoff
+#define APP_WAIT_BG(bar, parity) mbar_wait_backoff(bar, parity, VFM_APP_BACKOFF_NS)
 #else
 #define APP_WAIT_BG mbar_wait
 #endif
