@@ -172,6 +172,15 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
                            int crop_w, int lh, int lw, int H, int W, int n_img, uint8_t* labels,
                            float* logits_out, void* stream);
 
+/* Second pass of the flip test-time augmentation fused into the merge: lowres / boxes are the windows of the MIRRORED image,
+ * a = slide(img) (fp32 [n_img, nc, H, W], e.g. logits_out of vfm_slide_merge_argmax on the first pass); writes
+ * labels = argmax((a + flip(slide(flip(img)))) / 2) and, when logits_out != NULL (may alias a), those logits — the same bits as
+ * vfm_slide_merge_argmax + vfm_tta_flip_mean_argmax without materialising the second pass's logits.
+ * rein/models/segmentors/hrda_encoder_decoder.py:196-229 (scales = [1]). Needs W % 4 == 0, x4 windows, nc <= 19. */
+int vfm_slide_merge_flip_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh,
+                                int lw, int H, int W, int n_img, const float* a, uint8_t* labels, float* logits_out,
+                                void* stream);
+
 /* Horizontal-flip test-time augmentation, combining step: a = slide(img), b = slide(flip(img, x)), both fp32
  * [n_img, nc, H, W]; logits = (a + mirror_x(b)) / 2 (optional output, may alias a), labels = argmax, first maximum
  * wins. Bit-identical to res = 0; res += a; res += flip(b); res / 2.

@@ -301,6 +301,29 @@ def test_slide_merge_argmax(ops, H, W, crop, stride, n_img):
     assert none is None and torch.equal(labels, labels2)
 
 
+@pytest.mark.parametrize("H,W,crop,stride,n_img", [(1024, 2048, 512, 341, 1), (160, 224, 64, 43, 2), (64, 100, 64, 43, 1)])
+@pytest.mark.parametrize("want_logits", [True, False])
+def test_slide_merge_flip_argmax(ops, H, W, crop, stride, n_img, want_logits):
+    """The flip-TTA second pass fused into the merge kernel == merge of the mirrored pass + tta_flip_mean_argmax, bit for bit
+    (labels and averaged logits), incl. a width that is not a multiple of the 64-pixel tile."""
+    from vfmseg_b200.engine import slide_boxes
+    nc, lh = 19, crop // 4
+    boxes = torch.tensor(slide_boxes(H, W, (crop, crop), (stride, stride)), dtype=torch.int32).cuda()
+    low_a = _rand(n_img * boxes.shape[0], nc, lh, lh, seed=61)
+    low_b = _rand(n_img * boxes.shape[0], nc, lh, lh, seed=62)      # windows of the mirrored image
+    _, a = ops.slide_merge_argmax(low_a, boxes, n_img, (crop, crop), (H, W), want_logits=True)
+    _, b = ops.slide_merge_argmax(low_b, boxes, n_img, (crop, crop), (H, W), want_logits=True)
+    ref_labels, ref_logits = ops.tta_flip_mean_argmax(a.clone(), b, want_logits=True)
+    assert ops.flip_merge_supported(low_b, (crop, crop), W)
+    labels, logits = ops.slide_merge_flip_argmax(low_b, boxes, n_img, (crop, crop), a, want_logits=want_logits)
+    assert torch.equal(labels, ref_labels)
+    if want_logits:
+        assert logits is a and torch.equal(logits, ref_logits)
+    else:
+        assert logits is None
+    assert torch.equal(ref_labels.long(), ref_logits.argmax(1))
+
+
 @pytest.mark.parametrize("n,P,C,cls", [(3, 64, 256, 1), (2, 1024, 1024, 1), (3, 96, 128, 0), (5, 16, 256, 1), (2, 24, 64, 0)])
 def test_patch_embed_gemm_paths(ops, n, P, C, cls):
     """Patch-embed GEMM + bias + pos-embed: the fp32 TMA-store epilogue (patches % 32 == 0: boxes shifted past the cls

@@ -94,6 +94,7 @@ SIGNATURES = {
     "vfm_groupnorm_relu": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "vfm_slide_merge_argmax": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "vfm_confusion_matrix": (_i, [_p, _p, _ll, _i, _i, _p, _p]),
+    "vfm_slide_merge_flip_argmax": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vfm_tta_flip_mean_argmax": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "vfm_vit_workspace_bytes": (_sz, [C.POINTER(VfmVitParams), _i, _i, _i]),
     "vfm_vit_forward": (_i, [C.POINTER(VfmVitParams), _p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i,

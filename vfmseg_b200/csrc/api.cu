@@ -892,7 +892,7 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
     if (tiles) {    // low-res footprints staged through shared memory, one CTA per 64 x 16 output tile (edge tiles partly idle)
       const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
       slide_merge_tile_kernel<19><<<grid, 256, 0, S(stream)>>>(lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
-                                                              lh, lw, H, W, labels, logits_out);
+                                                              lh, lw, H, W, labels, logits_out, nullptr);
     } else if (strips) {   // four pixels per thread sharing their bilinear taps
       long long b4 = (total / 4 + 255) / 256;
       if (b4 > cap) b4 = cap;
@@ -906,6 +906,24 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
           lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out);
   }
   VFM_LAUNCH_CHECK("slide_merge_argmax");
+  return VFM_OK;
+}
+
+int vfm_slide_merge_flip_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh,
+                                int lw, int H, int W, int n_img, const float* a, uint8_t* labels, float* logits_out, void* stream) {
+  if (!lowres || !boxes || !labels || !a || n_crops <= 0 || nc <= 0 || nc > 19 || n_img <= 0 || n_img > 65535)
+    return fail(VFM_ERR_INVALID, "slide_merge_flip_argmax: bad args (num_classes <= 19)");
+  if ((W % 4) || crop_h != 4 * lh || crop_w != 4 * lw ||
+      ((reinterpret_cast<uintptr_t>(labels) & 3) | (reinterpret_cast<uintptr_t>(a) & 15) | (reinterpret_cast<uintptr_t>(logits_out) & 15)))
+    return fail(VFM_ERR_INVALID, "slide_merge_flip_argmax: needs W %% 4 == 0, windows upsampled x4 and 16-byte aligned logits "
+                                 "(use vfm_slide_merge_argmax + vfm_tta_flip_mean_argmax otherwise)");
+  {
+    LaunchScope scope("slide_merge_flip_argmax", S(stream));
+    const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
+    slide_merge_tile_kernel<19><<<grid, 256, 0, S(stream)>>>(lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
+                                                            lh, lw, H, W, labels, logits_out, a);
+  }
+  VFM_LAUNCH_CHECK("slide_merge_flip_argmax");
   return VFM_OK;
 }
 

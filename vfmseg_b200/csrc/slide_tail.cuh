@@ -193,7 +193,7 @@ template <int NC_MAX>
 __global__ void __launch_bounds__(256)
 slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict__ boxes, int n_crops, int nc,
                         int crop_h, int crop_w, int lh, int lw, int H, int W,
-                        uint8_t* __restrict__ labels, float* __restrict__ logits_out) {
+                        uint8_t* __restrict__ labels, float* logits_out, const float* flip_a) {
   __shared__ float fp[NC_MAX * MERGE_FR * MERGE_FC];
   const int tx0 = blockIdx.x * MERGE_TW, ty0 = blockIdx.y * MERGE_TH, b = blockIdx.z;
   const int t = threadIdx.x;
@@ -251,6 +251,35 @@ slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict
     }
   }
   if (!in_img) return;
+  if (flip_a != nullptr) {
+    // Second pass of the horizontal-flip test-time augmentation (hrda_encoder_decoder.py:196-229, scales = [1]): the windows
+    // were computed on the mirrored image, so this strip is b = slide(flip(img)) at columns xs .. xs + 3 and belongs to output
+    // columns W - 1 - xs - j. flip_a = slide(img) at full resolution; result = (a + flip(b)) / 2 with the arithmetic of
+    // tta_flip_mean_argmax_kernel (one rounded add, exact halving), first maximum wins. logits_out may alias flip_a: every
+    // element is read and written by the same thread.
+    const size_t pixm = static_cast<size_t>(y) * W + (W - 4 - xs);
+    float best[4];
+    int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < NC_MAX; ++c) {
+      if (c < nc) {
+        const size_t off = (static_cast<size_t>(b) * nc + c) * H * W + pixm;
+        const float4 av = *reinterpret_cast<const float4*>(flip_a + off);
+        const float a4[4] = {av.x, av.y, av.z, av.w};
+        float m[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // output column W - 4 - xs + i  <-  strip pixel j = 3 - i
+          const float bv = acc[3 - i][c] / static_cast<float>(count[3 - i]);
+          m[i] = __fadd_rn(a4[i], bv) * 0.5f;
+          if (c == 0 || m[i] > best[i]) { best[i] = m[i]; arg[i] = c; }
+        }
+        if (logits_out) *reinterpret_cast<float4*>(logits_out + off) = make_float4(m[0], m[1], m[2], m[3]);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(labels + static_cast<size_t>(b) * H * W + pixm) =
+        static_cast<uint32_t>(arg[0]) | (static_cast<uint32_t>(arg[1]) << 8) | (static_cast<uint32_t>(arg[2]) << 16) | (static_cast<uint32_t>(arg[3]) << 24);
+    return;
+  }
   const size_t pix = static_cast<size_t>(y) * W + xs;
   uint32_t lab = 0;
 #pragma unroll

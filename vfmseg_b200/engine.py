@@ -320,6 +320,21 @@ class SlideEngine:
         labels, logits = ops.slide_merge_argmax(low, bx, B, tuple(crop_size), (H, W), want_logits=want_logits)
         return labels, logits, low
 
+    def slide_flip_tta(self, img: torch.Tensor, crop_size, stride, want_logits: bool = False):
+        """Slide inference with the horizontal-flip test-time augmentation (hrda_encoder_decoder.py:196-229, scales = [1]):
+        (slide(img) + flip(slide(flip(img)))) / 2 -> argmax. The first pass materialises its merged logits; the second pass's
+        merge kernel reads them mirrored and writes the labels (and, on request, the averaged logits over the first pass's
+        buffer), so the second logit volume and the combining pass over both never exist."""
+        B, _, H, W = img.shape
+        _, a, _ = self.slide(img, crop_size, stride, want_logits=True)
+        boxes = slide_boxes(H, W, crop_size, stride)
+        crops, bx = self._crop_table(B, boxes)
+        low = self.crops_lowres(torch.flip(img, [3]), crops, tuple(crop_size))
+        if ops.flip_merge_supported(low, tuple(crop_size), W):
+            return ops.slide_merge_flip_argmax(low, bx, B, tuple(crop_size), a, want_logits=want_logits)
+        _, b = ops.slide_merge_argmax(low, bx, B, tuple(crop_size), (H, W), want_logits=True)
+        return ops.tta_flip_mean_argmax(a, b, want_logits=want_logits)
+
     def whole(self, img: torch.Tensor, want_logits: bool = False):
         """Whole-image inference (mmseg whole_inference): one window covering the image."""
         B, _, H, W = img.shape

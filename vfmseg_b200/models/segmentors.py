@@ -148,16 +148,14 @@ class LoraBackboneEncoderDecoder(nn.Module):
     def _slide(self, x: torch.Tensor, want_logits: bool):
         """Slide inference, optionally with the horizontal-flip test-time augmentation of
         rein/models/segmentors/hrda_encoder_decoder.py:196-229 (`test_cfg.test_time_aug` and `test_cfg.flip`, :114-115;
-        scales = [1]): logits = (slide(img) + flip(slide(flip(img)))) / 2, combined and arg-maxed in one kernel."""
+        scales = [1]): logits = (slide(img) + flip(slide(flip(img)))) / 2; the second pass's merge kernel reads the first pass's logits
+        mirrored and arg-maxes the mean (SlideEngine.slide_flip_tta), so only one logit volume is ever materialised."""
         eng = self.engine()
         crop, stride = self.test_cfg.crop_size, self.test_cfg.stride
         if not (self.test_cfg.get("test_time_aug", False) and self.test_cfg.get("flip", False)):
             labels, logits, _ = eng.slide(x, crop, stride, want_logits=want_logits)
             return labels, logits
-        from .. import ops
-        _, a, _ = eng.slide(x, crop, stride, want_logits=True)
-        _, b, _ = eng.slide(torch.flip(x, [3]), crop, stride, want_logits=True)
-        return ops.tta_flip_mean_argmax(a, b, want_logits=want_logits)
+        return eng.slide_flip_tta(x, crop, stride, want_logits=want_logits)
 
     def slide_inference(self, inputs: torch.Tensor, batch_img_metas=None) -> torch.Tensor:
         return self._slide(self._as_input(inputs), True)[1]

@@ -208,6 +208,26 @@ def slide_merge_argmax(lowres, boxes, n_img, crop_hw, out_hw, want_logits=False)
     return labels, logits
 
 
+def slide_merge_flip_argmax(lowres, boxes, n_img, crop_hw, a, want_logits=False):
+    """Second pass of the flip test-time augmentation fused into the merge: `lowres` are the window logits of the MIRRORED images,
+    `a` = slide(img) (fp32 [B, nc, H, W]). Returns (uint8 labels, logits or None) of (a + flip(slide(flip(img)))) / 2; the logits are
+    written over `a`. Same bits as slide_merge_argmax + tta_flip_mean_argmax (hrda_encoder_decoder.py:196-229)."""
+    n_crops = boxes.shape[0]
+    _, nc, lh, lw = lowres.shape
+    B, _, H, W = a.shape
+    assert B == n_img and a.dtype == torch.float32 and a.is_contiguous()
+    labels = torch.empty(n_img, H, W, device=lowres.device, dtype=torch.uint8)
+    _C.call("vfm_slide_merge_flip_argmax", _f32(lowres), _ptr(boxes), n_crops, nc, crop_hw[0], crop_hw[1], lh, lw, H, W, n_img,
+            _f32(a), _ptr(labels), _f32(a) if want_logits else None, _stream())
+    return labels, (a if want_logits else None)
+
+
+def flip_merge_supported(lowres, crop_hw, W) -> bool:
+    """Shapes vfm_slide_merge_flip_argmax takes (the tiled merge kernel: x4 windows, W % 4 == 0, at most 19 classes)."""
+    _, nc, lh, lw = lowres.shape
+    return W % 4 == 0 and nc <= 19 and crop_hw[0] == 4 * lh and crop_hw[1] == 4 * lw
+
+
 def tta_flip_mean_argmax(a, b, want_logits=False):
     """a = slide(img), b = slide(flip(img, x)): fp32 [B, nc, H, W]. Returns (uint8 labels [B,H,W], logits or None) of
     (a + flip(b, x)) / 2; the logits are written over `a` (hrda_encoder_decoder.py:196-229, scales = [1])."""
