@@ -103,6 +103,16 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #ifndef VFM_APP_OUT32
 #define VFM_APP_OUT32 0
 #endif
+#ifndef VFM_APP_SUM_IN_PASS
+#define VFM_APP_SUM_IN_PASS 16  // n > 0: the FADD2 row sums of pair i - n are issued inside the MUFU pass at iteration i (n = 16: 256 clk behind)
+#endif
+#ifndef VFM_APP_PACK_IN_PASS
+#define VFM_APP_PACK_IN_PASS 1   // 1 (with VFM_APP_SUM_IN_PASS > 0): those pairs are also packed to bf16 inside the pass, compacted in place.
+                                 // Measured (36 windows, same box): neither 596, sums only 600-603, sums + packs at distance 12 / 16 / 20 / 24: 591 / 618-625 / 620 / 586 TFLOP/s
+#endif
+#if VFM_APP_PACK_IN_PASS && (!VFM_APP_SUM_IN_PASS || VFM_APP_ALUPACK || VFM_APP_POLY)
+#error "VFM_APP_PACK_IN_PASS needs VFM_APP_SUM_IN_PASS > 0 and the default pack / exponential"
+#endif
 #ifndef VFM_APP_ELECT_WAIT
 #define VFM_APP_ELECT_WAIT 0   // 1: lane 0 alone polls the consumer pass's two mbarriers, the warp follows through __syncwarp
 #endif
@@ -610,7 +620,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // Per key tile t (one query row per thread, its 128 scores in registers s[]):
     //   reference check   m_ref moves (and O_X is rescaled) only when the tile max exceeds it by > 2^24
     //   token             named barrier: the MUFU pipe is ours
-    //   MUFU pass         64 FFMA2 + 128 MUFU.EX2, in place in s[]; nothing else, so the pipe runs at 8 clk / instruction
+    //   MUFU pass         64 FFMA2 + 128 MUFU.EX2, in place in s[], 8 clk / MUFU instruction; the pass's spare issue slots take the FADD2 row
+    //                     sums and the F2FP packs of the pairs exponentiated 16 iterations (256 clk) earlier (VFM_APP_SUM_IN_PASS /
+    //                     VFM_APP_PACK_IN_PASS: consumers directly behind their exponential would stall the in-order warp)
     //   token release
     //   consumer pass     FADD2 row sums + F2FP packs + 4 x tcgen05.st of P(t) — and, chunk by chunk into the registers
     //                     this frees, the tcgen05.ld of S(t+1), which the S issuer finished long ago.
@@ -758,6 +770,21 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ffma2_bc(x0, x1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), kLog2e, neg_m);
             s[2 * i] = __float_as_uint(fast_exp2(x0));
             s[2 * i + 1] = __float_as_uint((kPoly != 0 && (i % (kPoly ? kPoly : 1)) == 0) ? poly_exp2(x1) : fast_exp2(x1));
+#if VFM_APP_SUM_IN_PASS
+            // row sums of the pairs exponentiated VFM_APP_SUM_IN_PASS iterations (x 16 clk) ago: ready for sure, and the pass has
+            // issue slots to spare (one MUFU per 8 clk); the last pairs are added in the consumer pass. Same pairing as there.
+            if (i >= VFM_APP_SUM_IN_PASS) {
+              constexpr int kD = VFM_APP_SUM_IN_PASS;
+              const int kk = i - kD;
+              if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+              else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+#if VFM_APP_PACK_IN_PASS
+              // ... and their bf16 pack, compacted in place: packed pair kk lives in s[kk] (the exponentials s[kk] held belong to
+              // pair kk / 2 <= kk, summed and packed before), so P chunk c is the 16 consecutive registers s[16 c ..] for tcgen05.st
+              s[kk] = pack_bf16x2(__uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+#endif
+            }
+#endif
           }
 #if VFM_APP_EARLY_PROBE
           // A completed mbarrier wait still costs ~100 clk of round trip, twice, at the head of the consumer pass — on the
@@ -789,14 +816,40 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
           tc_fence_after();
           if (quad == 0) APP_TRACE(x, t, 1);
+#if VFM_APP_PACK_IN_PASS
+          // the pairs the pass did not get to (the last VFM_APP_SUM_IN_PASS), then P leaves from s[0 .. 63] and S(t+1) arrives:
+          // chunk 0 into s[0 .. 31] once P chunks 0 and 1 have been stored from there, chunk 1 into s[32 .. 63] after P chunks 2 and 3
+#pragma unroll
+          for (int kk = 64 - VFM_APP_SUM_IN_PASS; kk < 64; ++kk) {
+            if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+            else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+            s[kk] = pack_bf16x2(__uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+          }
+          if (more) {   // the upper half of s[] is free already
+            tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+            tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+          }
+          tmem_st16(tmem_p + 0, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
+          tmem_st16(tmem_p + 16, *reinterpret_cast<uint32_t(*)[16]>(&s[16]));
+          if (more) tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_st16(tmem_p + 32, *reinterpret_cast<uint32_t(*)[16]>(&s[32]));
+          tmem_st16(tmem_p + 48, *reinterpret_cast<uint32_t(*)[16]>(&s[48]));
+          if (more) tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+#else
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int kk = 16 * c + i;
+#if VFM_APP_SUM_IN_PASS
+              if (kk >= 64 - VFM_APP_SUM_IN_PASS) {
+#endif
               if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
               else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+#if VFM_APP_SUM_IN_PASS
+              }
+#endif
 #if VFM_APP_ALUPACK == 2
               pk[i] = __byte_perm(s[2 * kk], s[2 * kk + 1], 0x7632u);
 #elif VFM_APP_ALUPACK
@@ -808,6 +861,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             tmem_st16(tmem_p + c * 16, pk);
             if (more) tmem_ld32(tmem_s + 32 * c, *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]));   // into the registers just consumed
           }
+#endif
           if (quad == 0) APP_TRACE(x, t, 5);
           tmem_st_wait();
           tmem_ld_wait();
