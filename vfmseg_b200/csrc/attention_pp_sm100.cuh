@@ -87,7 +87,8 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #endif                               // ahead, by the output warps (1: measured slower, 0.277 against 0.263 ms)
 #ifndef VFM_APP_EARLY_PROBE
 #define VFM_APP_EARLY_PROBE 0   // 1: probe the consumer pass's two barriers (non-blocking test_wait) from the end of the MUFU pass
-#endif                          // (measured slower: 0.266 against 0.260 ms per 36-window launch, same box — the probes lengthen the exclusive pass)
+#endif                          // (measured slower: 0.266 against 0.260 ms per 36-window launch, same box — the probes lengthen the exclusive pass; probes from the
+                                // MIDDLE of the pass, with or without a fake dependence pinning them there: 552-556 against 600 TFLOP/s)
 #ifndef VFM_APP_HANDOFF
 #define VFM_APP_HANDOFF 1   // the two softmax warpgroups take turns on the MUFU pipe (named-barrier token):
 #endif                      // 1 = one token per warpgroup pair (256 threads), 2 = one per SM sub-partition (warp pair, 64 threads)
