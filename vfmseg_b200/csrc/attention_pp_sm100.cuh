@@ -820,6 +820,26 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #if VFM_APP_PACK_IN_PASS
           // the pairs the pass did not get to (the last VFM_APP_SUM_IN_PASS), then P leaves from s[0 .. 63] and S(t+1) arrives:
           // chunk 0 into s[0 .. 31] once P chunks 0 and 1 have been stored from there, chunk 1 into s[32 .. 63] after P chunks 2 and 3
+#if VFM_APP_PACK_IN_PASS == 2
+          // variant: the first 32 packed pairs leave (and score columns 64 .. 95 arrive, into registers the pass has already
+          // consumed when VFM_APP_SUM_IN_PASS <= 16) before the leftover pairs are summed and packed; P leaves as two x32 stores
+          tmem_st32(tmem_p + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          if (more) {
+            tmem_ld32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+            tmem_ld32(tmem_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          }
+#pragma unroll
+          for (int kk = 64 - VFM_APP_SUM_IN_PASS; kk < 64; ++kk) {
+            if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+            else fadd2_acc(l0, l1, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+            s[kk] = pack_bf16x2(__uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
+          }
+          tmem_st32(tmem_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          if (more) {
+            tmem_ld32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+            tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          }
+#else
 #pragma unroll
           for (int kk = 64 - VFM_APP_SUM_IN_PASS; kk < 64; ++kk) {
             if (kk & 1) fadd2_acc(l2, l3, __uint_as_float(s[2 * kk]), __uint_as_float(s[2 * kk + 1]));
@@ -836,6 +856,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tmem_st16(tmem_p + 32, *reinterpret_cast<uint32_t(*)[16]>(&s[32]));
           tmem_st16(tmem_p + 48, *reinterpret_cast<uint32_t(*)[16]>(&s[48]));
           if (more) tmem_ld32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+#endif
 #else
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
