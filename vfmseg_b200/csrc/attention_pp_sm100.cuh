@@ -114,6 +114,13 @@ constexpr float kTruncLog2 = 0.0037521f;   // log2(1 + kTruncEps)
 #if VFM_APP_PACK_IN_PASS && (!VFM_APP_SUM_IN_PASS || VFM_APP_ALUPACK || VFM_APP_POLY)
 #error "VFM_APP_PACK_IN_PASS needs VFM_APP_SUM_IN_PASS > 0 and the default pack / exponential"
 #endif
+#ifndef VFM_APP_ONE_ISSUER
+#define VFM_APP_ONE_ISSUER 0   // 1: one warp issues S_X(t+2) then PV_X(t) behind one commit; the softmax warp waits for / arrives on one barrier per tile
+                               // (correct at the first run; measured slower, 588 against 610 TFLOP/s on that box: the scores wait for the PV behind them)
+#endif
+#if VFM_APP_ONE_ISSUER && VFM_APP_EARLY_PROBE
+#error "VFM_APP_EARLY_PROBE probes the two-barrier protocol"
+#endif
 #ifndef VFM_APP_ELECT_WAIT
 #define VFM_APP_ELECT_WAIT 0   // 1: lane 0 alone polls the consumer pass's two mbarriers, the warp follows through __syncwarp
 #endif
@@ -407,6 +414,77 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           __syncwarp();
         }
       }
+#if VFM_APP_ONE_ISSUER
+    } else if (warp == 9) {
+      // ===================== one MMA issuer: after consumer pass tau of warpgroup X, S_X(tau + 2) then PV_X(tau), ONE commit =====================
+      // The softmax warp then waits for a single barrier per tile ("ready": s_full[x]) instead of s_full + p_free, and arrives on a
+      // single one ("done": s_free[x]) instead of p_full + s_free. ready[x] completes once at the start (S_X(0)) and once per step n:
+      // step n follows done[x] #n (n = 0: S_X(0) is in registers; n = tau + 1: consumer pass tau is over) and issues S_X(n + 1), PV_X(n - 1).
+      constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(APP_TILE_Q, ATT_D, 0, 1);   // B = V is MN-major
+      const uint64_t dq0 = make_sw128_desc(smem_u32(smem_q));
+      const uint64_t dk0 = make_sw128_desc(smem_u32(smem_k));
+      const uint64_t dv0 = make_sw128_desc(smem_u32(smem_v));
+      const int tail_ksteps = (tail_valid + 15) >> 4;
+      auto issue_s = [&](int ts, int x) {   // S_X(ts); the warp has waited for what it needs
+        const int k = ts / kv_tiles, j = ts - k * kv_tiles;
+        const int qs = k % APP_Q_STAGES, ks = ts % APP_K_STAGES;
+        if (x == 0) {
+          if (j == 0) mbar_wait(&q_full[qs], (k / APP_Q_STAGES) & 1);
+          mbar_wait(&k_full[ks], (ts / APP_K_STAGES) & 1);
+          tc_fence_after();
+        }
+        if (elect_one_sync()) {
+          const uint64_t dq = dq0 + static_cast<uint64_t>((2 * qs + x) * (APP_TILE_BYTES >> 4));
+          const uint64_t dk = dk0 + static_cast<uint64_t>(ks * (APP_TILE_BYTES >> 4));
+          const uint32_t tmem_s = tmem_base + APP_COL_S + x * APP_BLOCK_KV;
+#pragma unroll
+          for (int kk = 0; kk < ATT_D / 16; ++kk) umma_ss(tmem_s, dq + 2 * kk, dk + 2 * kk, idesc_s, kk != 0);
+          if (x == 1) {
+            tc_commit(&k_empty[ks]);
+            if (j == kv_tiles - 1) tc_commit(&q_empty[qs]);
+          }
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int tp, int x) {
+        const int k = tp / kv_tiles, j = tp - k * kv_tiles;
+        const int vs = tp % APP_V_STAGES;
+        const bool last = j == kv_tiles - 1;
+        const int ksteps = last ? tail_ksteps : APP_BLOCK_KV / 16;
+        if (x == 0) mbar_wait(&v_full[vs], (tp / APP_V_STAGES) & 1);
+        if (j == 0 && k > 0) mbar_wait(&o_free[x], (k - 1) & 1);   // the previous unit's O_X has been copied out
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint64_t dv = dv0 + static_cast<uint64_t>(vs * (APP_TILE_BYTES >> 4));
+          const uint32_t tmem_o = tmem_base + APP_COL_O + x * ATT_D;
+          const uint32_t tmem_p = tmem_base + APP_COL_P + x * (APP_BLOCK_KV / 2);
+          for (int kk = 0; kk < ksteps; ++kk) umma_ts(tmem_o, tmem_p + 8 * kk, dv + 128 * kk, idesc_pv, (j | kk) != 0);
+          if (last) tc_commit(&o_ready[x]);
+          if (x == 1) tc_commit(&v_empty[vs]);
+        }
+        __syncwarp();
+      };
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        issue_s(0, x);
+        if (elect_one_sync()) tc_commit(&s_full[x]);   // ready #0
+        __syncwarp();
+      }
+      for (int n = 0; n <= total_tiles; ++n) {
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&s_free[x], n & 1);   // done[x] #n
+          tc_fence_after();
+          if (n + 1 < total_tiles) issue_s(n + 1, x);
+          if (n >= 1) issue_pv(n - 1, x);
+          if (elect_one_sync()) tc_commit(&s_full[x]);   // ready #(n + 1): covers both
+          __syncwarp();
+        }
+      }
+    } else if (warp == 10) {
+      // idle in this variant
+#else
     } else if (warp == 9) {
       // ===================== S issuer: S_X(t) = Q_X K(t)^T, X = A then B =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(APP_TILE_Q, APP_BLOCK_KV, 0, 0);
@@ -479,6 +557,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           }
         }
       }
+#endif
     } else if (warp == 11) {
       // ===================== extra-token query rows (CUDA cores, background) =====================
       if (p.extra) {
@@ -732,7 +811,11 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const float alpha = jump ? fast_exp2(m_ref - m_tile) : 1.f;   // exp2(-inf) = 0 on the very first tile
             if (jump) { m_ref = m_tile; w_extra *= alpha; l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha; }
             if (j > 0) {
+#if VFM_APP_ONE_ISSUER
+              mbar_wait(&s_full[x], (t + 1) & 1);   // ready #(t + 1): PV_X(t-1) (and S_X(t+1)) have executed
+#else
               mbar_wait(&p_free[x], (t - 1) & 1);   // every PV_X up to tile t-1 has executed
+#endif
               tc_fence_after();
 #pragma unroll 1
               for (int c = 0; c < ATT_D / 16; ++c) {
@@ -810,6 +893,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);
             }
             __syncwarp();
+#elif VFM_APP_ONE_ISSUER
+            if (more || t > 0) mbar_wait(&s_full[x], (t + 1) & 1);   // ready #(t + 1): S_X(t+1) is in TMEM and PV_X(t-1) has read P_X
 #else
             if (more) mbar_wait(&s_full[x], (t + 1) & 1);   // S_X(t+1): issued as soon as S_X(t) had been copied out, a tile ago
             if (t > 0) mbar_wait(&p_free[x], (t - 1) & 1);   // PV_X(t-1) has read P_X: the buffer may be rewritten
@@ -890,8 +975,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
+#if VFM_APP_ONE_ISSUER
+            mbar_arrive(&s_free[x]);             // done #(t + 1): P_X(t) is stored, S_X(t+1) is in registers
+#else
             mbar_arrive(&p_full[x]);
             if (more) mbar_arrive(&s_free[x]);   // S_X(t+2) may overwrite the score columns now
+#endif
           }
           if (more) {   // the row max of tile t+1 is what stands between this warp and its next token request
             const int jn = j + 1 == kv_tiles ? 0 : j + 1;
