@@ -324,6 +324,33 @@ def test_slide_merge_flip_argmax(ops, H, W, crop, stride, n_img, want_logits):
     assert torch.equal(ref_labels.long(), ref_logits.argmax(1))
 
 
+@pytest.mark.parametrize("H,W,crop,stride,n_img", [(1024, 2048, 512, 341, 2), (1024, 1820, 512, 341, 1), (160, 224, 64, 43, 2),
+                                                   (160, 224, 64, 16, 1), (64, 100, 64, 43, 1), (96, 132, 64, 21, 1)])
+def test_slide_merge_class_major_equals_window_major(ops, monkeypatch, H, W, crop, stride, n_img):
+    """The class-major merge kernel (slide_merge_class_kernel: all footprints staged behind one barrier, one class at a time,
+    integer x4 geometry) against the round-1 window-major tile kernel (VFM_MERGE_MODE=1): labels and logits bit for bit, plain and
+    fused flip-TTA. The small crops put more than
+    four windows over a tile (per-pixel gather inside the class loop), 1820 / 100 / 132 leave edge tiles partly outside."""
+    from vfmseg_b200.engine import slide_boxes
+    nc, lh = 19, crop // 4
+    boxes = torch.tensor(slide_boxes(H, W, (crop, crop), (stride, stride)), dtype=torch.int32).cuda()
+    low = _rand(n_img * boxes.shape[0], nc, lh, lh, seed=71)
+    low_b = _rand(n_img * boxes.shape[0], nc, lh, lh, seed=72)
+    monkeypatch.setenv("VFM_MERGE_MODE", "1")
+    lab_old, log_old = ops.slide_merge_argmax(low, boxes, n_img, (crop, crop), (H, W), want_logits=True)
+    flab_old, flog_old = ops.slide_merge_flip_argmax(low_b, boxes, n_img, (crop, crop), log_old.clone(), want_logits=True)
+    for mode in ("0", "2", "3"):   # 4 (default) / 2 / 3 resident CTAs per SM: three register allocations of the same kernel
+        monkeypatch.setenv("VFM_MERGE_MODE", mode)
+        lab_new, log_new = ops.slide_merge_argmax(low, boxes, n_img, (crop, crop), (H, W), want_logits=True)
+        lab_new2, _ = ops.slide_merge_argmax(low, boxes, n_img, (crop, crop), (H, W))
+        flab_new, flog_new = ops.slide_merge_flip_argmax(low_b, boxes, n_img, (crop, crop), log_new.clone(), want_logits=True)
+        flab_new2, _ = ops.slide_merge_flip_argmax(low_b, boxes, n_img, (crop, crop), log_new.clone(), want_logits=False)
+        assert torch.equal(log_new, log_old) and torch.equal(lab_new, lab_old) and torch.equal(lab_new2, lab_old), mode
+        assert torch.equal(flog_new, flog_old) and torch.equal(flab_new, flab_old) and torch.equal(flab_new2, flab_old), mode
+    monkeypatch.delenv("VFM_MERGE_MODE")
+    assert torch.equal(lab_new.long(), log_new.argmax(1))
+
+
 @pytest.mark.parametrize("n,P,C,cls", [(3, 64, 256, 1), (2, 1024, 1024, 1), (3, 96, 128, 0), (5, 16, 256, 1), (2, 24, 64, 0)])
 def test_patch_embed_gemm_paths(ops, n, P, C, cls):
     """Patch-embed GEMM + bias + pos-embed: the fp32 TMA-store epilogue (patches % 32 == 0: boxes shifted past the cls

@@ -1,16 +1,33 @@
-import sys; sys.path.insert(0, "/root/repo")
+"""A/B of the two tiled merge kernels on BASELINE config 2's tail (2 images of 1024x2048, 18 windows each, 19 classes):
+VFM_MERGE_MODE=1 = round-1 window-major tile kernel, default = class-major kernel. CUDA events, L2 flushed between launches.
+Prints one JSON line per case. Optional argument: comma-separated list of modes to run."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vfmseg_b200 import ops
 from vfmseg_b200.engine import slide_boxes
+
 bx = torch.tensor(slide_boxes(1024, 2048, (512, 512), (341, 341)), dtype=torch.int32).cuda()
 low = torch.randn(36, 19, 128, 128, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for want in (False, True):
-    f = lambda: ops.slide_merge_argmax(low, bx, 2, (512, 512), (1024, 2048), want_logits=want)
-    for _ in range(3): f()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.zero_(); s.record(); f(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
-    print("want_logits", want, "median us", sorted(ts)[5] * 1e3)
+algo_bytes = low.numel() * 4 + 2 * 1024 * 2048   # low-res logits read once + uint8 labels written
+for mode in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("1", "2", "3", "0")):
+    os.environ["VFM_MERGE_MODE"] = mode
+    for want in (False, True):
+        f = lambda: ops.slide_merge_argmax(low, bx, 2, (512, 512), (1024, 2048), want_logits=want)
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_(); s.record(); f(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+        med = sorted(ts)[len(ts) // 2]
+        b = algo_bytes + (2 * 19 * 1024 * 2048 * 4 if want else 0)
+        print(json.dumps({"kernel": "slide_merge_tile (window-major)" if mode == "1" else "slide_merge_class (class-major), CTAs per SM >= " + {"2": "2", "3": "3", "0": "4"}[mode],
+                          "want_logits": want, "median_us": round(med * 1e3, 1), "min_us": round(min(ts) * 1e3, 1),
+                          "algorithmic_GBps": round(b / med / 1e6, 1)}))
+os.environ.pop("VFM_MERGE_MODE", None)

@@ -875,6 +875,25 @@ int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const floa
   return VFM_OK;
 }
 
+// VFM_MERGE_MODE=1: the round-1 window-major tile kernel (76 accumulators per thread) instead of the class-major one; 2 / 3: the
+// class-major kernel compiled for 2 / 3 resident CTAs per SM instead of 4 (tools/bench_merge.py: 215 / 190 / 185 us per 2 images). Read on every call (one getenv
+// per merge launch) so that a test can compare the kernels bit for bit inside one process.
+static int merge_mode() {
+  const char* e = getenv("VFM_MERGE_MODE");
+  return e ? atoi(e) : 0;
+}
+static void launch_merge_tiles(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh, int lw,
+                               int H, int W, int n_img, uint8_t* labels, float* logits_out, const float* flip_a, cudaStream_t st) {
+  const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
+  const int2* bx = reinterpret_cast<const int2*>(boxes);
+  switch (merge_mode()) {
+    case 1: slide_merge_tile_kernel<19><<<grid, 256, 0, st>>>(lowres, bx, n_crops, nc, crop_h, crop_w, lh, lw, H, W, labels, logits_out, flip_a); break;
+    case 2: slide_merge_class_kernel<19, 2><<<grid, 256, 0, st>>>(lowres, bx, n_crops, nc, crop_h, crop_w, lh, lw, H, W, labels, logits_out, flip_a); break;
+    case 3: slide_merge_class_kernel<19, 3><<<grid, 256, 0, st>>>(lowres, bx, n_crops, nc, crop_h, crop_w, lh, lw, H, W, labels, logits_out, flip_a); break;
+    default: slide_merge_class_kernel<19, 4><<<grid, 256, 0, st>>>(lowres, bx, n_crops, nc, crop_h, crop_w, lh, lw, H, W, labels, logits_out, flip_a);
+  }
+}
+
 int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h, int crop_w, int lh,
                            int lw, int H, int W, int n_img, uint8_t* labels, float* logits_out, void* stream) {
   if (!lowres || !boxes || !labels || n_crops <= 0 || nc <= 0 || nc > 32 || n_img <= 0)
@@ -890,9 +909,7 @@ int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, i
                         (!logits_out || (reinterpret_cast<uintptr_t>(logits_out) & 15) == 0);
     const bool tiles = strips && crop_h == 4 * lh && crop_w == 4 * lw && n_img <= 65535;
     if (tiles) {    // low-res footprints staged through shared memory, one CTA per 64 x 16 output tile (edge tiles partly idle)
-      const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
-      slide_merge_tile_kernel<19><<<grid, 256, 0, S(stream)>>>(lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
-                                                              lh, lw, H, W, labels, logits_out, nullptr);
+      launch_merge_tiles(lowres, boxes, n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out, nullptr, S(stream));
     } else if (strips) {   // four pixels per thread sharing their bilinear taps
       long long b4 = (total / 4 + 255) / 256;
       if (b4 > cap) b4 = cap;
@@ -919,9 +936,7 @@ int vfm_slide_merge_flip_argmax(const float* lowres, const int* boxes, int n_cro
                                  "(use vfm_slide_merge_argmax + vfm_tta_flip_mean_argmax otherwise)");
   {
     LaunchScope scope("slide_merge_flip_argmax", S(stream));
-    const dim3 grid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
-    slide_merge_tile_kernel<19><<<grid, 256, 0, S(stream)>>>(lowres, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h, crop_w,
-                                                            lh, lw, H, W, labels, logits_out, a);
+    launch_merge_tiles(lowres, boxes, n_crops, nc, crop_h, crop_w, lh, lw, H, W, n_img, labels, logits_out, a, S(stream));
   }
   VFM_LAUNCH_CHECK("slide_merge_flip_argmax");
   return VFM_OK;
