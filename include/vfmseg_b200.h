@@ -351,6 +351,84 @@ int vfm_rope_qk(void* qkv, long long M, int C, int heads, int tokens_per_seq, co
 int vfm_swiglu_layernorm(const void* in, void* out, const float* gamma, const float* beta, long long M, int H, int Hp, float eps,
                          void* stream);
 
+
+/* EVA2.forward_features over a batch of crop windows as ONE call (rein/models/backbones/eva_02.py:816-849, blocks :486-493,
+ * attention :331-381, SwiGLU :234-241) with peft LoRA merged: the launch sequence vfmseg_b200/eva_engine.py used to issue from
+ * Python (patch gather -> patch-embed GEMM + pos_embed -> cls rows -> per block: [LayerNorm | folded] qkv GEMM + RoPE ->
+ * attention -> proj + residual [+ statistics] -> [LayerNorm | folded] w1|w2 GEMM -> SwiGLU + LayerNorm -> w3 + residual
+ * [+ statistics]), same kernels in the same order, so the taps are bit-identical to the per-operator calls. */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w; const float* qkv_b;     /* [3C, C] bf16 = q (pre-scaled) | k | v; bias = q_bias * scale | 0 | v_bias */
+  const void* proj_w; const float* proj_b;   /* [C, C] */
+  const float* ln2_w; const float* ln2_b;
+  const void* w12; const float* b12;         /* [2 * hidden_pad, C] = w1 | w2, rows beyond `hidden` zero */
+  const float* ffn_ln_w; const float* ffn_ln_b;
+  const void* w3; const float* b3;           /* [C, hidden_pad], columns beyond `hidden` zero */
+  /* LayerNorm folded into the Linear behind it (see VfmBlockParams); all NULL = not folded */
+  const void* qkv_wf; const float* qkv_bf; const float* qkv_cs;   /* norm1 -> q|k|v */
+  const void* w12_wf; const float* w12_bf; const float* w12_cs;   /* norm2 -> w1|w2 */
+} VfmEvaBlockParams;
+
+typedef struct {
+  int embed_dim, depth, heads, hidden, hidden_pad, n_taps;
+  int grid;                     /* windows are grid x grid patches (pos_embed / RoPE tables are fixed to it, eva_02.py:690-697) */
+  int tap_blocks[8];            /* out_indices, ascending */
+  float ln_eps;
+  const void* patch_w;          /* [embed_dim, 768] bf16 */
+  const float* patch_b;
+  const float* cls_token;       /* [embed_dim] */
+  const float* pos_embed;       /* [1 + grid*grid, embed_dim] */
+  const float* rope_cos;        /* [grid*grid, 64] */
+  const float* rope_sin;
+  const float* ones;            /* [embed_dim] of 1.0f (no LayerScale in EVA02) */
+  const VfmEvaBlockParams* blocks; /* host array [depth] */
+} VfmEvaParams;
+
+size_t vfm_eva_workspace_bytes(const VfmEvaParams* p /*host*/, int n_crops);
+/* taps[(crop*grid*grid + p), t*embed_dim + c] (bf16): the un-normalised residual stream after the blocks in tap_blocks. */
+int vfm_eva_forward(const VfmEvaParams* p /*host*/, const void* img, int is_u8, const VfmPixelNorm* nrm /*host*/, int img_h,
+                    int img_w, const int* crops, int n_crops, void* taps, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+
+/* SAMViT.forward over a batch of crop windows as ONE call (rein/models/backbones/sam_vit.py:123-147, blocks :201-217, attention
+ * :272-287 with add_decomposed_rel_pos :391-428, window_partition / window_unpartition :292-346): the launch sequence
+ * vfmseg_b200/sam_engine.py used to issue from Python, same kernels in the same order (bit-identical taps). */
+typedef struct {
+  int window;                                 /* 0: global attention over the grid; else the window size of this block */
+  int qkv_n;                                  /* rows of qkv_w: 3C (+ heads * 2 * (2 size - 1) table-term rows, padded to 32) */
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w; const float* qkv_b;      /* [qkv_n, C] bf16: q | k | v | G_h | G_w (see vfm_attention_relpos_ex) */
+  const void* proj_w; const float* proj_b;
+  const float* ln2_w; const float* ln2_b;
+  const void* lin1_w; const float* lin1_b;    /* [hidden, C] */
+  const void* lin2_w; const float* lin2_b;    /* [C, hidden] */
+  const void* lin1_wf; const float* lin1_bf; const float* lin1_cs;   /* norm2 folded into lin1, or NULL */
+} VfmSamBlockParams;
+
+typedef struct {
+  int embed_dim, depth, heads, head_dim, hidden, n_taps, grid, use_rel_pos;
+  int tap_blocks[8];              /* out_indices, ascending */
+  float ln_eps;
+  const void* patch_w;            /* [embed_dim, 768] bf16 */
+  const float* patch_b;
+  const float* pos_embed;         /* [grid*grid, embed_dim] */
+  const float* ones;              /* [embed_dim] of 1.0f (no LayerScale) */
+  /* window maps for the n_crops of this call (device int32): part[window-order row] = token row or -1 (zero padding),
+   * unpart[token row] = window-order row; win_rows = number of window-order rows; win_buf = bf16 [win_rows, embed_dim], zero-filled
+   * ONCE by the caller (the padding rows are never written). All unused when no block is windowed. */
+  const int* part; const int* unpart; int win_rows; void* win_buf;
+  const void* onehot; int onehot_rows;   /* vfm_attention_global_tc's key matrix for the grid, or NULL */
+  const VfmSamBlockParams* blocks;       /* host array [depth] */
+} VfmSamParams;
+
+size_t vfm_sam_workspace_bytes(const VfmSamParams* p /*host*/, int n_crops);
+/* taps[(crop*grid*grid + p), t*embed_dim + c] (bf16): the raw block outputs at tap_blocks. */
+int vfm_sam_forward(const VfmSamParams* p /*host*/, const void* img, int is_u8, const VfmPixelNorm* nrm /*host*/, int img_h,
+                    int img_w, const int* crops, int n_crops, void* taps, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,41 @@ def test_abi_header_and_binding_agree_and_library_exports_every_symbol():
     assert lib.vfm_gemm_cls_nchw(None, 0, None, 0, None, None, 40, 1, 1, 64, None) == -1
 
 
+def test_struct_layouts_of_header_and_binding_agree(tmp_path):
+    """Every parameter struct of include/vfmseg_b200.h, as gcc lays it out, against the ctypes mirror in vfmseg_b200/_C.py:
+    size and the offset of every field (the fused drivers vfm_vit_forward / vfm_eva_forward / vfm_sam_forward /
+    vfm_linear_head_forward read these blocks on the host)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    structs = ["VfmPixelNorm", "VfmBlockParams", "VfmVitParams", "VfmLinearHeadParams", "VfmEvaBlockParams", "VfmEvaParams",
+               "VfmSamBlockParams", "VfmSamParams"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include <stdint.h>', f'#include "{ROOT / "include" / "vfmseg_b200.h"}"', "int main(void) {"]
+    for st in structs:
+        cls = getattr(_C, st)
+        lines.append(f'  printf("{st} size %zu\\n", sizeof({st}));')
+        for name, _ in cls._fields_:
+            lines.append(f'  printf("{st} {name} %zu\\n", offsetof({st}, {name}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        st, field, val = ln.split()
+        cls = getattr(_C, st)
+        want = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(val) == want, (st, field, val, want)
+        seen += 1
+    assert seen == sum(len(getattr(_C, st)._fields_) + 1 for st in structs)
+
+
 def test_metric_reduction_matches_oracle_and_accepts_reference_records():
     rng = np.random.default_rng(0)
     nc = 19

@@ -233,3 +233,31 @@ def test_sam_1024_crop_two_blocks_vs_oracle():
     for i, (f, r) in enumerate(zip(feats, ref)):
         assert f.shape == (1, 1280, 64, 64)
         _check_logits(f, r, f"SAM ViT-H 1024 crop, block {i} output vs oracle")
+
+
+@pytest.mark.parametrize("variant,fold", [("tiny80", "3"), ("tiny64", "3"), ("tiny64", "0"), ("real", "3"), ("real", "0")])
+def test_sam_c_driver_equals_python_driver(monkeypatch, variant, fold):
+    """vfm_sam_forward (one C call for SAMViT.forward, sam_vit.py:123-147) against the same launch sequence issued operator by
+    operator from Python (VFM_SAM_DRIVER=py): bit-identical taps. tiny80 = head_dim 80 (tcgen05 window / global attention, width
+    640: no LayerNorm folding), tiny64 = head_dim 64 (CUDA-core rel-pos attention + row gather, width 512: folding on / off),
+    real = SAM ViT-H dimensions (1280 wide, 32 blocks, 32 x 32 tokens, 14 x 14 windows)."""
+    from vfmseg_b200 import synthetic
+    if variant == "real":
+        cfg, crop = synthetic.sam_model_config(), 512
+    elif variant == "tiny64":
+        cfg, crop = synthetic.tiny_sam_config(embed_dim=512, num_heads=8), 256
+    else:
+        cfg, crop = synthetic.tiny_sam_config(), 256
+    model, _ = _build_sam(cfg)
+    eng = model.engine()
+    g = crop // 16
+    img = synthetic.synthetic_images(2, crop + 32, crop + 48, seed=78).cuda()
+    crops = torch.tensor([[0, 0, 0, 0], [1, 32, 48, 0], [0, 16, 8, 0]], dtype=torch.int32, device="cuda")
+    monkeypatch.setenv("VFM_LN_FOLD", fold)
+    for x, cr in ((img, crops), ((img.float() - 110.0) / 60.0, crops[:2].contiguous())):
+        monkeypatch.setenv("VFM_SAM_DRIVER", "py")
+        ref = eng.backbone_taps(x.contiguous(), cr, g, g)
+        monkeypatch.setenv("VFM_SAM_DRIVER", "c")
+        got = eng.backbone_taps(x.contiguous(), cr, g, g)
+        assert got.shape == ref.shape and torch.isfinite(got.float()).all()
+        assert torch.equal(got, ref)

@@ -37,6 +37,38 @@ class VfmVitParams(C.Structure):
     ]
 
 
+class VfmEvaBlockParams(C.Structure):
+    _fields_ = [(n, _p) for n in (
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "w12", "b12",
+        "ffn_ln_w", "ffn_ln_b", "w3", "b3", "qkv_wf", "qkv_bf", "qkv_cs", "w12_wf", "w12_bf", "w12_cs")]
+
+
+class VfmEvaParams(C.Structure):
+    _fields_ = [
+        ("embed_dim", _i), ("depth", _i), ("heads", _i), ("hidden", _i), ("hidden_pad", _i), ("n_taps", _i), ("grid", _i),
+        ("tap_blocks", _i * 8), ("ln_eps", _f),
+        ("patch_w", _p), ("patch_b", _p), ("cls_token", _p), ("pos_embed", _p), ("rope_cos", _p), ("rope_sin", _p), ("ones", _p),
+        ("blocks", C.POINTER(VfmEvaBlockParams)),
+    ]
+
+
+class VfmSamBlockParams(C.Structure):
+    _fields_ = [("window", _i), ("qkv_n", _i)] + [(n, _p) for n in (
+        "ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+        "lin1_wf", "lin1_bf", "lin1_cs")]
+
+
+class VfmSamParams(C.Structure):
+    _fields_ = [
+        ("embed_dim", _i), ("depth", _i), ("heads", _i), ("head_dim", _i), ("hidden", _i), ("n_taps", _i), ("grid", _i),
+        ("use_rel_pos", _i), ("tap_blocks", _i * 8), ("ln_eps", _f),
+        ("patch_w", _p), ("patch_b", _p), ("pos_embed", _p), ("ones", _p),
+        ("part", _p), ("unpart", _p), ("win_rows", _i), ("win_buf", _p),
+        ("onehot", _p), ("onehot_rows", _i),
+        ("blocks", C.POINTER(VfmSamBlockParams)),
+    ]
+
+
 class VfmLinearHeadParams(C.Structure):
     _fields_ = [
         ("in_channels", _i), ("mid_channels", _i), ("groups", _i), ("num_classes", _i), ("gn_eps", _f),
@@ -99,6 +131,10 @@ SIGNATURES = {
     "vfm_vit_workspace_bytes": (_sz, [C.POINTER(VfmVitParams), _i, _i, _i]),
     "vfm_vit_forward": (_i, [C.POINTER(VfmVitParams), _p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _i, _i,
                              _p, _p, _sz, _p]),
+    "vfm_eva_workspace_bytes": (_sz, [C.POINTER(VfmEvaParams), _i]),
+    "vfm_eva_forward": (_i, [C.POINTER(VfmEvaParams), _p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _p, _p, _sz, _p]),
+    "vfm_sam_workspace_bytes": (_sz, [C.POINTER(VfmSamParams), _i]),
+    "vfm_sam_forward": (_i, [C.POINTER(VfmSamParams), _p, _i, C.POINTER(VfmPixelNorm), _i, _i, _p, _i, _p, _p, _sz, _p]),
     "vfm_linear_head_workspace_bytes": (_sz, [C.POINTER(VfmLinearHeadParams), _i, _i, _i]),
     "vfm_linear_head_forward": (_i, [C.POINTER(VfmLinearHeadParams), _p, _i, _i, _i, _p, _p, _sz, _p]),
 }

@@ -1242,6 +1242,197 @@ int vfm_vit_forward(const VfmVitParams* p, const void* img, int is_u8, const Vfm
   return VFM_OK;
 }
 
+// EVA02 workspace: x fp32 [M, C], xn bf16 [M, C], att bf16 [M, C], qkv bf16 [M, 3C], h12 bf16 [M, 2 Hp] (also the gathered
+// patches [n P, 768]), u bf16 [M, Hp], LayerNorm statistics; M = n_crops * (grid^2 + 1).
+size_t vfm_eva_workspace_bytes(const VfmEvaParams* p, int n_crops) {
+  if (!p) return 0;
+  const size_t P = static_cast<size_t>(p->grid) * p->grid, M = static_cast<size_t>(n_crops) * (P + 1);
+  const size_t C = p->embed_dim, Hp = p->hidden_pad;
+  size_t h12 = M * 2 * Hp * 2;
+  const size_t patches = static_cast<size_t>(n_crops) * P * 768 * 2;
+  if (patches > h12) h12 = patches;
+  return align_up(M * C * 4, 256) + 2 * align_up(M * C * 2, 256) + align_up(M * 3 * C * 2, 256) + align_up(h12, 256) +
+         align_up(M * Hp * 2, 256) + align_up(M * (C / 128 + 1) * 8, 256);
+}
+
+int vfm_eva_forward(const VfmEvaParams* p, const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w,
+                    const int* crops, int n_crops, void* taps, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->blocks || !img || !crops || !taps || !workspace) return fail(VFM_ERR_INVALID, "eva_forward: null argument");
+  const int C = p->embed_dim, H = p->hidden, Hp = p->hidden_pad, g = p->grid;
+  if (C != p->heads * 64) return fail(VFM_ERR_INVALID, "eva_forward: head_dim must be 64 (embed_dim=%d heads=%d)", C, p->heads);
+  if (p->n_taps <= 0 || p->n_taps > 8) return fail(VFM_ERR_INVALID, "eva_forward: n_taps out of range");
+  if (Hp < H || (Hp % 8)) return fail(VFM_ERR_INVALID, "eva_forward: hidden_pad must be a multiple of 8 and >= hidden");
+  if (n_crops <= 0 || g <= 0) return fail(VFM_ERR_INVALID, "eva_forward: bad n_crops / grid");
+  const size_t need = vfm_eva_workspace_bytes(p, n_crops);
+  if (workspace_bytes < need) return fail(VFM_ERR_WORKSPACE, "eva_forward: workspace %zu < %zu", workspace_bytes, need);
+  const int P = g * g, T = P + 1;
+  const int M = n_crops * T;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws);            ws += align_up(static_cast<size_t>(M) * C * 4, 256);
+  void* xn = ws;                                      ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* att = ws;                                     ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* qkv = ws;                                     ws += align_up(static_cast<size_t>(M) * 3 * C * 2, 256);
+  void* h12 = ws;
+  {
+    size_t hb = static_cast<size_t>(M) * 2 * Hp * 2;
+    const size_t pb = static_cast<size_t>(n_crops) * P * 768 * 2;
+    if (pb > hb) hb = pb;
+    ws += align_up(hb, 256);
+  }
+  void* u = ws;                                       ws += align_up(static_cast<size_t>(M) * Hp * 2, 256);
+  float* stats = reinterpret_cast<float*>(ws);
+  // VFM_LN_FOLD as in vfm_vit_forward; read per call so that a test can compare the folded and the plain sequence in one process
+  int fold_env = 3;
+  if (const char* e = getenv("VFM_LN_FOLD")) fold_env = atoi(e);
+  const bool have_fold = (C % 256) == 0 && p->blocks[0].qkv_wf != nullptr;
+  const bool fold_ok1 = have_fold && (fold_env & 1), fold_ok2 = have_fold && (fold_env & 2);
+  auto is_tap = [&](int block) {
+    for (int t = 0; t < p->n_taps; ++t)
+      if (p->tap_blocks[t] == block) return t;
+    return -1;
+  };
+  int rc;
+  if ((rc = vfm_patch_gather(img, is_u8, nrm, img_h, img_w, crops, n_crops, g, g, h12, stream))) return rc;
+  if ((rc = vfm_gemm_patch_embed(h12, 768, p->patch_w, 768, p->patch_b, p->pos_embed, x, P, n_crops * P, C, 768, stream))) return rc;
+  if ((rc = vfm_cls_rows(x, p->cls_token, p->pos_embed, n_crops, T, C, stream))) return rc;
+  bool pre = false;   // xn = bf16(x) and stats are current (written by the previous block's w3 GEMM)
+  for (int l = 0; l < p->depth; ++l) {
+    const VfmEvaBlockParams& b = p->blocks[l];
+    const int tap_i = l > 0 ? is_tap(l - 1) : -1;   // tap of the previous block's output, emitted by this block's norm1 pass
+    if (pre) {
+      if ((rc = vfm_gemm_lnfold_rope_bf16(xn, C, b.qkv_wf, C, b.qkv_bf, b.qkv_cs, stats, p->ln_eps, qkv, 3 * C, M, 3 * C, C,
+                                          p->rope_cos, p->rope_sin, 2 * C, T, stream))) return rc;
+    } else {
+      if ((rc = vfm_layernorm_tap(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, tap_i >= 0 ? taps : nullptr, tap_i >= 0 ? p->n_taps * C : 0,
+                                  tap_i >= 0 ? tap_i * C : 0, T, stream))) return rc;
+      if ((rc = vfm_gemm_bias_rope_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, 3 * C, M, 3 * C, C, p->rope_cos, p->rope_sin, 2 * C, T, stream))) return rc;
+    }
+    if ((rc = vfm_attention_fwd_ex(qkv, att, n_crops, T, p->heads, 0, stream))) return rc;
+    if (fold_ok2 && b.w12_wf) {
+      if ((rc = vfm_gemm_bias_ls_residual_stats(att, C, b.proj_w, C, b.proj_b, p->ones, x, C, xn, C, stats, M, C, C, stream))) return rc;
+      if ((rc = vfm_gemm_lnfold_bf16(xn, C, b.w12_wf, C, b.w12_bf, b.w12_cs, stats, p->ln_eps, 0, h12, 2 * Hp, M, 2 * Hp, C, stream))) return rc;
+    } else {
+      if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, p->ones, x, C, nullptr, 0, 0, 1, M, C, C, stream))) return rc;
+      if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
+      if ((rc = vfm_gemm_bias_bf16(xn, C, b.w12, C, b.b12, h12, 2 * Hp, M, 2 * Hp, C, stream))) return rc;
+    }
+    if ((rc = vfm_swiglu_layernorm(h12, u, b.ffn_ln_w, b.ffn_ln_b, M, H, Hp, p->ln_eps, stream))) return rc;
+    pre = fold_ok1 && l + 1 < p->depth && is_tap(l) < 0 && p->blocks[l + 1].qkv_wf != nullptr;
+    if (pre) {
+      if ((rc = vfm_gemm_bias_ls_residual_stats(u, Hp, b.w3, Hp, b.b3, p->ones, x, C, xn, C, stats, M, C, Hp, stream))) return rc;
+    } else {
+      if ((rc = vfm_gemm_bias_ls_residual(u, Hp, b.w3, Hp, b.b3, p->ones, x, C, nullptr, 0, 0, 1, M, C, Hp, stream))) return rc;
+    }
+  }
+  const int last = is_tap(p->depth - 1);
+  if (last >= 0) {
+    if ((rc = vfm_layernorm_tap(x, nullptr, nullptr, nullptr, M, C, p->ln_eps, taps, p->n_taps * C, last * C, T, stream))) return rc;
+  }
+  return VFM_OK;
+}
+
+// SAM ViT workspace: x fp32 [M, C], xn bf16 [M, C], att bf16 [M, C], att_w bf16 [win_rows, C] (windowed blocks off the tcgen05
+// path only), qkv bf16 [max(M, win_rows), max qkv_n], hid bf16 [M, hidden] (also the gathered patches), statistics; M = n P.
+static size_t sam_qkv_elems(const VfmSamParams* p, size_t M) {
+  size_t best = 0;
+  for (int l = 0; l < p->depth; ++l) {
+    const size_t rows = p->blocks[l].window ? static_cast<size_t>(p->win_rows) : M;
+    const size_t e = rows * static_cast<size_t>(p->blocks[l].qkv_n);
+    if (e > best) best = e;
+  }
+  return best;
+}
+size_t vfm_sam_workspace_bytes(const VfmSamParams* p, int n_crops) {
+  if (!p || !p->blocks) return 0;
+  const size_t P = static_cast<size_t>(p->grid) * p->grid, M = static_cast<size_t>(n_crops) * P, C = p->embed_dim;
+  size_t hid = M * p->hidden * 2;
+  if (M * 768 * 2 > hid) hid = M * 768 * 2;
+  return align_up(M * C * 4, 256) + 2 * align_up(M * C * 2, 256) + align_up(static_cast<size_t>(p->win_rows) * C * 2, 256) +
+         align_up(sam_qkv_elems(p, M) * 2, 256) + align_up(hid, 256) + align_up(M * (C / 128 + 1) * 8, 256);
+}
+
+int vfm_sam_forward(const VfmSamParams* p, const void* img, int is_u8, const VfmPixelNorm* nrm, int img_h, int img_w,
+                    const int* crops, int n_crops, void* taps, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->blocks || !img || !crops || !taps || !workspace) return fail(VFM_ERR_INVALID, "sam_forward: null argument");
+  const int C = p->embed_dim, Hd = p->hidden, g = p->grid, H = p->heads, d = p->head_dim;
+  if (C != H * d || (d != 64 && d != 80)) return fail(VFM_ERR_INVALID, "sam_forward: head_dim must be 64 or 80 (embed_dim=%d heads=%d)", C, H);
+  if (p->n_taps <= 0 || p->n_taps > 8) return fail(VFM_ERR_INVALID, "sam_forward: n_taps out of range");
+  if (n_crops <= 0 || g <= 0) return fail(VFM_ERR_INVALID, "sam_forward: bad n_crops / grid");
+  const size_t need = vfm_sam_workspace_bytes(p, n_crops);
+  if (workspace_bytes < need) return fail(VFM_ERR_WORKSPACE, "sam_forward: workspace %zu < %zu", workspace_bytes, need);
+  const int P = g * g, M = n_crops * P;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(ws);            ws += align_up(static_cast<size_t>(M) * C * 4, 256);
+  void* xn = ws;                                      ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* att = ws;                                     ws += align_up(static_cast<size_t>(M) * C * 2, 256);
+  void* att_w = ws;                                   ws += align_up(static_cast<size_t>(p->win_rows) * C * 2, 256);
+  void* qkv = ws;                                     ws += align_up(sam_qkv_elems(p, M) * 2, 256);
+  void* hid = ws;
+  {
+    size_t hb = static_cast<size_t>(M) * Hd * 2;
+    if (static_cast<size_t>(M) * 768 * 2 > hb) hb = static_cast<size_t>(M) * 768 * 2;
+    ws += align_up(hb, 256);
+  }
+  float* stats = reinterpret_cast<float*>(ws);
+  int fold_env = 3;
+  if (const char* e = getenv("VFM_LN_FOLD")) fold_env = atoi(e);
+  const float scale = static_cast<float>(pow(static_cast<double>(d), -0.5));   // head_dim ** -0.5 as the Python driver computed it
+  const int g0 = p->use_rel_pos ? 3 * C : -1;   // first table-term column of the extended qkv rows
+  auto is_tap = [&](int block) {
+    for (int t = 0; t < p->n_taps; ++t)
+      if (p->tap_blocks[t] == block) return t;
+    return -1;
+  };
+  int rc;
+  if ((rc = vfm_patch_gather(img, is_u8, nrm, img_h, img_w, crops, n_crops, g, g, hid, stream))) return rc;
+  if ((rc = vfm_gemm_patch_embed_ex(hid, 768, p->patch_w, 768, p->patch_b, p->pos_embed, x, P, 0, M, C, 768, stream))) return rc;
+  for (int l = 0; l < p->depth; ++l) {
+    const VfmSamBlockParams& b = p->blocks[l];
+    const int tap_i = l > 0 ? is_tap(l - 1) : -1;   // tap of the previous block's output, emitted by this block's norm1 pass
+    void* tap = tap_i >= 0 ? taps : nullptr;
+    const int tap_ld = tap_i >= 0 ? p->n_taps * C : 0, tap_col0 = tap_i >= 0 ? tap_i * C : 0;
+    const int wsz = b.window, Nq = b.qkv_n;
+    if (wsz) {
+      // window_partition folded into the LayerNorm store, window_unpartition into the attention kernel's store
+      if (!p->part || !p->unpart || !p->win_buf || p->win_rows % (wsz * wsz))
+        return fail(VFM_ERR_INVALID, "sam_forward: windowed block %d needs part / unpart / win_buf (win_rows %% window^2 == 0)", l);
+      const int n_win = p->win_rows / (wsz * wsz);
+      if ((rc = vfm_layernorm_tap_map(x, b.ln1_w, b.ln1_b, p->win_buf, M, C, p->ln_eps, tap, tap_ld, tap_col0, 1, 0, p->unpart, stream))) return rc;
+      if ((rc = vfm_gemm_bias_bf16(p->win_buf, C, b.qkv_w, C, b.qkv_b, qkv, Nq, p->win_rows, Nq, C, stream))) return rc;
+      if (d == 80 && wsz * wsz <= 208 && wsz <= 16) {   // whole window in one tcgen05 score tile
+        if ((rc = vfm_attention_window_tc_map(qkv, Nq, g0, att, p->part, n_win, wsz * wsz, H, d, wsz, wsz, scale, stream))) return rc;
+      } else {
+        if ((rc = vfm_attention_relpos_ex(qkv, Nq, g0, nullptr, att_w, n_win, wsz * wsz, H, d, wsz, wsz, scale, stream))) return rc;
+        if ((rc = vfm_rows_gather(att_w, att, p->unpart, M, C, stream))) return rc;
+      }
+    } else {
+      if ((rc = vfm_layernorm_tap_ex(x, b.ln1_w, b.ln1_b, xn, M, C, p->ln_eps, tap, tap_ld, tap_col0, 1, 0, stream))) return rc;
+      if ((rc = vfm_gemm_bias_bf16(xn, C, b.qkv_w, C, b.qkv_b, qkv, Nq, M, Nq, C, stream))) return rc;
+      const int bias_cols = (g + 15) / 16 * 16 * 2;
+      if (d == 80 && g0 >= 0 && bias_cols <= 128 && p->onehot) {   // key-tile loop on tcgen05
+        if ((rc = vfm_attention_global_tc(qkv, Nq, g0, p->onehot, p->onehot_rows, att, n_crops, P, H, d, g, g, scale, stream))) return rc;
+      } else {
+        if ((rc = vfm_attention_relpos_ex(qkv, Nq, g0, nullptr, att, n_crops, P, H, d, g, g, scale, stream))) return rc;
+      }
+    }
+    if ((fold_env & 2) && b.lin1_wf && (C % 256) == 0) {
+      // the proj GEMM also emits bf16(x) and the row statistics; lin1 applies norm2 in its epilogue (no LayerNorm pass)
+      if ((rc = vfm_gemm_bias_ls_residual_stats(att, C, b.proj_w, C, b.proj_b, p->ones, x, C, xn, C, stats, M, C, C, stream))) return rc;
+      if ((rc = vfm_gemm_lnfold_bf16(xn, C, b.lin1_wf, C, b.lin1_bf, b.lin1_cs, stats, p->ln_eps, 1, hid, Hd, M, Hd, C, stream))) return rc;
+    } else {
+      if ((rc = vfm_gemm_bias_ls_residual(att, C, b.proj_w, C, b.proj_b, p->ones, x, C, nullptr, 0, 0, 1, M, C, C, stream))) return rc;
+      if ((rc = vfm_layernorm(x, b.ln2_w, b.ln2_b, xn, M, C, p->ln_eps, stream))) return rc;
+      if ((rc = vfm_gemm_bias_gelu_bf16(xn, C, b.lin1_w, C, b.lin1_b, hid, Hd, M, Hd, C, stream))) return rc;
+    }
+    if ((rc = vfm_gemm_bias_ls_residual(hid, Hd, b.lin2_w, Hd, b.lin2_b, p->ones, x, C, nullptr, 0, 0, 1, M, C, Hd, stream))) return rc;
+  }
+  const int last = is_tap(p->depth - 1);
+  if (last >= 0) {
+    if ((rc = vfm_layernorm_tap_ex(x, nullptr, nullptr, nullptr, M, C, p->ln_eps, taps, p->n_taps * C, last * C, 1, 0, stream))) return rc;
+  }
+  return VFM_OK;
+}
+
 // LinearHead workspace: f0 bf16 [R, mid] (fusion out), f1 bf16 [R, mid] (GN+ReLU), u1 bf16 [4R, mid/2],
 // u2 bf16 [16R, mid/4]; R = n_crops * gh * gw.
 size_t vfm_linear_head_workspace_bytes(const VfmLinearHeadParams* p, int n_crops, int gh, int gw) {

@@ -268,7 +268,7 @@ class SlideEngine:
     def backbone_taps(self, img: torch.Tensor, crops: torch.Tensor, gh: int, gw: int) -> torch.Tensor:
         """Feature taps (token-major, cls dropped) for the crop windows listed in `crops`
         (int32 [n,4] = image, y1, x1, 0): bf16 [n*gh*gw, n_taps*C]."""
-        if hasattr(self.vit, "forward_taps"):      # backbones driven block by block from Python (EVA02)
+        if hasattr(self.vit, "forward_taps"):      # EVA02 / SAM ViT: their own fused C drivers (vfm_eva_forward / vfm_sam_forward)
             return self.vit.forward_taps(img, crops, gh, gw, self.pixel_norm)
         lib = _C.load()
         n = crops.shape[0]

@@ -10,7 +10,9 @@ nn.LayerNorm eps is 1e-5 in the blocks: EVA2.__init__ does not forward the confi
 """
 from __future__ import annotations
 
+import ctypes as C_
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -127,16 +129,67 @@ class PackedEva:
                 ffn_ln=(dev(sd[p + "mlp.ffn_ln.weight"], f32), dev(sd[p + "mlp.ffn_ln.bias"], f32)),
                 w3=dev(w3, bf), b3=dev(_bias(sd, p + "mlp.w3"), f32)))
         self._keep = keep
+        self._ws = None
+        self._params = self._c_params()
+
+    def _c_params(self) -> _C.VfmEvaParams:
+        """The host-side parameter block of vfm_eva_forward (include/vfmseg_b200.h): pointers into the packed weights."""
+        s = self.spec
+        outs = sorted(s.out_indices)
+        if len(outs) > 8:
+            raise ValueError("at most 8 feature taps")
+        self._c_blocks = (_C.VfmEvaBlockParams * s.depth)()
+        for blk, b in zip(self._c_blocks, self.blocks):
+            blk.ln1_w, blk.ln1_b = (t.data_ptr() for t in b["n1"])
+            blk.ln2_w, blk.ln2_b = (t.data_ptr() for t in b["n2"])
+            blk.qkv_w, blk.qkv_b = b["qkv_w"].data_ptr(), b["qkv_b"].data_ptr()
+            blk.proj_w, blk.proj_b = b["proj_w"].data_ptr(), b["proj_b"].data_ptr()
+            blk.w12, blk.b12 = b["w12"].data_ptr(), b["b12"].data_ptr()
+            blk.ffn_ln_w, blk.ffn_ln_b = (t.data_ptr() for t in b["ffn_ln"])
+            blk.w3, blk.b3 = b["w3"].data_ptr(), b["b3"].data_ptr()
+            if "qkv_f" in b:
+                blk.qkv_wf, blk.qkv_bf, blk.qkv_cs = (t.data_ptr() for t in b["qkv_f"])
+                blk.w12_wf, blk.w12_bf, blk.w12_cs = (t.data_ptr() for t in b["w12_f"])
+        p = _C.VfmEvaParams()
+        p.embed_dim, p.depth, p.heads, p.hidden, p.hidden_pad = s.embed_dim, s.depth, s.num_heads, s.hidden, self.Hp
+        p.n_taps, p.grid, p.ln_eps = len(outs), s.grid, s.ln_eps
+        for i, o in enumerate(outs):
+            p.tap_blocks[i] = o
+        p.patch_w, p.patch_b = self.patch_w.data_ptr(), self.patch_b.data_ptr()
+        p.cls_token, p.pos_embed = self.cls_token.data_ptr(), self.pos.data_ptr()
+        p.rope_cos, p.rope_sin, p.ones = self.rope_cos.data_ptr(), self.rope_sin.data_ptr(), self.ones.data_ptr()
+        p.blocks = C_.cast(self._c_blocks, C_.POINTER(_C.VfmEvaBlockParams))
+        return p
 
     # SlideEngine.backbone_taps dispatches here
     def forward_taps(self, img: torch.Tensor, crops: torch.Tensor, gh: int, gw: int, pixel_norm) -> torch.Tensor:
         """EVA2.forward_features (eva_02.py:816-849) for the listed windows -> taps bf16 [n*gh*gw, n_taps*C] (token-major,
-        cls dropped): the un-normalised residual stream after the blocks in out_indices."""
+        cls dropped): the un-normalised residual stream after the blocks in out_indices. One call of the fused C driver
+        vfm_eva_forward; VFM_EVA_DRIVER=py issues the same launch sequence operator by operator from Python (the comparison path
+        of tests/test_eva_gpu.py: bit-identical taps)."""
         s = self.spec
         if gh != s.grid or gw != s.grid:
             raise _C.VfmError(f"EVA02 adds a fixed {s.grid}x{s.grid} pos_embed / RoPE table without interpolation "
                               f"(eva_02.py:690-697,825-826): windows must be {s.grid * 16}x{s.grid * 16}, got grid {gh}x{gw}")
         n, P, C = crops.shape[0], gh * gw, s.embed_dim
+        if os.environ.get("VFM_EVA_DRIVER", "c") != "py":
+            is_u8 = img.dtype == torch.uint8
+            if is_u8 and pixel_norm is None:
+                raise _C.VfmError("uint8 input needs set_pixel_norm() (SegDataPreProcessor mean/std)")
+            if not is_u8 and img.dtype != torch.float32:
+                raise _C.VfmError(f"input must be uint8 or float32, got {img.dtype}")
+            assert img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+            assert crops.dtype == torch.int32 and crops.is_contiguous() and crops.shape[1] == 4
+            lib = _C.load()
+            need = lib.vfm_eva_workspace_bytes(C_.byref(self._params), n)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            taps = torch.empty(n * P, len(s.out_indices) * C, dtype=torch.bfloat16, device=self.device)
+            _C.call("vfm_eva_forward", C_.byref(self._params), img.data_ptr(), int(is_u8),
+                    C_.byref(pixel_norm) if (is_u8 and pixel_norm is not None) else None, img.shape[2], img.shape[3],
+                    crops.data_ptr(), n, taps.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                    torch.cuda.current_stream().cuda_stream)
+            return taps
         T = P + 1
         a = ops.patch_gather(img, crops, gh, gw, pixel_norm if img.dtype == torch.uint8 else None)
         x = ops.gemm_patch_embed(a, self.patch_w, self.patch_b, self.pos, n, P)        # :818-826 (+ pos_embed[1:])

@@ -12,6 +12,8 @@ Block (sam_vit.py:201-217):  x += attn(window_partition(norm1(x)));  x += mlp(no
 """
 from __future__ import annotations
 
+import ctypes as C_
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
@@ -127,6 +129,50 @@ class PackedSam:
             self.blocks.append(blk)
         self._keep = keep
         self._maps: Dict[tuple, tuple] = {}
+        self._ws = None
+        self._c_blocks = (_C.VfmSamBlockParams * spec.depth)()
+        for blk, b in zip(self._c_blocks, self.blocks):
+            blk.window, blk.qkv_n = b["window"], b["qkv_w"].shape[0]
+            blk.ln1_w, blk.ln1_b = (t.data_ptr() for t in b["n1"])
+            blk.ln2_w, blk.ln2_b = (t.data_ptr() for t in b["n2"])
+            for nm in ("qkv_w", "qkv_b", "proj_w", "proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b"):
+                setattr(blk, nm, b[nm].data_ptr())
+            if "lin1_f" in b:
+                blk.lin1_wf, blk.lin1_bf, blk.lin1_cs = (t.data_ptr() for t in b["lin1_f"])
+
+    def _c_params(self, n: int) -> _C.VfmSamParams:
+        """The host-side parameter block of vfm_sam_forward (include/vfmseg_b200.h) for n windows: pointers into the packed
+        weights, the window maps / persistent window buffer of this n and the one-hot key matrix of the grid."""
+        key = ("cparams", n)
+        if key in self._maps:
+            return self._maps[key]
+        s = self.spec
+        outs = sorted(s.out_indices)
+        if len(outs) > 8:
+            raise ValueError("at most 8 feature taps")
+        p = _C.VfmSamParams()
+        p.embed_dim, p.depth, p.heads, p.head_dim, p.hidden = s.embed_dim, s.depth, s.num_heads, self.head_dim, s.hidden
+        p.n_taps, p.grid, p.use_rel_pos, p.ln_eps = len(outs), s.grid, int(s.use_rel_pos), s.ln_eps
+        for i, o in enumerate(outs):
+            p.tap_blocks[i] = o
+        p.patch_w, p.patch_b = self.patch_w.data_ptr(), self.patch_b.data_ptr()
+        p.pos_embed, p.ones = self.pos.data_ptr(), self.ones.data_ptr()
+        wsz = {b["window"] for b in self.blocks if b["window"]}
+        if len(wsz) > 1:
+            raise ValueError("one window size per backbone (sam_vit.py:94-107)")
+        if wsz:
+            ws = wsz.pop()
+            part, unpart, n_win = self._window_maps(n, s.grid, s.grid, ws)
+            p.part, p.unpart, p.win_rows = part.data_ptr(), unpart.data_ptr(), n_win * ws * ws
+            p.win_buf = self._window_buffer(n_win * ws * ws, s.embed_dim).data_ptr()
+        if s.use_rel_pos and self.head_dim == 80 and (s.grid + 15) // 16 * 32 <= 128:
+            key1 = ("onehot", s.grid, s.grid)
+            if key1 not in self._maps:
+                self._maps[key1] = ops.relpos_onehot(s.grid, s.grid, self.device)
+            p.onehot, p.onehot_rows = self._maps[key1].data_ptr(), self._maps[key1].shape[0]
+        p.blocks = C_.cast(self._c_blocks, C_.POINTER(_C.VfmSamBlockParams))
+        self._maps[key] = p
+        return p
 
     def _window_maps(self, n: int, gh: int, gw: int, ws: int):
         """Row maps of window_partition / window_unpartition (sam_vit.py:292-346) for n crops of gh x gw tokens:
@@ -160,6 +206,26 @@ class PackedSam:
             raise _C.VfmError(f"SAMViT adds a fixed {s.grid}x{s.grid} pos_embed without interpolation (sam_vit.py:131-132): "
                               f"windows must be {s.grid * 16}x{s.grid * 16}, got grid {gh}x{gw}")
         n, P, C, H, d = crops.shape[0], gh * gw, s.embed_dim, s.num_heads, self.head_dim
+        if os.environ.get("VFM_SAM_DRIVER", "c") != "py":
+            # one call of the fused C driver; VFM_SAM_DRIVER=py issues the same launch sequence operator by operator from Python
+            # (the comparison path of tests/test_sam_gpu.py: bit-identical taps)
+            is_u8 = img.dtype == torch.uint8
+            if is_u8 and pixel_norm is None:
+                raise _C.VfmError("uint8 input needs set_pixel_norm() (SegDataPreProcessor mean/std)")
+            if not is_u8 and img.dtype != torch.float32:
+                raise _C.VfmError(f"input must be uint8 or float32, got {img.dtype}")
+            assert img.is_contiguous() and img.dim() == 4 and img.shape[1] == 3
+            assert crops.dtype == torch.int32 and crops.is_contiguous() and crops.shape[1] == 4
+            prm = self._c_params(n)
+            need = _C.load().vfm_sam_workspace_bytes(C_.byref(prm), n)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            taps = torch.empty(n * P, len(s.out_indices) * C, dtype=torch.bfloat16, device=self.device)
+            _C.call("vfm_sam_forward", C_.byref(prm), img.data_ptr(), int(is_u8),
+                    C_.byref(pixel_norm) if (is_u8 and pixel_norm is not None) else None, img.shape[2], img.shape[3],
+                    crops.data_ptr(), n, taps.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                    torch.cuda.current_stream().cuda_stream)
+            return taps
         scale = d ** -0.5
         g0 = 3 * C if s.use_rel_pos else -1          # first table-term column of the extended qkv rows
         a = ops.patch_gather(img, crops, gh, gw, pixel_norm if img.dtype == torch.uint8 else None)
