@@ -319,7 +319,7 @@ slide_merge_tile_kernel(const float* __restrict__ lowres, const int2* __restrict
 //    with cx >= 2 takes its 4-6 taps per class from shared memory once and evaluates the four pixels with immediate weights;
 //    strips on a window's left / right border use the per-pixel expression, out of line;
 //  * a warp owns two strips x 16 rows (not 16 strips x 2 rows): a window's left / right border then crosses one warp of the
-//    tile instead of all eight (the first version of this kernel spent 17 % of its instructions in the border path);
+//    tile instead of all eight (the first version of this kernel spent 12 % of its instructions in the border path);
 //  * count in {1, 2, 4, 8, ...}: multiplying by the exact reciprocal equals the IEEE division, other counts divide.
 // Every pixel evaluates the same expression in the same window order as slide_merge_argmax_kernel: bit-identical results
 // (tests/test_ops_gpu.py compares the kernels). A tile overlapped by more than MERGE_MAXW windows (stride < crop / 2) gathers
