@@ -141,3 +141,36 @@ def test_ms_merge_argmax(ops, refine):
     ref = preds / count
     assert (logits.cpu() - ref).abs().max() < 1e-4
     assert (labels.cpu().long() == logits.cpu().argmax(1)).all()
+
+
+@pytest.mark.parametrize("H,W,crop,stride,lg0,lgr,n_img", [(1024, 2048, 512, 341, 3, 4, 2), (96, 160, 64, 40, 3, 4, 2), (128, 192, 64, 33, 3, 4, 1),
+                                                          (64, 128, 64, 43, 2, 2, 1), (96, 132, 64, 21, 2, 5, 1)])
+@pytest.mark.parametrize("refine", ["none", "some", "all"])
+def test_ms_merge_class_major_equals_pixel_kernel(ops, monkeypatch, H, W, crop, stride, lg0, lgr, n_img, refine):
+    """The class-major tile kernel of the stage-1 merge (ms_merge_class_kernel: context + refined-window footprints staged in shared
+    memory, one class at a time, integer geometry for power-of-two upsampling) against the per-pixel gather kernel
+    (VFM_MERGE_MODE=1): labels and logits bit for bit; full BASELINE config 3 size, tiles under more than four windows, ragged
+    widths, upsampling factors 4 .. 32, no / some / all windows refined."""
+    nc = 19
+    low0 = _rand(n_img, nc, H >> lg0, W >> lg0, scale=2.0, seed=23)
+    boxes = _boxes(H, W, (crop, crop), (stride, stride))
+    nk = len(boxes)
+    bt = torch.tensor(boxes, dtype=torch.int32).cuda()
+    g = torch.Generator().manual_seed(24)
+    mask = {"none": torch.zeros(n_img, nk, dtype=torch.bool), "all": torch.ones(n_img, nk, dtype=torch.bool),
+            "some": torch.rand(n_img, nk, generator=g) > 0.5}[refine]
+    ref_index = torch.full((n_img, nk), -1, dtype=torch.int32)
+    n_ref = int(mask.sum())
+    ref_index[mask] = torch.randperm(n_ref, generator=g).to(torch.int32)
+    refined = _rand(max(n_ref, 1), nc, crop >> lgr, crop >> lgr, scale=2.0, seed=25) if n_ref else None
+    ri = ref_index.cuda()
+    monkeypatch.setenv("VFM_MERGE_MODE", "1")
+    lab_old, log_old = ops.ms_merge_argmax(low0, refined, ri, bt, (crop, crop), (H, W), want_logits=True)
+    for mode in ("0", "3"):   # 2 (default) / 3 resident CTAs per SM
+        monkeypatch.setenv("VFM_MERGE_MODE", mode)
+        lab, log = ops.ms_merge_argmax(low0, refined, ri, bt, (crop, crop), (H, W), want_logits=True)
+        lab2, none = ops.ms_merge_argmax(low0, refined, ri, bt, (crop, crop), (H, W))
+        assert none is None
+        assert torch.equal(log, log_old) and torch.equal(lab, lab_old) and torch.equal(lab2, lab_old), mode
+    monkeypatch.delenv("VFM_MERGE_MODE")
+    assert torch.equal(lab_old.long(), log_old.argmax(1))

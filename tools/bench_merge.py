@@ -31,3 +31,27 @@ for mode in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("1", "2", "3", "0
                           "want_logits": want, "median_us": round(med * 1e3, 1), "min_us": round(min(ts) * 1e3, 1),
                           "algorithmic_GBps": round(b / med / 1e6, 1)}))
 os.environ.pop("VFM_MERGE_MODE", None)
+
+# Stage-1 merge of ms_inference (BASELINE config 3): 2 images, coarse logits 128x256 (x8), 24 of 36 windows refined (32x32, x16)
+if len(sys.argv) <= 2 or sys.argv[2] != "noms":
+    low0 = torch.randn(2, 19, 128, 256, device="cuda")
+    g = torch.Generator().manual_seed(1)
+    mask = torch.rand(2, 18, generator=g) < 0.67
+    ref_index = torch.full((2, 18), -1, dtype=torch.int32)
+    ref_index[mask] = torch.arange(int(mask.sum()), dtype=torch.int32)
+    refined = torch.randn(int(mask.sum()), 19, 32, 32, device="cuda")
+    ri = ref_index.cuda()
+    for mode, name in (("1", "ms_merge_argmax_kernel (per-pixel gather)"), ("3", "ms_merge_class_kernel, CTAs per SM >= 3"),
+                       ("0", "ms_merge_class_kernel, CTAs per SM >= 2")):
+        os.environ["VFM_MERGE_MODE"] = mode
+        f = lambda: ops.ms_merge_argmax(low0, refined, ri, bx, (512, 512), (1024, 2048))
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_(); s.record(); f(); e.record(); torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
+        print(json.dumps({"kernel": name, "refined_windows": int(mask.sum()), "median_us": round(sorted(ts)[10] * 1e3, 1),
+                          "min_us": round(min(ts) * 1e3, 1)}))
+    os.environ.pop("VFM_MERGE_MODE", None)

@@ -1082,9 +1082,27 @@ int vfm_ms_merge_argmax(const float* low0, const float* refined, const int* ref_
     return fail(VFM_ERR_INVALID, "ms_merge_argmax: bad args (num_classes <= 32)");
   const unsigned grid = grid_for(static_cast<long long>(n_img) * H * W, 32);
   const size_t smem = sizeof(int2) * n_crops;
+  // class-major tile kernel (slide_tail.cuh): both upsampling factors powers of two >= 4 (8 and 16 in the shipped config)
+  auto log2_factor = [](int big_h, int big_w, int small_h, int small_w) {
+    for (int lg = 2; lg < 16; ++lg)
+      if ((small_h << lg) == big_h && (small_w << lg) == big_w) return lg;
+    return -1;
+  };
+  const int lg0 = (lh > 0 && lw > 0) ? log2_factor(H, W, lh, lw) : -1;
+  const int lgr = refined ? ((rh > 0 && rw > 0) ? log2_factor(crop_h, crop_w, rh, rw) : -1) : 2;
+  const bool tiles = merge_mode() != 1 && nc <= 19 && lg0 >= 2 && lgr >= 2 && (W % 4) == 0 && n_img <= 65535 &&
+                     (reinterpret_cast<uintptr_t>(labels) & 3) == 0 && (!logits_out || (reinterpret_cast<uintptr_t>(logits_out) & 15) == 0);
   {
     LaunchScope scope("ms_merge_argmax", S(stream));
-    if (nc <= 19)
+    if (tiles) {
+      const dim3 tgrid((W + MERGE_TW - 1) / MERGE_TW, (H + MERGE_TH - 1) / MERGE_TH, n_img);
+      if (merge_mode() == 3)   // 3 resident CTAs per SM (80 registers, loop-invariant slot state partly spilled): 335 us against 309 us per 2 images
+        ms_merge_class_kernel<19, 3><<<tgrid, 256, 0, S(stream)>>>(low0, refined, ref_index, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h,
+                                                                  crop_w, lh, lw, rh, rw, H, W, lg0, lgr, labels, logits_out);
+      else
+        ms_merge_class_kernel<19, 2><<<tgrid, 256, 0, S(stream)>>>(low0, refined, ref_index, reinterpret_cast<const int2*>(boxes), n_crops, nc, crop_h,
+                                                                  crop_w, lh, lw, rh, rw, H, W, lg0, lgr, labels, logits_out);
+    } else if (nc <= 19)
       ms_merge_argmax_kernel<19><<<grid, 256, smem, S(stream)>>>(low0, refined, ref_index, reinterpret_cast<const int2*>(boxes), n_crops,
                                                                  nc, crop_h, crop_w, lh, lw, rh, rw, H, W, n_img, labels, logits_out);
     else

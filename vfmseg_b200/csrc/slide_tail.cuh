@@ -1,6 +1,7 @@
 // The memory-bound tail of slide inference: overlapped-window logit merge + argmax, and the
 // confusion-matrix histogram behind mIoU.
 #pragma once
+#include "ms_refine.cuh"
 #include "sm100_ptx.cuh"
 
 namespace vfm {
@@ -537,6 +538,249 @@ slide_merge_class_kernel(const float* __restrict__ lowres, const int2* __restric
       float acc[4] = {r.x, r.y, r.z, r.w};
       finish_class(c, acc);
     }
+  }
+  *reinterpret_cast<uint32_t*>(labels + static_cast<size_t>(b) * plane_out + pix) =
+      static_cast<uint32_t>(arg[0]) | (static_cast<uint32_t>(arg[1]) << 8) | (static_cast<uint32_t>(arg[2]) << 16) | (static_cast<uint32_t>(arg[3]) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-1 merge of ms_inference (Ms_VFM_encoder_decoder.py:449-461) + argmax in the class-major tile form of
+// slide_merge_class_kernel: same results, bit for bit, as ms_merge_argmax_kernel (ms_refine.cuh; tests compare the two). Sources
+// per 64 x 16 output tile: the coarse logits low0 (context value U(y, x), upsampled by S0 = H / lh) and, for every REFINED window
+// over the tile, its aux-decoder logits (upsampled by Sr = crop / rh); windows that were confident enough to be skipped add the
+// context value. Both upsampling factors must be powers of two >= 4 (8 and 16 in the shipped config): for a source pixel
+// coordinate c >= S / 2, x0 = (c - S / 2) >> log2 S and w1 = (((c - S / 2) & (S - 1)) + 0.5) / S exactly as the float expression
+// of bilerp_setup, a strip of four pixels touches at most three source columns, and w1 of pixel j is w1 of pixel 0 plus j / S
+// (minus one past the column step) without rounding. Per class a strip costs 6 shared loads per source instead of 16 L2-latency
+// loads per pixel and source, with 4 accumulators per thread instead of 19 + 19.
+struct MsStrip {        // per-thread view of one source (context or one refined window) for this thread's strip
+  uint32_t off;         // shared address of the tap (row y0, column x0 of pixel 0 | footprint column 0 for border strips), class 0
+  int meta;             // bits 0-2: 0 = border strip (per-pixel path), 1..4 = index of the first pixel one source column further (4: none);
+                        // bits 4-7: pixel j lies inside the window; bit 8: source used by this strip; bit 9: window refined;
+                        // bits 16-31: source-local x of pixel 0 plus 8 (border strips)
+  float w1_0, h1;
+};
+
+// Out of line on purpose: inlined five times (context + four window slots) the compiler hoists every slot's per-pixel weights and
+// select masks out of the class loop and spills them (192 bytes of stack at 128 registers).
+__device__ __noinline__ float4 ms_strip_eval(uint32_t q, int kx, float w1_0, float inv_s, float h1) {
+  const float h0 = 1.f - h1;
+  const float a0 = merge_lds(q), a1 = merge_lds(q + 4), a2 = merge_lds(q + 8);
+  const float b0 = merge_lds(q + 4 * MERGE_FC), b1 = merge_lds(q + 4 * MERGE_FC + 4), b2 = merge_lds(q + 4 * MERGE_FC + 8);
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool o = j >= kx;
+    const float w1 = __fadd_rn(w1_0, static_cast<float>(j) * inv_s) - (o ? 1.f : 0.f);   // exact
+    const float w0 = 1.f - w1;
+    v[j] = bilerp_rn(h0, h1, w0, w1, o ? a1 : a0, o ? a2 : a1, o ? b1 : b0, o ? b2 : b1);
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// Border strip of a source (pixels outside [0, limit), or c < S / 2 where the source coordinate clamps to 0): bilerp_setup's float
+// expression per pixel on the staged footprint (q = shared address of footprint row y0, source column 0). Returns the four
+// values; pixels outside the range return 0 (the caller masks them).
+__device__ __noinline__ float4 ms_strip_border(uint32_t q, int c0, int limit, float inv_s, float h1) {
+  const float h0 = 1.f - h1;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + j;
+    if (c < 0 || c >= limit) continue;
+    float sx = inv_s * (c + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+    const int x0 = static_cast<int>(sx);
+    const float w1 = sx - x0, w0 = 1.f - w1;
+    const uint32_t r = q + 4 * x0;   // taps beyond the last column / row are replicated in the footprint
+    v[j] = bilerp_rn(h0, h1, w0, w1, merge_lds(r), merge_lds(r + 4), merge_lds(r + 4 * MERGE_FC), merge_lds(r + 4 * MERGE_FC + 4));
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// More windows over a tile than footprint slots: one class of one strip from global memory, the loop of ms_merge_argmax_kernel.
+__device__ __noinline__ float4 ms_strip_gather(const float* __restrict__ low0_c, const float* __restrict__ refined_c, size_t ref_stride,
+                                               const int* __restrict__ ref_index, const int2* __restrict__ boxes, int n_crops,
+                                               int crop_h, int crop_w, int lh, int lw, int rh, int rw, int H, int W, int xs, int y) {
+  const float up_h = static_cast<float>(lh) / H, up_w = static_cast<float>(lw) / W;
+  const float r_h = static_cast<float>(rh) / crop_h, r_w = static_cast<float>(rw) / crop_w;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, ctx[4] = {0.f, 0.f, 0.f, 0.f};
+  bool have_ctx = false;
+  for (int k = 0; k < n_crops; ++k) {
+    const int cy = y - __ldg(&boxes[k].x), cx0 = xs - __ldg(&boxes[k].y);
+    if (cy < 0 || cy >= crop_h || cx0 + 3 < 0 || cx0 >= crop_w) continue;
+    const int ri = __ldg(ref_index + k);
+    if (ri < 0 && !have_ctx) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ctx[j] = bilerp_eval(low0_c, bilerp_setup(y, xs + j, up_h, up_w, lh, lw));
+      have_ctx = true;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cx = cx0 + j;
+      if (cx < 0 || cx >= crop_w) continue;
+      const float v = ri >= 0 ? bilerp_eval(refined_c + ri * ref_stride, bilerp_setup(cy, cx, r_h, r_w, rh, rw)) : ctx[j];
+      a[j] = __fadd_rn(a[j], v);
+    }
+  }
+  return make_float4(a[0], a[1], a[2], a[3]);
+}
+
+template <int NC_MAX, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
+ms_merge_class_kernel(const float* __restrict__ low0, const float* __restrict__ refined, const int* __restrict__ ref_index,
+                      const int2* __restrict__ boxes, int n_crops, int nc, int crop_h, int crop_w, int lh, int lw, int rh, int rw,
+                      int H, int W, int lg0, int lgr, uint8_t* __restrict__ labels, float* __restrict__ logits_out) {
+  __shared__ float fp[(MERGE_MAXW + 1) * NC_MAX * MERGE_SLOT];   // slot 0: context footprint, 1..4: refined windows
+  const int tx0 = blockIdx.x * MERGE_TW, ty0 = blockIdx.y * MERGE_TH, b = blockIdx.z;
+  const int t = threadIdx.x, lane = t & 31;
+  const int xs = tx0 + ((t >> 5) * 2 + (lane >> 4)) * 4, y = ty0 + (lane & 15);   // warp = 2 strips x 16 rows
+  const bool in_img = xs < W && y < H;   // W % 4 == 0
+  const int S0 = 1 << lg0, Sr = 1 << lgr;
+  const float inv_s0 = 1.f / static_cast<float>(S0), inv_sr = 1.f / static_cast<float>(Sr);   // = lw / W, rw / crop_w (exact)
+  const uint32_t fp_addr = static_cast<uint32_t>(__cvta_generic_to_shared(fp));
+  auto src = [](int cpix, float inv_s) { float v = inv_s * (cpix + 0.5f) - 0.5f; return v < 0.f ? 0.f : v; };
+  // footprint of a source over output pixels [c_lo, c_hi] x [r_lo, r_hi] (source-local coordinates), staged with all loads in flight
+  auto stage = [&](int slot, const float* __restrict__ base, int plane, int ih, int iw, int r_lo, int r_hi, int c_lo, int c_hi, float inv_s,
+                   int& ly_lo, int& lx_lo) {
+    ly_lo = static_cast<int>(src(r_lo, inv_s));
+    lx_lo = static_cast<int>(src(c_lo, inv_s));
+    const int fr = static_cast<int>(src(r_hi, inv_s)) + 2 - ly_lo, fc = static_cast<int>(src(c_hi, inv_s)) + 2 - lx_lo;   // <= 6 x 18 for S >= 4
+    const int e = t & 127;
+    if (e < fr * fc) {   // two thread groups take the even / odd classes of one footprint element each
+      const int r = e / fc, col = e - r * fc;
+      const float* g = base + (min(ly_lo + r, ih - 1) * iw + min(lx_lo + col, iw - 1));
+      float* d = fp + slot * (NC_MAX * MERGE_SLOT) + r * MERGE_FC + col;
+#pragma unroll
+      for (int c = 0; c < NC_MAX; c += 2) {
+        const int cc = c + (t >> 7);
+        if (cc < nc) d[cc * MERGE_SLOT] = __ldg(g + cc * plane);
+      }
+    }
+  };
+  // this thread's strip in a source: c0 = source-local x of pixel 0, [0, limit) the valid range, (ly_lo, lx_lo) the footprint origin
+  auto strip = [&](int slot, int row, int c0, int limit, int lg, float inv_s, int ly_lo, int lx_lo, bool rowok, bool refined_w) {
+    MsStrip st;
+    const int S = 1 << lg;
+    const bool anyin = rowok && c0 + 3 >= 0 && c0 < limit;
+    const bool fast = anyin && c0 >= (S >> 1) && c0 + 3 < limit;
+    const float sy = src(row, inv_s);
+    const int y0 = static_cast<int>(sy);
+    const int t0 = c0 - (S >> 1);
+    st.off = fp_addr + 4u * static_cast<uint32_t>(slot * (NC_MAX * MERGE_SLOT) + (y0 - ly_lo) * MERGE_FC - lx_lo + (fast ? (t0 >> lg) : 0));
+    const int ph0 = t0 & (S - 1);
+    int inmask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) inmask |= (rowok && c0 + j >= 0 && c0 + j < limit) ? (16 << j) : 0;
+    st.meta = (fast ? min(S - ph0, 4) : 0) | inmask | (anyin ? 256 : 0) | (refined_w ? 512 : 0) | (anyin ? ((c0 + 8) << 16) : 0);
+    st.w1_0 = (static_cast<float>(ph0) + 0.5f) * inv_s;
+    st.h1 = sy - y0;
+    return st;
+  };
+
+  // context footprint: the tile itself in image coordinates
+  MsStrip cst;
+  {
+    int ly_lo, lx_lo;
+    stage(0, low0 + static_cast<size_t>(b) * nc * lh * lw, lh * lw, lh, lw, ty0, min(ty0 + MERGE_TH - 1, H - 1), tx0, min(tx0 + MERGE_TW - 1, W - 1),
+          inv_s0, ly_lo, lx_lo);
+    cst = strip(0, y, xs, W, lg0, inv_s0, ly_lo, lx_lo, in_img, false);
+  }
+  MsStrip wst[MERGE_MAXW];
+#pragma unroll
+  for (int s = 0; s < MERGE_MAXW; ++s) { wst[s].off = 0; wst[s].meta = 0; wst[s].w1_0 = 0.f; wst[s].h1 = 0.f; }
+  int count[4] = {0, 0, 0, 0};
+  int n_ov = 0;
+  for (int k0 = 0; k0 < n_crops; k0 += 32) {
+    int by_l = 0, bx_l = 0, ri_l = -1;
+    bool ov = false;
+    if (k0 + lane < n_crops) {
+      by_l = __ldg(&boxes[k0 + lane].x); bx_l = __ldg(&boxes[k0 + lane].y);
+      ri_l = __ldg(ref_index + static_cast<size_t>(b) * n_crops + k0 + lane);
+      ov = max(ty0 - by_l, 0) <= min(ty0 + MERGE_TH - 1 - by_l, crop_h - 1) && max(tx0 - bx_l, 0) <= min(tx0 + MERGE_TW - 1 - bx_l, crop_w - 1);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ov);
+    while (m) {   // overlapping windows in window order
+      const int kl = __ffs(m) - 1;
+      m &= m - 1;
+      const int by = __shfl_sync(0xffffffffu, by_l, kl), bx = __shfl_sync(0xffffffffu, bx_l, kl), ri = __shfl_sync(0xffffffffu, ri_l, kl);
+      const int cy = y - by, cx0 = xs - bx;
+      const bool rowok = in_img && cy >= 0 && cy < crop_h;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) count[j] += (rowok && cx0 + j >= 0 && cx0 + j < crop_w) ? 1 : 0;
+      if (n_ov < MERGE_MAXW) {
+        int ly_lo = 0, lx_lo = 0;
+        if (ri >= 0)
+          stage(1 + n_ov, refined + static_cast<size_t>(ri) * nc * rh * rw, rh * rw, rh, rw, max(ty0 - by, 0), min(ty0 + MERGE_TH - 1 - by, crop_h - 1),
+                max(tx0 - bx, 0), min(tx0 + MERGE_TW - 1 - bx, crop_w - 1), inv_sr, ly_lo, lx_lo);
+        const MsStrip st = strip(1 + n_ov, cy, cx0, crop_w, lgr, inv_sr, ly_lo, lx_lo, rowok, ri >= 0);
+#pragma unroll
+        for (int s = 0; s < MERGE_MAXW; ++s)
+          if (s == n_ov) wst[s] = st;
+      }
+      ++n_ov;
+    }
+  }
+  __syncthreads();
+  if (!in_img) return;
+
+  bool pow2 = true, need_ctx = false;
+  float inv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {   // count >= 1: the grid covers the image (count_mat assert in the reference)
+    pow2 = pow2 && count[j] > 0 && (count[j] & (count[j] - 1)) == 0;
+    inv[j] = __int_as_float((128 - __ffs(count[j])) << 23);   // 2^-k for count = 2^k
+  }
+#pragma unroll
+  for (int s = 0; s < MERGE_MAXW; ++s) need_ctx = need_ctx || ((wst[s].meta & 256) && !(wst[s].meta & 512));
+  const size_t plane_out = static_cast<size_t>(H) * W;
+  const size_t pix = static_cast<size_t>(y) * W + xs;
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int arg[4] = {0, 0, 0, 0};
+  for (int c = 0; c < nc; ++c) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n_ov <= MERGE_MAXW) {
+      const uint32_t coff = static_cast<uint32_t>(c) * (4u * MERGE_SLOT);
+      float ctx[4] = {0.f, 0.f, 0.f, 0.f};
+      if (need_ctx) {   // U(y, xs + j): the context value of the strip, evaluated once per class
+        const float4 r = (cst.meta & 7) ? ms_strip_eval(cst.off + coff, cst.meta & 7, cst.w1_0, inv_s0, cst.h1)
+                                        : ms_strip_border(cst.off + coff, xs, W, inv_s0, cst.h1);
+        ctx[0] = r.x; ctx[1] = r.y; ctx[2] = r.z; ctx[3] = r.w;
+      }
+#pragma unroll
+      for (int s = 0; s < MERGE_MAXW; ++s) {
+        const int meta = wst[s].meta;
+        if (!(meta & 256)) continue;
+        float v[4];
+        if (!(meta & 512)) {   // window skipped by the confidence gate: its logits are the context
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = ctx[j];
+        } else {
+          const float4 r = (meta & 7) ? ms_strip_eval(wst[s].off + coff, meta & 7, wst[s].w1_0, inv_sr, wst[s].h1)
+                                      : ms_strip_border(wst[s].off + coff, (meta >> 16) - 8, crop_w, inv_sr, wst[s].h1);
+          v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (meta & (16 << j)) acc[j] = __fadd_rn(acc[j], v[j]);
+      }
+    } else {   // more windows over this tile than footprint slots
+      const float4 r = ms_strip_gather(low0 + (static_cast<size_t>(b) * nc + c) * lh * lw, refined ? refined + static_cast<size_t>(c) * rh * rw : nullptr,
+                                       static_cast<size_t>(nc) * rh * rw, ref_index + static_cast<size_t>(b) * n_crops, boxes, n_crops, crop_h, crop_w,
+                                       lh, lw, rh, rw, H, W, xs, y);
+      acc[0] = r.x; acc[1] = r.y; acc[2] = r.z; acc[3] = r.w;
+    }
+    if (pow2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] *= inv[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = acc[j] / static_cast<float>(count[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c == 0 || acc[j] > best[j]) { best[j] = acc[j]; arg[j] = c; }   // strict >: the first maximum wins
+    if (logits_out)
+      *reinterpret_cast<float4*>(logits_out + (static_cast<size_t>(b) * nc + c) * plane_out + pix) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
   *reinterpret_cast<uint32_t*>(labels + static_cast<size_t>(b) * plane_out + pix) =
       static_cast<uint32_t>(arg[0]) | (static_cast<uint32_t>(arg[1]) << 8) | (static_cast<uint32_t>(arg[2]) << 16) | (static_cast<uint32_t>(arg[3]) << 24);
