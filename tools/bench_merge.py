@@ -1,6 +1,7 @@
 """A/B of the two tiled merge kernels on BASELINE config 2's tail (2 images of 1024x2048, 18 windows each, 19 classes):
 VFM_MERGE_MODE=1 = round-1 window-major tile kernel, default = class-major kernel. CUDA events, L2 flushed between launches.
-Prints one JSON line per case. Optional argument: comma-separated list of modes to run."""
+Prints one JSON line per case. Optional arguments: comma-separated VFM_MERGE_MODE values for the slide merge, then for the stage-1 merge
+of ms_inference ("none" skips that part)."""
 import json
 import os
 import sys
@@ -14,7 +15,8 @@ bx = torch.tensor(slide_boxes(1024, 2048, (512, 512), (341, 341)), dtype=torch.i
 low = torch.randn(36, 19, 128, 128, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 algo_bytes = low.numel() * 4 + 2 * 1024 * 2048   # low-res logits read once + uint8 labels written
-for mode in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("1", "2", "3", "0")):
+slide_modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["1", "2", "3", "0"]
+for mode in ([] if slide_modes == ["none"] else slide_modes):
     os.environ["VFM_MERGE_MODE"] = mode
     for want in (False, True):
         f = lambda: ops.slide_merge_argmax(low, bx, 2, (512, 512), (1024, 2048), want_logits=want)
@@ -33,7 +35,8 @@ for mode in (sys.argv[1].split(",") if len(sys.argv) > 1 else ("1", "2", "3", "0
 os.environ.pop("VFM_MERGE_MODE", None)
 
 # Stage-1 merge of ms_inference (BASELINE config 3): 2 images, coarse logits 128x256 (x8), 24 of 36 windows refined (32x32, x16)
-if len(sys.argv) <= 2 or sys.argv[2] != "noms":
+ms_modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["1", "3", "0"]
+if ms_modes != ["none"]:
     low0 = torch.randn(2, 19, 128, 256, device="cuda")
     g = torch.Generator().manual_seed(1)
     mask = torch.rand(2, 18, generator=g) < 0.67
@@ -41,8 +44,9 @@ if len(sys.argv) <= 2 or sys.argv[2] != "noms":
     ref_index[mask] = torch.arange(int(mask.sum()), dtype=torch.int32)
     refined = torch.randn(int(mask.sum()), 19, 32, 32, device="cuda")
     ri = ref_index.cuda()
-    for mode, name in (("1", "ms_merge_argmax_kernel (per-pixel gather)"), ("3", "ms_merge_class_kernel, CTAs per SM >= 3"),
-                       ("0", "ms_merge_class_kernel, CTAs per SM >= 2")):
+    names = {"1": "ms_merge_argmax_kernel (per-pixel gather)", "3": "ms_merge_class_kernel, CTAs per SM >= 3", "0": "ms_merge_class_kernel, CTAs per SM >= 2"}
+    for mode in ms_modes:
+        name = names[mode]
         os.environ["VFM_MERGE_MODE"] = mode
         f = lambda: ops.ms_merge_argmax(low0, refined, ri, bx, (512, 512), (1024, 2048))
         for _ in range(3):
