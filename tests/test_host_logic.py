@@ -469,3 +469,75 @@ def test_fold_layernorm_algebra():
     e_new = (got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()
     e_old = (old - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()
     assert e_new < 5e-3 and e_new < 1.5 * e_old + 1e-4, (float(e_new), float(e_old))
+
+
+def test_fused_backbone_driver_parameter_blocks_and_host_side_validation():
+    """vfm_eva_forward / vfm_sam_forward read host parameter blocks (VfmEvaParams / VfmSamParams). On the CPU: the packers fill them
+    from the reference-named state dict (pointers = the packed tensors, taps ascending, padded hidden width), the library's
+    workspace arithmetic agrees with the buffer list in its source, and the argument checks (null pointers, head_dim, workspace
+    size) answer before any CUDA call."""
+    import ctypes as C
+    import vfmseg_b200
+    from vfmseg_b200 import synthetic
+    from vfmseg_b200.eva_engine import PackedEva
+    from vfmseg_b200.sam_engine import PackedSam
+    lib = _C.load()
+    al = lambda n: (n + 255) // 256 * 256
+
+    # ---- EVA02 (tiny: 256 wide, 4 blocks, 4 x 4 patches, hidden 682 -> 688)
+    cfg = synthetic.tiny_eva_config()
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    model.load_state_dict(synthetic.synthetic_eva_state_dict(cfg, seed=0), strict=False)
+    pk = None
+    for m in model.modules():
+        if hasattr(m, "packed") and hasattr(m, "pt_hw_seq_len"):
+            pk = m.packed(torch.device("cpu"))
+    assert isinstance(pk, PackedEva)
+    p = pk._params
+    assert (p.embed_dim, p.depth, p.heads, p.hidden, p.hidden_pad, p.n_taps, p.grid) == (256, 4, 4, 682, 688, 4, 4)
+    assert list(p.tap_blocks)[:4] == [0, 1, 2, 3] and abs(p.ln_eps - 1e-5) < 1e-12
+    assert p.patch_w == pk.patch_w.data_ptr() and p.rope_cos == pk.rope_cos.data_ptr() and p.ones == pk.ones.data_ptr()
+    for blk, b in zip(pk._c_blocks, pk.blocks):
+        assert blk.qkv_w == b["qkv_w"].data_ptr() and blk.w12 == b["w12"].data_ptr() and blk.w3 == b["w3"].data_ptr()
+        assert blk.qkv_wf == b["qkv_f"][0].data_ptr() and blk.w12_cs == b["w12_f"][2].data_ptr()
+        assert b["w12"].shape == (2 * 688, 256) and b["w3"].shape == (256, 688)
+    n, P, Cc, Hp = 3, 16, 256, 688
+    M = n * (P + 1)
+    want = al(M * Cc * 4) + 2 * al(M * Cc * 2) + al(M * 3 * Cc * 2) + al(max(M * 2 * Hp * 2, n * P * 768 * 2)) + al(M * Hp * 2) + al(M * (Cc // 128 + 1) * 8)
+    assert lib.vfm_eva_workspace_bytes(C.byref(p), n) == want
+    one = C.c_void_p(8)      # a non-null pointer that is never dereferenced: every check below fails before a CUDA call
+    assert lib.vfm_eva_forward(None, one, 1, None, 64, 64, one, n, one, one, want, None) == -1
+    assert lib.vfm_eva_forward(C.byref(p), one, 1, None, 64, 64, one, n, one, one, want - 1, None) == -3
+    assert b"eva_forward: workspace" in lib.vfm_last_error()
+    p.heads = 3
+    assert lib.vfm_eva_forward(C.byref(p), one, 1, None, 64, 64, one, n, one, one, want, None) == -1
+    assert b"head_dim" in lib.vfm_last_error()
+    p.heads = 4
+
+    # ---- SAM ViT (tiny: 640 wide = 8 heads x 80, 16 x 16 tokens, 14 x 14 windows, global blocks 1 and 3)
+    cfg = synthetic.tiny_sam_config()
+    model = vfmseg_b200.MODELS.build(dict(cfg))
+    model.load_state_dict(synthetic.synthetic_sam_state_dict(cfg, seed=0), strict=False)
+    pk = None
+    for m in model.modules():
+        if hasattr(m, "packed") and hasattr(m, "global_attn_indexes"):
+            pk = m.packed(torch.device("cpu"))
+    assert isinstance(pk, PackedSam)
+    n = 2
+    p = pk._c_params(n)
+    assert (p.embed_dim, p.depth, p.heads, p.head_dim, p.hidden, p.n_taps, p.grid, p.use_rel_pos) == (640, 4, 8, 80, 2560, 4, 16, 1)
+    part, unpart, n_win = pk._window_maps(n, 16, 16, 14)
+    assert p.win_rows == n_win * 196 == n * 4 * 196 and p.part == part.data_ptr() and p.unpart == unpart.data_ptr()
+    assert p.win_buf == pk._window_buffer(n_win * 196, 640).data_ptr() and p.onehot and p.onehot_rows == 256
+    assert [blk.window for blk in pk._c_blocks] == [14, 0, 14, 0]
+    for blk, b in zip(pk._c_blocks, pk.blocks):
+        size = 16 if blk.window == 0 else 14
+        assert blk.qkv_n == b["qkv_w"].shape[0] == (3 * 640 + 2 * 8 * (2 * size - 1) + 31) // 32 * 32 and blk.qkv_w == b["qkv_w"].data_ptr()
+        assert blk.lin1_wf is None                       # 640 % 256 != 0: no LayerNorm folding at this width
+    M = n * 256
+    qkv_elems = max(M * pk._c_blocks[1].qkv_n, p.win_rows * pk._c_blocks[0].qkv_n)
+    want = al(M * 640 * 4) + 2 * al(M * 640 * 2) + al(p.win_rows * 640 * 2) + al(qkv_elems * 2) + al(max(M * 2560 * 2, M * 768 * 2)) + al(M * (640 // 128 + 1) * 8)
+    assert lib.vfm_sam_workspace_bytes(C.byref(p), n) == want
+    assert lib.vfm_sam_forward(C.byref(p), one, 1, None, 256, 256, one, n, one, None, want, None) == -1
+    assert lib.vfm_sam_forward(C.byref(p), one, 1, None, 256, 256, one, n, one, one, want - 1, None) == -3
+    assert b"sam_forward: workspace" in lib.vfm_last_error()
