@@ -167,7 +167,10 @@ int vfm_groupnorm_relu(const void* in, void* out, const float* gamma, const floa
  * [n_img*n_crops, nc, lh, lw]; boxes: device int[2*n_crops] = {y1, x1}; labels: uint8 [n_img,H,W];
  * logits_out: optional fp32 [n_img, nc, H, W].
  * Replaces mmseg predict_by_feat resize + slide_inference pad/add/count/divide
- * (Ms_VFM_encoder_decoder.py:453-461) + postprocess_result argmax. */
+ * (Ms_VFM_encoder_decoder.py:453-461) + postprocess_result argmax.
+ * Kernel choice (all bit-identical): exact x4 windows, W % 4 == 0, nc <= 19 and aligned outputs run the class-major tile
+ * kernel; other shapes a per-pixel gather. Environment VFM_MERGE_MODE=1 forces the round-1 window-major tile kernel (A/B
+ * runs); the same variable makes vfm_ms_merge_argmax use its per-pixel kernel. */
 int vfm_slide_merge_argmax(const float* lowres, const int* boxes, int n_crops, int nc, int crop_h,
                            int crop_w, int lh, int lw, int H, int W, int n_img, uint8_t* labels,
                            float* logits_out, void* stream);
